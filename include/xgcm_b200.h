@@ -1,0 +1,186 @@
+/*
+ * xgcm_b200.h — C-ABI of the B200-native grid-ufunc stencil engine.
+ *
+ * This is the drop-in boundary for xgcm's data-parallel hot path.  Every entry
+ * point replaces one numeric site of the reference (paths relative to the
+ * xgcm source tree, snapshot 052b033a):
+ *
+ *   xg_stencil2        <- xgcm/padding.py:575-616 (_pad_basic -> np.pad)
+ *                         + xgcm/gridops.py:23-24,76-77,123-126,172-175
+ *                           (diff_forward / interp_forward / pairwise min,max)
+ *                         + xgcm/grid.py:806-808,830-832,1576-1578
+ *                           (metric multiply before / divide after)
+ *   xg_cumscan         <- xgcm/grid.py:1306-1391 (metric, flip, cumsum, trim, pad)
+ *                         + xgcm/grid.py:1411-1414 (metric divide)
+ *   xg_wreduce         <- xgcm/grid.py:1598-1605 (integrate) and :1680-1685 (average)
+ *   xg_vinterp_linear  <- xgcm/transform.py:15-41,44-85 (_interp_1d_linear)
+ *   xg_pad             <- xgcm/padding.py:765-871 (pad) for callers that want the
+ *                         padded array itself (custom grid ufuncs)
+ *   xg_binary / xg_unary
+ *                      <- the xarray broadcast arithmetic around the hot path
+ *                         (xgcm/grid.py:808,832,1578,1599,1657)
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch / numpy / C++ types.
+ *   - every array is C-contiguous; `shape` has `ndim` entries; `axis` is the
+ *     operated dimension.  Internally any such array collapses to
+ *     (outer, n, inner); inner == 1 selects the innermost-axis kernels.
+ *   - "device" entry points take DEVICE pointers and a cudaStream_t (passed as
+ *     void*); launches are asynchronous; nothing is allocated.
+ *   - "*_host" entry points take HOST pointers; the library stages through the
+ *     device in slabs along the outermost dimension with copy/compute overlap.
+ *   - metric operands broadcast against the field: `*_strides` gives the
+ *     metric's ELEMENT stride for every dim of the field (0 = broadcast).
+ *     pre_* is laid out against the INPUT shape, post_* against the OUTPUT shape.
+ *   - returns 0 on success, a negative xg_status otherwise; xg_last_error()
+ *     returns a thread-local message.  CUDA errors never abort the process.
+ *   - re-entrant: no global mutable state apart from an init-once device
+ *     property cache.
+ */
+#ifndef XGCM_B200_H
+#define XGCM_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define XG_API __attribute__((visibility("default")))
+#else
+#define XG_API
+#endif
+
+#define XG_VERSION 100 /* 0.1.0 */
+#define XG_MAX_NDIM 8
+
+typedef enum {
+  XG_OK = 0,
+  XG_EINVAL = -1,   /* -> ValueError   */
+  XG_ENOTIMPL = -2, /* -> NotImplementedError */
+  XG_ECUDA = -3,    /* -> RuntimeError */
+  XG_ENCCL = -4     /* -> RuntimeError */
+} xg_status;
+
+typedef enum { XG_F32 = 0, XG_F64 = 1 } xg_dtype;
+
+/* gridops.py:23-24 / :76-77 / :123-126 / :172-175 */
+typedef enum { XG_OP_DIFF = 0, XG_OP_INTERP = 1, XG_OP_MIN = 2, XG_OP_MAX = 3 } xg_op;
+
+/* padding.py:15-19 ("periodic"->wrap, "fill"->constant, "extend"->edge).
+ * XG_BC_NONE with a non-zero halo width is an error (padding.py:601-608).
+ * XG_BC_EXTRAPOLATE (halo = 2*edge - next) has no counterpart in the
+ * reference snapshot: opt-in, parity unpinned. */
+typedef enum {
+  XG_BC_NONE = 0,
+  XG_BC_PERIODIC = 1,
+  XG_BC_FILL = 2,
+  XG_BC_EXTEND = 3,
+  XG_BC_EXTRAPOLATE = 4
+} xg_bc;
+
+/* grid.py:1326-1383 trim table of cumsum */
+typedef enum { XG_TRIM_NONE = 0, XG_TRIM_DROP_LAST = 1, XG_TRIM_DROP_FIRST = 2 } xg_trim;
+
+typedef enum { XG_REDUCE_SUM = 0, XG_REDUCE_MEAN = 1 } xg_reduce_mode;
+
+typedef enum {
+  XG_BIN_MUL = 0, XG_BIN_DIV = 1, XG_BIN_ADD = 2, XG_BIN_SUB = 3
+} xg_binop;
+
+XG_API int xg_version(void);
+XG_API const char* xg_last_error(void);
+
+/* Device properties the host side needs for planning (SM count, L2 bytes). */
+XG_API int xg_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t* hbm_bytes);
+
+/*
+ * Fused halo-pad + 2-point stencil + optional metric multiply/divide along one
+ * axis.  out[..., j, ...] = OP(P[j], P[j+1]) / post, where P is the array
+ * (in * pre) padded by `lo` cells below and `hi` cells above (lo, hi in {0,1})
+ * according to `bc`.  Output length along axis = n + lo + hi - 1.
+ *
+ * halo_lo / halo_hi: optional device planes of shape (outer, inner) that supply
+ * the halo instead of `bc` (used when the operated axis is sharded across GPUs,
+ * cf. grid_ufunc.py:1057-1133 map_overlap); values are taken as-is (already
+ * metric-weighted).
+ */
+XG_API int xg_stencil2(int op, int dtype, const void* in, void* out, int ndim,
+                const int64_t* shape, int axis, int lo, int hi, int bc,
+                double fill_value, const void* pre_metric,
+                const int64_t* pre_strides, const void* post_metric,
+                const int64_t* post_strides, const void* halo_lo,
+                const void* halo_hi, void* stream);
+
+/*
+ * Cumulative sum along one axis with xgcm's position-shift bookkeeping:
+ * c = cumsum(in * pre) (from the high end when reverse), then trim, then pad
+ * (pad_lo, pad_hi in {0,1}) with `bc` applied to the cumsum'd data, then / post.
+ * skipna != 0 treats NaN as 0 (xarray's default for float data).
+ * Summation order is strictly sequential along the axis (numpy's order).
+ */
+XG_API int xg_cumscan(int dtype, const void* in, void* out, int ndim,
+               const int64_t* shape, int axis, int reverse, int trim,
+               int pad_lo, int pad_hi, int bc, double fill_value,
+               const void* pre_metric, const int64_t* pre_strides,
+               const void* post_metric, const int64_t* post_strides,
+               int skipna, void* stream);
+
+/*
+ * Weighted reduction along one axis: out = sum_j in[j] * w[j]   (XG_REDUCE_SUM)
+ * or  sum_j in*w / sum_j w over non-NaN in  (XG_REDUCE_MEAN, needs weight).
+ * weight may be NULL (plain sum / mean).  Output shape = shape without `axis`.
+ */
+XG_API int xg_wreduce(int dtype, const void* in, const void* weight,
+               const int64_t* w_strides, void* out, int ndim,
+               const int64_t* shape, int axis, int mode, int skipna,
+               void* stream);
+
+/*
+ * Linear interpolation of phi (defined on theta) onto target levels, per
+ * column along `axis`; output dimension is appended LAST (transform.py:233-249).
+ * phi: `shape`; theta: broadcast against phi via theta_strides (a shared 1-D
+ * coordinate has stride 1 on `axis` and 0 elsewhere); target: m levels.
+ * out: shape-without-axis + (m,).  fp64 arithmetic, rounded once.
+ */
+XG_API int xg_vinterp_linear(int dtype, const void* phi, const void* theta,
+                      const int64_t* theta_strides, const void* target,
+                      int64_t m, void* out, int ndim, const int64_t* shape,
+                      int axis, int mask_edges, int bypass_checks,
+                      int logarithmic, void* stream);
+
+/* The padded array itself (padding.py:765-871), one axis per call. */
+XG_API int xg_pad(int dtype, const void* in, void* out, int ndim,
+           const int64_t* shape, int axis, int lo, int hi, int bc,
+           double fill_value, void* stream);
+
+/* out = a (op) b with b broadcast against a's shape via b_strides. */
+XG_API int xg_binary(int binop, int dtype, const void* a, const void* b,
+              const int64_t* b_strides, void* out, int ndim,
+              const int64_t* shape, void* stream);
+
+/* Deterministic synthetic field: out[i] = U(0,1) keyed by (seed, offset+i);
+ * identical bits on host (xg_fill_uniform_host) and device. */
+XG_API int xg_fill_uniform(int dtype, void* out, int64_t count, uint64_t seed,
+                    uint64_t offset, void* stream);
+XG_API int xg_fill_uniform_host(int dtype, void* out, int64_t count, uint64_t seed,
+                         uint64_t offset);
+
+/*
+ * Host-buffer variant of xg_stencil2: same semantics, HOST pointers.  The field
+ * is streamed through the device in slabs of the outermost non-operated
+ * dimension with H2D / kernel / D2H overlapped on three streams.  Host buffers
+ * should be page-locked for full PCIe rate (pageable memory is staged).
+ * `device` selects the GPU.  Synchronous: returns when `out` is complete.
+ */
+XG_API int xg_stencil2_host(int op, int dtype, const void* in, void* out, int ndim,
+                     const int64_t* shape, int axis, int lo, int hi, int bc,
+                     double fill_value, const void* pre_metric,
+                     const int64_t* pre_strides, const void* post_metric,
+                     const int64_t* post_strides, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XGCM_B200_H */

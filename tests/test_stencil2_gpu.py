@@ -1,0 +1,136 @@
+"""Parity of the fused stencil kernel (through the C-ABI) against the oracle: bit-exact."""
+
+import itertools
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stencil as oracle
+
+pytestmark = pytest.mark.gpu
+
+SHIFTS = sorted(set(oracle.PADDING_WIDTH.values()))  # (0,0) (0,1) (1,0) (1,1)
+OPS = ["diff", "interp", "min", "max"]
+BCS = [("periodic", 0.0), ("fill", 0.0), ("fill", 1.5), ("fill", float("nan")), ("extend", 0.0)]
+
+
+def _field(shape, dtype, seed=0, nan_frac=0.0):
+    rng = np.random.default_rng(seed)
+    a = rng.random(shape).astype(dtype)
+    if nan_frac:
+        a[rng.random(shape) < nan_frac] = np.nan
+    return a
+
+
+def _run(a, axis, op, lo, hi, bc, fill, pre=None, post=None):
+    from xgcm_b200 import ops
+
+    dev = torch.device("cuda:0")
+    x = torch.from_numpy(a).to(dev)
+    p = None if pre is None else torch.from_numpy(np.ascontiguousarray(pre)).to(dev)
+    q = None if post is None else torch.from_numpy(np.ascontiguousarray(post)).to(dev)
+    out = ops.stencil2(x, axis, op, lo, hi, bc, fill, pre=p, post=q)
+    torch.cuda.synchronize()
+    return out.cpu().numpy()
+
+
+def _check(a, axis, op, lo, hi, bc, fill, pre=None, post=None):
+    if a.shape[axis] + lo + hi - 1 <= 0:
+        return
+    want = oracle.stencil2(op, a, axis, lo, hi, bc if (lo or hi) else None, fill, pre, post)
+    got = _run(a, axis, op, lo, hi, bc, fill, pre, post)
+    assert got.dtype == want.dtype
+    assert got.shape == want.shape
+    np.testing.assert_array_equal(got, want)  # NaN == NaN positions, bit-exact values
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("op", OPS)
+def test_config2_all_axes_shifts_bcs(dtype, op):
+    """MITgcm-like (50, 240, 360) field, every axis x shift x boundary (BASELINE configs[1])."""
+    a = _field((50, 240, 360), dtype, seed=1)
+    for axis, (lo, hi), (bc, fill) in itertools.product(range(3), SHIFTS, BCS):
+        _check(a, axis, op, lo, hi, bc, fill)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize(
+    "shape",
+    [(1,), (2,), (5,), (127,), (128,), (129,), (4097,), (1000,), (3, 5), (7, 13, 5), (2, 3, 4, 6),
+     (5, 1, 7), (1, 9), (9, 1), (3, 130), (2, 3, 256), (2, 3, 258), (4, 1026)],
+)
+def test_ragged_shapes(dtype, shape):
+    a = _field(shape, dtype, seed=2, nan_frac=0.05)
+    for axis in range(len(shape)):
+        for op, (lo, hi), (bc, fill) in itertools.product(OPS, SHIFTS, BCS):
+            _check(a, axis, op, lo, hi, bc, fill)
+
+
+def test_config1_periodic_1d_fp64():
+    """BASELINE configs[0]: 1e6 fp64 cells, periodic, center->left diff and interp."""
+    a = _field((1_000_000,), np.float64, seed=3)
+    for op in ("diff", "interp"):
+        _check(a, 0, op, 1, 0, "periodic", 0.0)
+        _check(a, 0, op, 0, 1, "periodic", 0.0)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_metric_weighting_bit_exact(dtype):
+    """op(a*m)/m_new must round exactly like the reference's three separate passes
+    (xgcm/test/test_metrics_ops.py:35-95 uses .equals)."""
+    rng = np.random.default_rng(4)
+    shape = (6, 20, 36)
+    a = _field(shape, dtype, seed=5)
+    full = (1.0 + rng.random(shape)).astype(dtype)
+    dx2 = (1.0 + rng.random((1,) + shape[1:])).astype(dtype)  # (Y, X) metric
+    dz1 = (1.0 + rng.random((shape[0], 1, 1))).astype(dtype)  # (Z,) metric
+    dy1 = (1.0 + rng.random((1, shape[1], 1))).astype(dtype)  # (Y,) metric
+    dx1 = (1.0 + rng.random((1, 1, shape[2]))).astype(dtype)  # (X,) metric
+    for axis in range(3):
+        for (lo, hi), (bc, fill) in itertools.product(SHIFTS, BCS[:3] + BCS[4:]):
+            n_out = shape[axis] + lo + hi - 1
+            if n_out <= 0:
+                continue
+            oshape = list(shape)
+            oshape[axis] = n_out
+            for pre in (None, full, dx2, dz1, dy1, dx1):
+                for post_kind in (None, "full", "dx2", "dz1", "dy1", "dx1"):
+                    if pre is None and post_kind is None:
+                        continue
+                    post = None
+                    if post_kind is not None:
+                        src = {"full": full, "dx2": dx2, "dz1": dz1, "dy1": dy1, "dx1": dx1}[post_kind]
+                        pshape = [oshape[d] if src.shape[d] != 1 else 1 for d in range(3)]
+                        post = (1.0 + np.random.default_rng(7).random(pshape)).astype(dtype)
+                    _check(a, axis, "diff", lo, hi, bc, fill, pre, post)
+                    _check(a, axis, "interp", lo, hi, bc, fill, pre, post)
+
+
+def test_metric_4d_outer_broadcast():
+    """(T, Z, Y, X) field with dx(Y, X) along X and dz(Z) along Y: multi-group outer index."""
+    shape = (3, 4, 10, 16)
+    a = _field(shape, np.float32, seed=8)
+    rng = np.random.default_rng(9)
+    dx = (1 + rng.random((1, 1, 10, 16))).astype(np.float32)
+    dz = (1 + rng.random((1, 4, 1, 1))).astype(np.float32)
+    dt = (1 + rng.random((3, 1, 1, 1))).astype(np.float32)
+    for axis in range(4):
+        for pre, post in ((dx, None), (None, dz), (dz, dx), (dt, dz), (dx, dt)):
+            lo, hi = 1, 0
+            _check(a, axis, "diff", lo, hi, "periodic", 0.0, pre, post)
+            _check(a, axis, "interp", 0, 1, "extend", 0.0, pre, post)
+
+
+def test_errors():
+    from xgcm_b200 import ops
+
+    x = torch.zeros((4, 4), device="cuda")
+    with pytest.raises(ValueError):
+        ops.stencil2(x, 0, "diff", 1, 0, None)  # padding.py:601-608
+    with pytest.raises(ValueError):
+        ops.stencil2(x, 0, "diff", 1, 0, "bogus")
+    with pytest.raises(RuntimeError):
+        ops.stencil2(torch.zeros((4, 4)), 0, "diff", 1, 0, "fill")  # no CPU fallback
+    with pytest.raises(TypeError):
+        ops.stencil2(x.to(torch.int32), 0, "diff", 1, 0, "fill")
