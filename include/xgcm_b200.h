@@ -180,6 +180,9 @@ XG_API int xg_stencil2_host(int op, int dtype, const void* in, void* out, int nd
                      const int64_t* pre_strides, const void* post_metric,
                      const int64_t* post_strides, int device);
 
+/* Free the cached device slabs / streams of the *_host entry points. */
+XG_API int xg_host_workspace_release(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -63,6 +63,7 @@ SIGNATURES = {
         [C.c_int, C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int,
          C.c_double, _vp, _i64p, _vp, _i64p, C.c_int],
     ),
+    "xg_host_workspace_release": (C.c_int, []),
 }
 
 _lib: Optional[C.CDLL] = None

@@ -200,4 +200,4 @@ __device__ __forceinline__ T xg_apply_op(T a, T b) {
   }
 }
 
-static inline int64_t xg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+__host__ __device__ static inline int64_t xg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

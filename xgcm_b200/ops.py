@@ -128,3 +128,251 @@ def stencil2(
         )
     _capi.check(rc)
     return out
+
+
+def pad(x: torch.Tensor, axis: int, lo: int, hi: int, padding: Optional[str],
+        fill_value: float = 0.0) -> torch.Tensor:
+    """The padded array itself (padding.py:575-616), one axis."""
+    lib = _capi.load()
+    _require_cuda(x, "field")
+    if padding not in _capi.BCS:
+        raise ValueError(
+            f"padding must be one of ['periodic', 'fill', 'extend'] or None, but got {padding}"
+        )
+    x = x.contiguous()
+    axis = _norm_axis(axis, x.dim())
+    shape = list(x.shape)
+    out_shape = list(shape)
+    out_shape[axis] = shape[axis] + lo + hi
+    out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+    with torch.cuda.device(x.device):
+        rc = lib.xg_pad(_dtype_code(x), x.data_ptr(), out.data_ptr(), x.dim(),
+                        _capi.i64_array(shape), axis, lo, hi, _capi.BCS[padding],
+                        float(fill_value), _stream_ptr(x))
+    _capi.check(rc)
+    return out
+
+
+def binary(opname: str, a: torch.Tensor, b: torch.Tensor, shape: Optional[Sequence[int]] = None) -> torch.Tensor:
+    """``a (op) b`` with numpy-style broadcasting, on the device (xg_binary).
+
+    The kernel broadcasts ``b`` against ``a``; when ``a`` itself has to be
+    broadcast it is expanded first (only happens for metric x metric products).
+    """
+    lib = _capi.load()
+    _require_cuda(a, "a")
+    _require_cuda(b, "b")
+    if opname not in _capi.BINOPS:
+        raise ValueError(f"unknown binary op {opname!r}")
+    dt = torch.promote_types(a.dtype, b.dtype)
+    if dt not in (torch.float32, torch.float64):
+        dt = torch.float64
+    a = a.to(dt)
+    b = b.to(dt)
+    if shape is None:
+        shape = torch.broadcast_shapes(a.shape, b.shape)
+    shape = tuple(int(s) for s in shape)
+    if len(shape) == 0:
+        a = a.reshape(1)
+        b = b.reshape(1)
+        shape = (1,)
+        scalar = True
+    else:
+        scalar = False
+    a_full = a.expand(shape).contiguous()
+    keep, b_ptr, b_st = _operand(b, shape, a_full, "b")
+    out = torch.empty(shape, dtype=dt, device=a.device)
+    if out.numel():
+        with torch.cuda.device(a.device):
+            rc = lib.xg_binary(_capi.BINOPS[opname], _dtype_code(a_full), a_full.data_ptr(), b_ptr,
+                               b_st, out.data_ptr(), len(shape), _capi.i64_array(shape),
+                               _stream_ptr(a_full))
+        _capi.check(rc)
+    return out.reshape(()) if scalar else out
+
+
+def cumscan(
+    x: torch.Tensor,
+    axis: int,
+    reverse: bool = False,
+    trim: str = "none",
+    pad_lo: int = 0,
+    pad_hi: int = 0,
+    padding: Optional[str] = None,
+    fill_value: float = 0.0,
+    pre: Optional[torch.Tensor] = None,
+    post: Optional[torch.Tensor] = None,
+    skipna: bool = True,
+) -> torch.Tensor:
+    """Cumulative sum with xgcm's trim / pad table fused (grid.py:1306-1414)."""
+    lib = _capi.load()
+    _require_cuda(x, "field")
+    if padding not in _capi.BCS:
+        raise ValueError(
+            f"padding must be one of ['periodic', 'fill', 'extend'] or None, but got {padding}"
+        )
+    x = x.contiguous()
+    axis = _norm_axis(axis, x.dim())
+    shape = list(x.shape)
+    kept = shape[axis] - (0 if trim == "none" else 1)
+    if kept < 0:
+        raise ValueError("operated axis too short to trim")
+    out_shape = list(shape)
+    out_shape[axis] = kept + pad_lo + pad_hi
+    out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+    keep_pre, pre_ptr, pre_st = _operand(pre, shape, x, "pre metric")
+    keep_post, post_ptr, post_st = _operand(post, out_shape, x, "post metric")
+    with torch.cuda.device(x.device):
+        rc = lib.xg_cumscan(
+            _dtype_code(x), x.data_ptr(), out.data_ptr(), x.dim(), _capi.i64_array(shape), axis,
+            int(bool(reverse)), _capi.TRIMS[trim], pad_lo, pad_hi, _capi.BCS[padding],
+            float(fill_value), pre_ptr, pre_st, post_ptr, post_st, int(bool(skipna)),
+            _stream_ptr(x),
+        )
+    _capi.check(rc)
+    return out
+
+
+def wreduce(x: torch.Tensor, axis: int, weight: Optional[torch.Tensor] = None, mode: str = "sum",
+            skipna: bool = True) -> torch.Tensor:
+    """Weighted sum / mean along ``axis`` (grid.py:1598-1605, :1680-1685)."""
+    lib = _capi.load()
+    _require_cuda(x, "field")
+    x = x.contiguous()
+    axis = _norm_axis(axis, x.dim())
+    shape = list(x.shape)
+    out_shape = [s for d, s in enumerate(shape) if d != axis]
+    out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+    keep, w_ptr, w_st = _operand(weight, shape, x, "weight")
+    if out.numel():
+        with torch.cuda.device(x.device):
+            rc = lib.xg_wreduce(_dtype_code(x), x.data_ptr(), w_ptr, w_st, out.data_ptr(), x.dim(),
+                                _capi.i64_array(shape), axis, _capi.REDUCE[mode],
+                                int(bool(skipna)), _stream_ptr(x))
+        _capi.check(rc)
+    return out
+
+
+def vinterp_linear(phi: torch.Tensor, theta: torch.Tensor, target: torch.Tensor, axis: int,
+                   mask_edges: bool = False, bypass_checks: bool = False,
+                   logarithmic: bool = False) -> torch.Tensor:
+    """Per-column linear interpolation onto ``target`` levels; new dim LAST
+    (transform.py:15-85).  ``theta`` broadcasts against ``phi``."""
+    lib = _capi.load()
+    _require_cuda(phi, "phi")
+    _require_cuda(theta, "theta")
+    _require_cuda(target, "target")
+    # numba gufunc loop resolution (transform.py:15-22): float32 only if all are
+    if not (phi.dtype == theta.dtype == target.dtype == torch.float32):
+        phi, theta, target = phi.to(torch.float64), theta.to(torch.float64), target.to(torch.float64)
+    phi = phi.contiguous()
+    target = target.contiguous()
+    if target.dim() != 1:
+        raise ValueError("target levels must be 1-D")
+    axis = _norm_axis(axis, phi.dim())
+    shape = list(phi.shape)
+    keep, th_ptr, th_st = _operand(theta, shape, phi, "theta")
+    out_shape = [s for d, s in enumerate(shape) if d != axis] + [int(target.numel())]
+    out = torch.empty(out_shape, dtype=phi.dtype, device=phi.device)
+    if out.numel():
+        with torch.cuda.device(phi.device):
+            rc = lib.xg_vinterp_linear(
+                _dtype_code(phi), phi.data_ptr(), th_ptr, th_st, target.data_ptr(),
+                int(target.numel()), out.data_ptr(), phi.dim(), _capi.i64_array(shape), axis,
+                int(bool(mask_edges)), int(bool(bypass_checks)), int(bool(logarithmic)),
+                _stream_ptr(phi),
+            )
+        _capi.check(rc)
+    return out
+
+
+def fill_uniform(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
+    """Deterministic U(0,1) synthetic field keyed by (seed, offset + flat index)."""
+    lib = _capi.load()
+    _require_cuda(out, "out")
+    if not out.is_contiguous():
+        raise ValueError("out must be contiguous")
+    with torch.cuda.device(out.device):
+        rc = lib.xg_fill_uniform(_dtype_code(out), out.data_ptr(), out.numel(), int(seed),
+                                 int(offset), _stream_ptr(out))
+    _capi.check(rc)
+    return out
+
+
+def fill_uniform_host(out: np.ndarray, seed: int, offset: int = 0) -> np.ndarray:
+    """Host twin of :func:`fill_uniform` (same bits)."""
+    lib = _capi.load()
+    if not out.flags.c_contiguous:
+        raise ValueError("out must be C-contiguous")
+    rc = lib.xg_fill_uniform_host(_capi.dtype_code(out.dtype), out.ctypes.data, out.size,
+                                  int(seed), int(offset))
+    _capi.check(rc)
+    return out
+
+
+def _host_operand(m: Optional[np.ndarray], shape: Sequence[int], dtype, what: str):
+    if m is None:
+        return None, None, None
+    m = np.ascontiguousarray(m, dtype=dtype)
+    try:
+        mb = np.broadcast_to(m, tuple(shape))
+    except ValueError as err:
+        raise ValueError(f"{what} of shape {m.shape} does not broadcast to {tuple(shape)}") from err
+    es = m.dtype.itemsize
+    strides = [0 if s == 1 else st // es for s, st in zip(shape, mb.strides)]
+    return m, m.ctypes.data, _capi.i64_array(strides)
+
+
+def pinned_empty(shape, dtype=np.float32) -> np.ndarray:
+    """A page-locked numpy array (torch's caching host allocator owns the memory)."""
+    tdt = {np.dtype("float32"): torch.float32, np.dtype("float64"): torch.float64}[np.dtype(dtype)]
+    t = torch.empty(tuple(int(s) for s in shape), dtype=tdt, pin_memory=True)
+    return t.numpy()
+
+
+def stencil2_host(
+    x: np.ndarray,
+    axis: int,
+    op: str,
+    lo: int,
+    hi: int,
+    padding: Optional[str],
+    fill_value: float = 0.0,
+    pre: Optional[np.ndarray] = None,
+    post: Optional[np.ndarray] = None,
+    out: Optional[np.ndarray] = None,
+    device: Optional[int] = None,
+) -> np.ndarray:
+    """Host-buffer twin of :func:`stencil2`: slabs stream H2D -> kernel -> D2H on three
+    streams inside ``xg_stencil2_host``.  Page-locked buffers get the full PCIe rate."""
+    lib = _capi.load()
+    if not isinstance(x, np.ndarray):
+        raise TypeError("stencil2_host takes numpy arrays")
+    if not torch.cuda.is_available():
+        raise RuntimeError("xgcm_b200 needs a CUDA device: the stencil engine has no CPU fallback")
+    if op not in _capi.OPS:
+        raise ValueError(f"unknown op {op!r}")
+    if padding not in _capi.BCS:
+        raise ValueError(
+            f"padding must be one of ['periodic', 'fill', 'extend'] or None, but got {padding}"
+        )
+    if not x.flags.c_contiguous:
+        x = np.ascontiguousarray(x)
+    axis = _norm_axis(axis, x.ndim)
+    shape = list(x.shape)
+    out_shape = list(shape)
+    out_shape[axis] = shape[axis] + lo + hi - 1
+    if out is None:
+        out = pinned_empty(out_shape, x.dtype)
+    elif list(out.shape) != out_shape or out.dtype != x.dtype or not out.flags.c_contiguous:
+        raise ValueError("out has wrong shape/dtype/layout")
+    kp, pre_ptr, pre_st = _host_operand(pre, shape, x.dtype, "pre metric")
+    kq, post_ptr, post_st = _host_operand(post, out_shape, x.dtype, "post metric")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    rc = lib.xg_stencil2_host(
+        _capi.OPS[op], _capi.dtype_code(x.dtype), x.ctypes.data, out.ctypes.data, x.ndim,
+        _capi.i64_array(shape), axis, lo, hi, _capi.BCS[padding], float(fill_value),
+        pre_ptr, pre_st, post_ptr, post_st, dev,
+    )
+    _capi.check(rc)
+    return out
