@@ -185,7 +185,9 @@ def _interp_column(phi, theta, target, mask_edges, bypass_checks):
     """transform.py:23-41 for one column; np.interp works in float64 like numba's."""
     if not bypass_checks:
         t = theta[~np.isnan(theta)]
-        if t[-1] < t[0]:
+        # an all-NaN column indexes an empty array in the reference (numba reads out of
+        # bounds: undefined); the restatement leaves such a column unflipped
+        if t.size and t[-1] < t[0]:
             theta = theta[::-1]
             phi = phi[::-1]
     out = np.interp(target, theta, phi)

@@ -1,0 +1,83 @@
+"""CPU stand-in for the CUDA kernels, for HOST-LOGIC tests only.
+
+On a machine without a GPU the Grid façade cannot compute anything (by design there is no CPU
+path in the product).  To still exercise the Python host logic here — kwarg precedence, metric
+selection, dims / coords bookkeeping, error behaviour — this fixture swaps ``xgcm_b200.ops`` for
+oracle-backed functions operating on CPU torch tensors.  It lives under tests/, is never
+imported by the package, and is not used on the GPU box, where the same test bodies run against
+the real kernels (tests/test_grid_gpu.py, tests/test_transform_gpu.py).
+"""
+
+import numpy as np
+import torch
+
+from oracle import stencil as oracle
+
+
+def _np(t):
+    if t is None:
+        return None
+    if isinstance(t, torch.Tensor):
+        return t.detach().cpu().numpy()
+    return np.asarray(t)
+
+
+def _t(a):
+    return torch.from_numpy(np.array(a, copy=True, order="C"))
+
+
+def install(monkeypatch):
+    from xgcm_b200 import device, ops
+
+    cpu = torch.device("cpu")
+    monkeypatch.setattr(device, "default_device", lambda: cpu)
+
+    def as_device_tensor(data, dev=None):
+        if isinstance(data, torch.Tensor):
+            t = data if data.dtype in (torch.float32, torch.float64) else data.to(torch.float64)
+            return t.contiguous(), False
+        arr = np.asarray(data)
+        if arr.dtype not in (np.float32, np.float64):
+            arr = arr.astype(np.float64)
+        return _t(arr), True
+
+    monkeypatch.setattr(device, "as_device_tensor", as_device_tensor)
+    monkeypatch.setattr(device, "result_like", lambda t, was_host: t.numpy() if was_host else t)
+
+    def stencil2(x, axis, op, lo, hi, padding, fill_value=0.0, pre=None, post=None, halo_lo=None,
+                 halo_hi=None, out=None):
+        if (lo or hi) and padding is None:
+            raise ValueError("no boundary condition was specified")
+        r = oracle.stencil2(op, _np(x), axis, lo, hi, padding if (lo or hi) else None, fill_value,
+                            _np(pre), _np(post))
+        return _t(r.astype(_np(x).dtype))
+
+    def stencil2_host(x, axis, op, lo, hi, padding, fill_value=0.0, pre=None, post=None, out=None,
+                      device=None):
+        return stencil2(x, axis, op, lo, hi, padding, fill_value, pre, post).numpy()
+
+    def pad(x, axis, lo, hi, padding, fill_value=0.0):
+        return _t(oracle.pad_axis(_np(x), axis, lo, hi, padding, fill_value))
+
+    def binary(opname, a, b, shape=None):
+        fn = {"mul": np.multiply, "div": np.true_divide, "add": np.add, "sub": np.subtract}[opname]
+        return _t(np.asarray(fn(_np(a), _np(b))))
+
+    def cumscan(x, axis, reverse=False, trim="none", pad_lo=0, pad_hi=0, padding=None,
+                fill_value=0.0, pre=None, post=None, skipna=True):
+        r = oracle.cumscan(_np(x), axis, reverse, trim, pad_lo, pad_hi,
+                           padding if (pad_lo or pad_hi) else None, fill_value, _np(pre), _np(post), skipna)
+        return _t(r)
+
+    def wreduce(x, axis, weight=None, mode="sum", skipna=True):
+        return _t(np.asarray(oracle.wreduce(_np(x), _np(weight), axis, mode, skipna)))
+
+    def vinterp_linear(phi, theta, target, axis, mask_edges=False, bypass_checks=False,
+                       logarithmic=False):
+        p = _np(phi)
+        th = np.broadcast_to(_np(theta), p.shape)
+        return _t(oracle.vinterp_linear(p, th, _np(target), axis, mask_edges, bypass_checks, logarithmic))
+
+    for name, fn in dict(stencil2=stencil2, stencil2_host=stencil2_host, pad=pad, binary=binary,
+                         cumscan=cumscan, wreduce=wreduce, vinterp_linear=vinterp_linear).items():
+        monkeypatch.setattr(ops, name, fn)

@@ -1,0 +1,131 @@
+"""Grid.transform (linear / log) against the reference's golden `cases` and the oracle."""
+
+import json
+import os
+
+import numpy as np
+import pytest
+
+import xgcm_b200 as xg
+from oracle import stencil as oracle
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def _arr(v):
+    return np.array([np.nan if x is None else x for x in v])
+
+
+def _cases():
+    cases = json.load(open(os.path.join(GOLDEN, "transform_cases.json")))
+    return {k: v for k, v in cases.items() if "multidim_target" not in k}
+
+
+@pytest.mark.parametrize("name", sorted(_cases()))
+def test_reference_transform_cases(name):
+    """xgcm/test/test_transform.py:41-683 + :951-1069 (high-level Grid.transform)."""
+    c = _cases()[name]
+    sdim, scoord = c["source_coord"]
+    data_vars = {c["source_data"][0]: ((sdim,), _arr(c["source_data"][1]))}
+    if "source_additional_data" in c:
+        data_vars[c["source_additional_data"][0]] = ((c["source_additional_data_coord"][0],), _arr(c["source_additional_data"][1]))
+    coords = {sdim: _arr(scoord)}
+    if "source_bounds_coord" in c:
+        coords[c["source_bounds_coord"][0]] = _arr(c["source_bounds_coord"][1])
+    ds = xg.Dataset(data_vars=data_vars, coords=coords)
+    tdim, tvals = c["target_coord"]
+    target = xg.DataArray(_arr(c["target_data"][1]), dims=(tdim,), coords={tdim: _arr(tvals)}, name=c["target_data"][0])
+    kw = dict(c["transform_kwargs"])
+    if kw.get("target_data"):
+        kw["target_data"] = ds[kw["target_data"]]
+    grid = xg.Grid(ds, **c["grid_kwargs"])
+    got = grid.transform(ds[c["source_data"][0]], "Z", target, **kw)
+    want = _arr(c["expected_data"][1]).astype(float)
+    for ii in c.get("expected_data_mask_index", []):
+        want[ii] = np.nan
+    assert got.dims == (c["expected_coord"][0],)
+    assert got.name == c["source_data"][0]  # reference transform.py:455-466 never forwards `suffix`
+    from xgcm_b200.transform import linear_interpolation
+
+    theta = kw["target_data"] if kw.get("target_data") is not None else ds[sdim]
+    mid = linear_interpolation(ds[c["source_data"][0]], theta, target, sdim, sdim, tdim,
+                               mask_edges=kw.get("mask_edges", True), logarithmic=kw["method"] == "log",
+                               suffix=kw.get("suffix", ""), grid=grid)
+    assert mid.name == "data" + kw.get("suffix", "")  # test_transform.py:951-992 (mid level)
+    np.testing.assert_allclose(mid.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(got.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+    np.testing.assert_array_equal(got.coords[c["expected_coord"][0]].values, _arr(c["expected_coord"][1]))
+
+
+def test_reference_numba_golden_vectors():
+    """tests/golden/interp1d_ref.npz: outputs of the reference's own numba gufunc, bit-exact."""
+    from xgcm_b200.transform import interp_1d_linear
+
+    g = np.load(os.path.join(GOLDEN, "interp1d_ref.npz"))
+    for tag in ("float32", "float64"):
+        phi, theta, target = g[f"phi|{tag}"], g[f"theta|{tag}"], g[f"target|{tag}"]
+        for mask in (0, 1):
+            for bypass in (0, 1):
+                got = interp_1d_linear(phi, theta, target, mask_edges=bool(mask), bypass_checks=bool(bypass))
+                want = g[f"out|{tag}|{mask}|{bypass}|0"]
+                assert got.dtype == want.dtype
+                np.testing.assert_array_equal(got, want)
+        got = interp_1d_linear(phi, g[f"log_theta|{tag}"], g[f"log_target|{tag}"], mask_edges=True, logarithmic=True)
+        tol = 2e-6 if tag == "float32" else 1e-12
+        np.testing.assert_allclose(got, g[f"out|{tag}|1|0|1"], rtol=tol, atol=tol, equal_nan=True)
+
+
+def test_analytic_interp(rtol=1e-4):
+    """xgcm/test/test_transform.py:850-865: uniformly stratified scalar, rtol 1e-4."""
+    from xgcm_b200.transform import interp_1d_linear
+
+    nz, nx = 100, 1000
+    z_vertex = np.linspace(0, 1, nz + 1)
+    z = 0.5 * (z_vertex[:-1] + z_vertex[1:])
+    x = 2 * np.pi * np.linspace(0, 1, nx)
+    theta = z + 0.1 * np.cos(3 * x)[:, None]
+    phi = np.sin(theta) + 0.1 * np.cos(5 * x)[:, None]
+    levels = np.arange(0.2, 0.9, 0.025)
+    expected = np.sin(levels) + 0.1 * np.cos(5 * x)[:, None]
+    got = interp_1d_linear(phi, theta, levels, mask_edges=False)
+    np.testing.assert_allclose(got, expected, rtol=rtol)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_config5_like_vertical_regrid(dtype):
+    """BASELINE configs[4] in miniature: (Z, Y, X) field to new depth levels, output (Y, X, Znew)."""
+    rng = np.random.default_rng(5)
+    nz, ny, nx, m = 25, 12, 20, 33
+    dz = 10 * 1.05 ** np.arange(nz)
+    depth = (np.cumsum(dz) - dz / 2).astype(dtype)
+    a = rng.random((nz, ny, nx)).astype(dtype)
+    ds = xg.Dataset(data_vars={"temp": (("z", "y", "x"), a)}, coords={"z": depth, "y": np.arange(ny), "x": np.arange(nx)})
+    grid = xg.Grid(ds, coords={"Z": {"center": "z"}})
+    levels = np.linspace(depth[0] - 5, depth[-1] + 5, m).astype(dtype)
+    got = grid.transform(ds["temp"], "Z", levels)
+    assert got.dims == ("y", "x", "z") and got.shape == (ny, nx, m)
+    assert got.name == "temp"
+    want = oracle.vinterp_linear(a, depth.reshape(-1, 1, 1) * np.ones((1, ny, nx), dtype), levels, 0, True)
+    assert got.dtype == want.dtype
+    np.testing.assert_array_equal(got.values, want)
+    assert np.isnan(got.values[..., 0]).all() and np.isnan(got.values[..., -1]).all()
+    # target_data given as a 3-D tracer field (transform onto e.g. density)
+    dens = np.cumsum(0.1 + rng.random((nz, ny, nx)), axis=0).astype(dtype)
+    ds2 = xg.Dataset(data_vars={"temp": (("z", "y", "x"), a), "dens": (("z", "y", "x"), dens)}, coords={"z": depth})
+    grid2 = xg.Grid(ds2, coords={"Z": {"center": "z"}})
+    tg = xg.DataArray(np.linspace(0, dens.max(), 17).astype(dtype), dims=("dens_lev",))
+    got = grid2.transform(ds2["temp"], "Z", tg, target_data=ds2["dens"])
+    assert got.dims == ("y", "x", "dens_lev")
+    np.testing.assert_array_equal(got.values, oracle.vinterp_linear(a, dens, tg.values, 0, True))
+
+
+def test_transform_errors():
+    ds = xg.Dataset(data_vars={"t": (("z",), np.arange(5.0))}, coords={"z": np.arange(5.0)})
+    with pytest.raises(ValueError, match="non-periodic"):
+        xg.Grid(ds, coords={"Z": {"center": "z"}}, padding="periodic").transform(ds["t"], "Z", np.arange(3.0))
+    grid = xg.Grid(ds, coords={"Z": {"center": "z"}})
+    with pytest.raises(ValueError):
+        grid.transform(ds["t"], "Z", [1, 2, 3])  # list target: must be ndarray / DataArray
+    with pytest.raises(NotImplementedError):
+        grid.transform(ds["t"], "Z", np.arange(3.0), method="conservative")

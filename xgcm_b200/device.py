@@ -49,5 +49,7 @@ def as_device_tensor(data, device=None) -> Tuple[torch.Tensor, bool]:
 def result_like(t: torch.Tensor, was_host: bool):
     """Give the result the residency of the input: numpy for host inputs."""
     if was_host:
-        return t.cpu().numpy()
+        host = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)  # torch's caching host allocator
+        host.copy_(t)
+        return host.numpy()
     return t

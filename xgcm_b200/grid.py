@@ -1,0 +1,724 @@
+"""``Grid``: the user-facing façade, API-compatible with the reference's ``xgcm.Grid``.
+
+Method names, kwargs (``axis, to, padding, fill_value, metric_weighted, reverse,
+other_component``), kwarg precedence (per call > ufunc default > Axis default,
+reference grid.py:315-332), default shifts, metric selection rules
+(``get_metric`` conditions 1-4, grid.py:534-657) and error behaviour follow the
+reference.  What differs is where the numbers come from: every array value is
+produced by a CUDA kernel behind the C-ABI:
+
+* ``diff / interp / min / max`` (+ ``metric_weighted``) and ``derivative``:
+  one fused ``xg_stencil2`` launch per axis (reference: np.pad copy + ufunc +
+  up to two metric passes, grid.py:800-832,1576-1578);
+* ``cumsum / cumint``: one ``xg_cumscan`` launch per axis (grid.py:1306-1414);
+* ``integrate / average``: one ``xg_wreduce`` launch per axis (grid.py:1598-1605,1680-1685);
+* ``transform`` (linear / log): ``xg_vinterp_linear`` (transform.py).
+
+Host (numpy-backed) inputs are streamed through the GPU and come back as numpy;
+CUDA-resident inputs stay resident.  Out of scope (raise ``NotImplementedError``):
+face connections, north-fold padding, dask chunking, metadata autoparsing.
+"""
+
+from __future__ import annotations
+
+import functools
+import inspect
+import itertools
+import warnings
+from collections import OrderedDict
+from typing import Any, Callable, Dict, Iterable, List, Mapping, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+from . import gridops
+from .axis import Axis, _is_dataset
+from .grid_ufunc import (
+    GridUFunc,
+    _check_data_input,
+    _GridUFuncSignature,
+    _maybe_unpack_vector_component,
+    _reattach_coords,
+    apply_as_grid_ufunc,
+)
+from .labeled import DataArray, Dataset, is_device_array
+from .metrics import iterate_axis_combinations
+from .padding import pad
+
+
+def _maybe_promote_str_to_list(a):
+    return [a] if isinstance(a, str) else a
+
+
+class Grid:
+    """A collection of :class:`Axis` objects plus grid metrics, bound to a dataset."""
+
+    def __init__(
+        self,
+        ds,
+        coords: Optional[Mapping[str, Mapping[str, str]]] = None,
+        fill_value: Optional[Union[float, Mapping[str, float]]] = None,
+        default_shifts: Optional[Mapping[str, str]] = None,
+        padding: Optional[Union[str, Mapping[str, str]]] = None,
+        face_connections: Optional[Dict[str, Any]] = None,
+        metrics: Optional[Mapping[Tuple[str], List[str]]] = None,
+        autoparse_metadata: bool = True,
+        device=None,
+        **kwargs,
+    ):
+        if "boundary" in kwargs:
+            raise ValueError(
+                "Argument 'boundary' has been renamed to 'padding'. Please use 'padding' instead."
+            )
+        self._xarray_io = False
+        if not _is_dataset(ds):
+            raise TypeError(
+                f"ds argument to `xgcm.Grid` must be of type xarray.Dataset, but is of type {type(ds)}"
+            )
+        if not isinstance(ds, Dataset):
+            from . import interop
+
+            ds = interop.dataset_from_xarray(ds)
+            self._xarray_io = True
+        self._ds = ds
+        self._device = device
+
+        if autoparse_metadata and coords is None:
+            from .metadata import parse_comodo
+
+            parsed = parse_comodo(ds)
+            if parsed:
+                coords = parsed
+
+        if "periodic" in kwargs:
+            raise ValueError(
+                "The `periodic` argument has been removed. Use "
+                "`padding='periodic'` (per axis if needed, e.g. "
+                "`padding={'X': 'periodic', 'Y': 'fill'}`) instead. "
+                "Previously `periodic=False` corresponded to `padding='fill'`."
+            )
+        if kwargs:
+            raise TypeError(
+                f"Grid.__init__() got unexpected keyword argument(s): "
+                f"{', '.join(repr(k) for k in kwargs)}"
+            )
+        if fill_value:
+            warnings.warn(
+                "The default fill_value will be changed to nan (from 0.0 previously) "
+                "in future versions. Provide `fill_value=0.0` to preserve previous behavior.",
+                category=DeprecationWarning,
+            )
+        if coords is None:
+            raise ValueError(
+                "Could not determine Axis names - please provide them in the coords kwarg "
+                "or provide a dataset from which they can be parsed"
+            )
+        if face_connections:
+            raise NotImplementedError(
+                "face_connections (cubed-sphere / LLC tile topology, reference padding.py:230-572) "
+                "are outside the scope of xgcm_b200"
+            )
+        self._facedim = None
+        self._face_connections = None
+        self._folds = {}
+
+        all_axes = list(coords.keys())
+        padding_dict = self._map_kwargs_over_axes(padding, axes=all_axes)
+        shifts_dict = self._map_kwargs_over_axes(default_shifts, axes=all_axes)
+        fill_dict = self._map_kwargs_over_axes(fill_value, axes=all_axes)
+        self._explicitly_periodic_axes = {ax for ax, p in padding_dict.items() if p == "periodic"}
+
+        self.axes: "OrderedDict[str, Axis]" = OrderedDict()
+        for name in all_axes:
+            self.axes[name] = Axis(
+                ds,
+                name,
+                coords=coords[name],
+                default_shifts=shifts_dict.get(name, None),
+                padding=padding_dict.get(name, None),
+                fill_value=fill_dict.get(name, None),
+            )
+
+        self._metrics: Dict[frozenset, List[DataArray]] = {}
+        self._metric_cache: Dict[Any, Any] = {}
+        if metrics is not None:
+            for key, value in metrics.items():
+                self.set_metrics(key, value)
+
+    # ------------------------------------------------------------------ kwargs plumbing
+    def _map_kwargs_over_axes(self, kwargs, axes: Optional[Iterable[str]] = None) -> Dict[str, Any]:
+        """``'fill'`` -> ``{'X': 'fill', 'Y': 'fill'}``; dicts pass through (grid.py:291-313)."""
+        if axes is None:
+            axes = self.axes
+        if isinstance(kwargs, dict):
+            return kwargs
+        return {name: kwargs for name in axes}
+
+    def _complete_user_kwargs_using_axis_defaults(self, user_kwargs, property: str) -> Dict[str, Any]:
+        """Per-call value wins, else the Axis default (grid.py:315-332)."""
+        defaults = {ax: getattr(self.axes[ax], property) for ax in self.axes}
+        if user_kwargs is None:
+            return defaults
+        return {**defaults, **self._map_kwargs_over_axes(user_kwargs)}
+
+    # ------------------------------------------------------------------ device plumbing
+    def _device_for(self, da=None):
+        import torch
+
+        if da is not None and is_device_array(getattr(da, "data", None)):
+            return da.data.device
+        if self._device is not None:
+            return torch.device(self._device)
+        from .device import default_device
+
+        return default_device()
+
+    def _metric_tensor(self, metric: DataArray, field_dims: Sequence[str], like):
+        """Device tensor of ``metric`` shaped to broadcast against ``field_dims`` (size-1 elsewhere)."""
+        import torch
+
+        missing = [d for d in metric.dims if d not in field_dims]
+        if missing:
+            raise ValueError(f"metric dims {metric.dims} are not a subset of the field dims {tuple(field_dims)}")
+        key = (id(metric.data), tuple(metric.dims), tuple(field_dims), str(like.dtype), str(like.device))
+        hit = self._metric_cache.get(key)
+        if hit is not None and hit[0] is metric.data:
+            return hit[1]
+        data = metric.data
+        if not is_device_array(data):
+            arr = np.ascontiguousarray(np.asarray(data))
+            if arr.dtype.kind != "f":
+                arr = arr.astype(np.float64)
+            data = torch.from_numpy(arr).to(like.device)
+        data = data.to(like.dtype)
+        present = [d for d in field_dims if d in metric.dims]
+        perm = [metric.dims.index(d) for d in present]
+        if perm != list(range(len(perm))):
+            data = data.permute(*perm).contiguous()
+        shape = [metric.sizes[d] if d in metric.dims else 1 for d in field_dims]
+        t = data.reshape(shape)
+        if len(self._metric_cache) > 64:
+            self._metric_cache.clear()
+        self._metric_cache[key] = (metric.data, t)
+        return t
+
+    def _metric_host(self, metric: DataArray, field_dims: Sequence[str], dtype) -> np.ndarray:
+        """Host array of ``metric`` shaped to broadcast against ``field_dims``."""
+        missing = [d for d in metric.dims if d not in field_dims]
+        if missing:
+            raise ValueError(f"metric dims {metric.dims} are not a subset of the field dims {tuple(field_dims)}")
+        arr = metric.values
+        present = [d for d in field_dims if d in metric.dims]
+        perm = [metric.dims.index(d) for d in present]
+        if perm != list(range(len(perm))):
+            arr = np.transpose(arr, perm)
+        shape = [metric.sizes[d] if d in metric.dims else 1 for d in field_dims]
+        return np.ascontiguousarray(arr, dtype=dtype).reshape(shape)
+
+    def _wrap_in(self, obj):
+        """Accept real xarray objects when xarray is installed."""
+        if isinstance(obj, (DataArray, dict)) or obj is None:
+            return obj, False
+        if type(obj).__name__ == "DataArray" and hasattr(obj, "dims"):
+            from . import interop
+
+            return interop.dataarray_from_xarray(obj), True
+        return obj, False
+
+    def _wrap_out(self, res, as_xarray: bool):
+        if not as_xarray:
+            return res
+        from . import interop
+
+        return interop.dataarray_to_xarray(res)
+
+    # ------------------------------------------------------------------ metrics
+    def set_metrics(self, key, value, overwrite=False):
+        """Register dataset variables as metrics for a set of axes (grid.py:472-514)."""
+        metric_axes = frozenset(_maybe_promote_str_to_list(key))
+        missing = [ma for ma in metric_axes if ma not in self.axes]
+        if missing:
+            raise KeyError(f"Metric axes {missing!r} not compatible with grid axes {tuple(self.axes)!r}")
+        names = _maybe_promote_str_to_list(value)
+        for name in names:
+            if name not in self._ds.variables:
+                raise KeyError(f"Metric variable {name} not found in dataset.")
+        self._metric_cache.clear()
+        if metric_axes in self._metrics:
+            existing = self._metrics[metric_axes]
+            new = self._ds[name].reset_coords(drop=True)
+            replaced = False
+            for idx, old in enumerate(existing):
+                if set(new.dims) == set(old.dims):
+                    if not overwrite:
+                        raise ValueError(
+                            f"Metric variable {old.name} with dimensions {old.dims} already assigned in metrics."
+                            f" Overwrite {old.name} with {name} by setting overwrite=True."
+                        )
+                    existing[idx] = new
+                    replaced = True
+            if not replaced:
+                existing.append(new)
+        else:
+            self._metrics[metric_axes] = [self._ds[n].reset_coords(drop=True) for n in names]
+
+    def _get_dims_from_axis(self, da, axis) -> List[str]:
+        da = _maybe_unpack_vector_component(da)
+        dims = []
+        for ax in _maybe_promote_str_to_list(axis):
+            if ax not in self.axes:
+                raise KeyError(f"Did not find axis {ax} from data array {da.name}")
+            matching = [d for d in self.axes[ax].coords.values() if d in da.dims]
+            if len(matching) != 1:
+                raise ValueError(
+                    f"Did not find single matching dimension {da.dims} from {da.name} corresponding to axis {ax}, got {matching}."
+                )
+            dims.append(matching[0])
+        return dims
+
+    def _metric_product(self, metrics: Sequence[DataArray]) -> DataArray:
+        """Product of metrics (dx * dy ...), computed on the device (reference:
+        ``functools.reduce(operator.mul, ...)``, grid.py:617-619)."""
+        if len(metrics) == 1:
+            return metrics[0]
+        key = ("prod",) + tuple(id(m.data) for m in metrics)
+        hit = self._metric_cache.get(key)
+        if hit is not None and all(a is b.data for a, b in zip(hit[0], metrics)):
+            return hit[1]
+        dev = self._device_for(None)
+        out = metrics[0] if metrics[0].is_device else metrics[0].to_device(dev)
+        for m in metrics[1:]:
+            out = out * (m if m.is_device else m.to_device(dev))
+        self._metric_cache[key] = (tuple(m.data for m in metrics), out)
+        return out
+
+    def get_metric(self, array, axes):
+        """The metric for ``axes`` that broadcasts against ``array`` (only its dims matter).
+
+        Selection follows the reference (grid.py:534-657): (1) a metric registered under
+        exactly these axes whose dims fit; (2) else that metric interpolated to the array's
+        position; (3) else a product of sub-axis metrics whose dims fit; (4) else the
+        interpolated product.
+        """
+        array_dims = set(array.dims)
+        self._get_dims_from_axis(array, frozenset(axes))
+        registered = set(tuple(k) for k in self._metrics.keys())
+        overlap = registered.intersection(set(itertools.permutations(tuple(axes))))
+        found = None
+        if overlap:
+            key = frozenset(*overlap)
+            candidates = self._metrics[key]
+            for mv in candidates:
+                if set(mv.dims).issubset(array_dims):
+                    found = mv
+                    break
+            if found is None:
+                mv = candidates[-1]
+                warnings.warn(
+                    f"Metric at {array.dims} being interpolated from metrics at dimensions {mv.dims}. Boundary value set to 'extend'."
+                )
+                found = self.interp_like(mv, array, "extend", None)
+        else:
+            fallback = None
+            locked = False
+            for combo in iterate_axis_combinations(axes):
+                try:
+                    pools = [self._metrics[ac] for ac in combo]
+                except KeyError:
+                    continue
+                for choice in itertools.product(*pools):
+                    dims = set(d for mv in choice for d in mv.dims)
+                    if dims.issubset(array_dims):
+                        found = self._metric_product(choice)
+                        break
+                    if not locked:
+                        fallback = choice
+                if found is not None:
+                    break
+                locked = True
+            if found is None and fallback is not None:
+                warnings.warn(
+                    f"Metric at {array.dims} being interpolated from metrics at dimensions {[pc.dims for pc in fallback]}. Boundary value set to 'extend'."
+                )
+                found = self._metric_product(
+                    tuple(self.interp_like(pc, array, "extend", None) for pc in fallback)
+                )
+        if found is None:
+            raise KeyError(
+                f"Unable to find any combinations of metrics for array dims {array_dims!r} and axes {axes!r}"
+            )
+        return found
+
+    def interp_like(self, array, like, padding=None, fill_value=None, **kwargs):
+        """Interpolate ``array`` to the grid positions of ``like`` (grid.py:659-716)."""
+        if "boundary" in kwargs:
+            raise ValueError(
+                "Argument 'boundary' has been renamed to 'padding'. Please use 'padding' instead."
+            )
+        interp_axes = []
+        for name, axis in self.axes.items():
+            try:
+                pos_array, _ = axis._get_position_name(array)
+                pos_like, _ = axis._get_position_name(like)
+            except KeyError:
+                continue
+            if pos_like != pos_array:
+                interp_axes.append(name)
+        return self.interp(array, interp_axes, fill_value=fill_value, padding=padding)
+
+    def __repr__(self):
+        lines = ["<xgcm.Grid>"]
+        for name, axis in self.axes.items():
+            kind = "periodic" if axis._periodic else "not periodic"
+            lines.append("%s Axis (%s, padding=%r):" % (name, kind, axis.padding))
+            lines += axis._coord_desc()
+        return "\n".join(lines)
+
+    # ------------------------------------------------------------------ 1-D operator dispatch
+    def _create_1d_grid_ufunc_signatures(self, da, axis, to) -> List[_GridUFuncSignature]:
+        sigs = []
+        for ax_name in axis:
+            ax = self.axes[ax_name]
+            from_pos, _ = ax._get_position_name(da)
+            to_pos = to[ax_name] if to.get(ax_name) is not None else None
+            if to_pos is None:
+                to_pos = ax._default_shifts[from_pos]
+            sigs.append(_GridUFuncSignature.from_string(f"({ax_name}:{from_pos})->({ax_name}:{to_pos})"))
+        return sigs
+
+    def _1d_grid_ufunc_dispatch(self, funcname, data, axis, to=None, metric_weighted=None,
+                                other_component=None, _divide_by_metric_of=None, **kwargs):
+        """Apply the built-in 1-D grid ufunc along each axis in turn (grid.py:728-836).
+
+        ``metric_weighted`` (and the divide of ``derivative``) are handed to the kernel as
+        pre-multiply / post-divide operands instead of separate full-array passes.
+        """
+        if "keep_coords" in kwargs:
+            raise ValueError(
+                "The 'keep_coords' argument has been removed. Coordinates "
+                "compatible with the output are now always preserved."
+            )
+        if isinstance(axis, str):
+            axis = [axis]
+        data, as_xarray = self._wrap_in(data)
+        data = _check_data_input(data, self)
+        unpacked = _maybe_unpack_vector_component(data)
+        for ax_name in axis:
+            if ax_name not in self.axes:
+                raise KeyError(f"Did not find axis {ax_name} in grid axes {list(self.axes)}")
+        to = self._map_kwargs_over_axes(to)
+        if isinstance(metric_weighted, str):
+            metric_weighted = (metric_weighted,)
+        metric_weighted = self._map_kwargs_over_axes(metric_weighted)
+        signatures = self._create_1d_grid_ufunc_signatures(unpacked, axis=axis, to=to)
+
+        host_input = not unpacked.is_device
+        array = unpacked.copy(deep=False)
+        n_axes = len(axis)
+        if host_input and n_axes > 1:
+            # several passes: upload once, keep the intermediates resident, download once
+            array = array.to_device(self._device_for(None))
+
+        for sig, ax_name in zip(signatures, axis):
+            grid_ufunc, remaining = _select_grid_ufunc(funcname, sig, module=gridops, **kwargs)
+            weighted = metric_weighted.get(ax_name) if isinstance(metric_weighted, dict) else None
+            extra = {}
+            post_fns = []
+            if weighted:
+                extra["_pre_metric"] = self.get_metric(array, weighted)
+                post_fns.append(lambda probe, _w=weighted: self.get_metric(probe, _w))
+            if _divide_by_metric_of is not None:
+                post_fns.append(lambda probe, _a=_divide_by_metric_of: self.get_metric(probe, _a))
+            if post_fns:
+                extra["_post_metric"] = post_fns[0]
+            arg = {ax_name_key: array for ax_name_key in data} if isinstance(data, dict) else array
+            array = grid_ufunc(
+                self, arg, axis=[(ax_name,)], dask="forbidden", map_overlap=False,
+                other_component=other_component, **remaining, **extra,
+            )
+            for fn in post_fns[1:]:  # metric_weighted AND derivative: second divide, own pass
+                array = array / fn(array)
+        if host_input and array.is_device:
+            from .device import result_like
+
+            array = array._replace(data=result_like(array.data, True))
+        return self._wrap_out(array, as_xarray)
+
+    def apply_as_grid_ufunc(self, func: Callable, *args, axis=None, signature="", padding_width=None,
+                            padding=None, fill_value=None, dask="forbidden", map_overlap=False,
+                            **kwargs):
+        """Apply a user function in a grid-aware manner (grid.py:866-968)."""
+        if "boundary" in kwargs:
+            raise ValueError(
+                "Argument 'boundary' has been renamed to 'padding'. Please use 'padding' instead."
+            )
+        if "boundary_width" in kwargs:
+            raise ValueError(
+                "Argument 'boundary_width' has been renamed to 'padding_width'. "
+                "Please use 'padding_width' instead."
+            )
+        return apply_as_grid_ufunc(
+            func, *args, axis=axis, grid=self, signature=signature, padding_width=padding_width,
+            padding=padding, fill_value=fill_value, dask=dask, map_overlap=map_overlap, **kwargs,
+        )
+
+    def interp(self, da, axis, **kwargs):
+        """Interpolate neighbouring points to the intermediate position along ``axis``."""
+        return self._1d_grid_ufunc_dispatch("interp", da, axis, **kwargs)
+
+    def diff(self, da, axis, **kwargs):
+        """Difference of neighbouring points, landing on the intermediate position."""
+        return self._1d_grid_ufunc_dispatch("diff", da, axis, **kwargs)
+
+    def min(self, da, axis, **kwargs):
+        """Minimum of neighbouring points (NaN-propagating, like np.min)."""
+        return self._1d_grid_ufunc_dispatch("min", da, axis, **kwargs)
+
+    def max(self, da, axis, **kwargs):
+        """Maximum of neighbouring points (NaN-propagating, like np.max)."""
+        return self._1d_grid_ufunc_dispatch("max", da, axis, **kwargs)
+
+    def derivative(self, da, axis, **kwargs):
+        """Centered-difference derivative: ``diff(da, axis) / get_metric(diff, (axis,))``
+        (grid.py:1534-1578), the divide fused into the stencil launch."""
+        if not isinstance(axis, str):
+            raise ValueError("derivative acts on a single axis; pass its name as a string")
+        return self._1d_grid_ufunc_dispatch("diff", da, axis, _divide_by_metric_of=(axis,), **kwargs)
+
+    # ------------------------------------------------------------------ cumsum family
+    def cumsum(self, da, axis, to=None, padding=None, fill_value=None, metric_weighted=None,
+               reverse=False, **kwargs):
+        """Cumulative sum moving to the intermediate position (grid.py:1183-1418).
+
+        Per axis ONE ``xg_cumscan`` launch does metric multiply, (reverse) sequential
+        cumsum, trim, boundary pad of the cumsum'd data and metric divide.
+        """
+        from . import ops
+        from .device import as_device_tensor, result_like
+
+        if "boundary" in kwargs:
+            raise ValueError(
+                "Argument 'boundary' has been renamed to 'padding'. Please use 'padding' instead."
+            )
+        if "keep_coords" in kwargs:
+            raise ValueError(
+                "The 'keep_coords' argument has been removed. Coordinates "
+                "compatible with the output are now always preserved."
+            )
+        if kwargs:
+            raise TypeError(f"cumsum() got unexpected keyword argument(s): {list(kwargs)}")
+        da, as_xarray = self._wrap_in(da)
+        if isinstance(axis, str):
+            axis = [axis]
+        to = self._map_kwargs_over_axes(to)
+        if isinstance(reverse, dict):
+            extra = [name for name in reverse if name not in axis]
+            if extra:
+                raise ValueError(
+                    f"`reverse` was given for axes {extra} which are not being "
+                    f"cumulatively summed (axis={axis}). Only pass `reverse` for "
+                    f"the axes in `axis`."
+                )
+        reverse = self._map_kwargs_over_axes(reverse)
+        if isinstance(metric_weighted, str):
+            metric_weighted = (metric_weighted,)
+        metric_weighted = self._map_kwargs_over_axes(metric_weighted)
+        paddings = self._complete_user_kwargs_using_axis_defaults(padding, "padding")
+        fills = self._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
+
+        host_input = not da.is_device
+        x, _ = as_device_tensor(da.data, self._device_for(da))
+        data = da._replace(data=x)
+        for ax_name in axis:
+            ax = self.axes[ax_name]
+            pos, dim = ax._get_position_name(da)
+            input_da = data
+            ax_reverse = bool(reverse.get(ax.name, False))
+            weighted = metric_weighted.get(ax.name) if isinstance(metric_weighted, dict) else None
+            ax_to = to.get(ax.name) if isinstance(to, dict) else None
+            if ax_to is None:
+                ax_to = ax._default_shifts[pos]
+            try:
+                trim, (pad_lo, pad_hi) = (_CUMSUM_REV if ax_reverse else _CUMSUM_FWD)[(pos, ax_to)]
+            except KeyError:
+                raise ValueError(
+                    f"From `{pos}` to `{ax_to}` is not a valid position "
+                    f"shift for cumsum operation along axis {ax}."
+                )
+            ax_padding = paddings[ax.name]
+            if (pad_lo or pad_hi) and ax_padding is None:
+                raise ValueError(
+                    f"No boundary condition was specified for axis {ax.name!r}, but the "
+                    f"requested operation needs to pad it. Set a boundary condition, "
+                    f"e.g. ``padding='fill'`` (or 'extend'/'periodic'), on the Grid "
+                    f"(``Grid(..., padding=...)``) or pass ``padding=`` to the "
+                    f"grid method."
+                )
+            new_dim = ax.coords[ax_to]
+            out_dims = tuple(new_dim if d == dim else d for d in data.dims)
+            axis_num = data.get_axis_num(dim)
+            pre_t = post_t = None
+            if weighted:
+                pre_t = self._metric_tensor(self.get_metric(data, weighted), data.dims, data.data)
+                probe = DataArray.__new__(DataArray)
+                probe._dims = out_dims
+                post_t = self._metric_tensor(self.get_metric(probe, weighted), out_dims, data.data)
+            fv = fills[ax.name] if fills[ax.name] is not None else 0.0
+            y = ops.cumscan(
+                data.data, axis_num, ax_reverse, trim, pad_lo, pad_hi,
+                ax_padding if (pad_lo or pad_hi) else None, fv, pre=pre_t, post=post_t, skipna=True,
+            )
+            coordless = DataArray(y, dims=out_dims, name=da.name, attrs=da.attrs)
+            data = _reattach_coords(
+                [coordless], grid=self, padding_width={ax.name: (pad_lo, pad_hi)},
+                out_core_dim_names={new_dim}, input_args=[input_da],
+            )[0]
+        if host_input:
+            data = data._replace(data=result_like(data.data, True))
+        return self._wrap_out(data, as_xarray)
+
+    def cumint(self, da, axis, **kwargs):
+        """Cumulative integral: ``cumsum(da * get_metric(da, axis), axis)`` (grid.py:1607-1660)."""
+        da, as_xarray = self._wrap_in(da)
+        weight = self.get_metric(da, axis)
+        host_input = not da.is_device
+        dev = self._device_for(da)
+        dd = da if da.is_device else da.to_device(dev)
+        wd = weight if weight.is_device else weight.to_device(dev)
+        res = self.cumsum(dd * wd, axis, **kwargs)  # product on the device (xg_binary)
+        if host_input:
+            res = res.to_host()
+        return self._wrap_out(res, as_xarray)
+
+    # ------------------------------------------------------------------ reductions
+    def _weighted_reduce(self, da, axis, mode, kwargs):
+        from . import ops
+        from .device import as_device_tensor, result_like
+
+        da, as_xarray = self._wrap_in(da)
+        skipna = kwargs.pop("skipna", None)
+        keep_attrs = kwargs.pop("keep_attrs", None)  # accepted, attrs are dropped like xarray's default
+        if kwargs:
+            raise TypeError(f"unexpected keyword argument(s): {list(kwargs)}")
+        if skipna is None:
+            skipna = True  # xarray default for float data
+        weight = self.get_metric(da, axis)
+        dims = self._get_dims_from_axis(da, axis)
+        host_input = not da.is_device
+        x, _ = as_device_tensor(da.data, self._device_for(da))
+        cur = da._replace(data=x)
+        wt = self._metric_tensor(weight, cur.dims, x)
+        # several axes: reduce the innermost listed dim first with the weights; the weights are
+        # constant along nothing in general, so multi-axis = one weighted pass per dim is only
+        # exact when the metric factorises; otherwise weight once, then plain sums.
+        order = sorted(dims, key=lambda d: cur.get_axis_num(d), reverse=True)
+        if mode == "mean" and len(order) > 1:
+            num = cur
+            den_src = None
+            first = True
+            for d in order:
+                axn = num.get_axis_num(d)
+                if first:
+                    valid_w = ops.wreduce(_nan_mask_weights(cur.data, wt), axn, None, "sum", False)
+                    numer = ops.wreduce(num.data, axn, wt, "sum", True)
+                    first = False
+                    den = valid_w
+                else:
+                    numer = ops.wreduce(num.data, axn, None, "sum", True)
+                    den = ops.wreduce(den_src.data, axn, None, "sum", False)
+                keep = tuple(x_ for x_ in num.dims if x_ != d)
+                num = DataArray(numer, dims=keep)
+                den_src = DataArray(den, dims=keep)
+            out_t = ops.binary("div", num.data, den_src.data)
+            import torch
+
+            out_t = torch.where(den_src.data != 0, out_t, torch.full_like(out_t, float("nan")))
+            res = DataArray(out_t, dims=num.dims, name=da.name)
+        else:
+            first = True
+            for d in order:
+                axn = cur.get_axis_num(d)
+                y = ops.wreduce(cur.data, axn, wt if first else None, mode, bool(skipna))
+                first = False
+                cur = DataArray(y, dims=tuple(x_ for x_ in cur.dims if x_ != d), name=da.name)
+            res = cur
+        coords = {k: c for k, c in da.coords.items() if all(d in res.dims for d in c.dims)}
+        res = res.assign_coords(coords)
+        if host_input:
+            res = res._replace(data=result_like(res.data, True))
+        return self._wrap_out(res, as_xarray)
+
+    def integrate(self, da, axis, **kwargs):
+        """Finite-volume integral ``(da * metric).sum(dim)`` (grid.py:1580-1605), fused."""
+        return self._weighted_reduce(da, axis, "sum", dict(kwargs))
+
+    def average(self, da, axis, **kwargs):
+        """Metric-weighted mean ignoring NaNs (grid.py:1662-1685), fused."""
+        return self._weighted_reduce(da, axis, "mean", dict(kwargs))
+
+    # ------------------------------------------------------------------ vertical transform
+    def transform(self, da, axis, target, **kwargs):
+        """Convert ``da`` to new 1-D coordinates along ``axis`` (grid.py:1687-1776)."""
+        from .transform import transform
+
+        da, as_xarray = self._wrap_in(da)
+        if "target_data" in kwargs and kwargs["target_data"] is not None:
+            kwargs["target_data"], _ = self._wrap_in(kwargs["target_data"])
+        target, _ = self._wrap_in(target)
+        return self._wrap_out(transform(self, axis, da, target, **kwargs), as_xarray)
+
+    # deprecated 2-D vector wrappers of the reference (grid.py:1420-1532) are not carried over
+    def diff_2d_vector(self, *a, **k):
+        raise NotImplementedError("diff_2d_vector is deprecated upstream; call diff on each component")
+
+    def interp_2d_vector(self, *a, **k):
+        raise NotImplementedError("interp_2d_vector is deprecated upstream; call interp on each component")
+
+
+def _nan_mask_weights(x, w):
+    """weights where the field is valid, 0 where it is NaN (xarray Weighted._sum_of_weights)."""
+    import torch
+
+    return torch.where(torch.isnan(x), torch.zeros((), dtype=x.dtype, device=x.device), w.expand(x.shape))
+
+
+# (from, to) -> (trim, (pad_lo, pad_hi)); transcription of the enumerated shifts of
+# reference grid.py:1326-1383
+_CUMSUM_FWD = {
+    ("center", "right"): ("none", (0, 0)),
+    ("left", "center"): ("none", (0, 0)),
+    ("center", "left"): ("drop_last", (1, 0)),
+    ("right", "center"): ("drop_last", (1, 0)),
+    ("center", "inner"): ("drop_last", (0, 0)),
+    ("outer", "center"): ("drop_last", (0, 0)),
+    ("center", "outer"): ("none", (1, 0)),
+    ("inner", "center"): ("none", (1, 0)),
+}
+_CUMSUM_REV = {
+    ("center", "left"): ("none", (0, 0)),
+    ("right", "center"): ("none", (0, 0)),
+    ("center", "right"): ("drop_first", (0, 1)),
+    ("left", "center"): ("drop_first", (0, 1)),
+    ("center", "inner"): ("drop_first", (0, 0)),
+    ("outer", "center"): ("drop_first", (0, 0)),
+    ("center", "outer"): ("none", (0, 1)),
+    ("inner", "center"): ("none", (0, 1)),
+}
+
+
+def _select_grid_ufunc(funcname, signature: _GridUFuncSignature, module, **kwargs):
+    """Pick the GridUFunc of ``module`` whose name starts with ``funcname`` and whose
+    signature is equivalent (grid.py:1779-1824)."""
+    candidates = inspect.getmembers(module, lambda obj: isinstance(obj, GridUFunc))
+    by_name = [f for name, f in candidates if name.startswith(funcname)]
+    if not by_name:
+        raise NotImplementedError(f"Could not find any pre-defined {funcname} grid ufuncs")
+    matching = [f for f in by_name if f.signature.equivalent(signature)]
+    if not matching:
+        raise NotImplementedError(
+            f"Could not find any pre-defined {funcname} grid ufuncs with signature {signature}"
+        )
+    if len(matching) > 1:
+        raise ValueError(
+            f"Function {funcname} with signature='{signature}' and kwargs={kwargs} is an ambiguous selection"
+        )
+    return matching[0], kwargs

@@ -537,22 +537,30 @@ def _apply_fused_stencil(op, da, grid, ax_name, in_dim, out_dim, padding_width_r
     if grid._face_connections is not None:
         raise NotImplementedError("face connections are outside the scope of xgcm_b200")
     axis_num = da.get_axis_num(in_dim)
-    x, was_host = as_device_tensor(da.data, grid._device_for(da))
-    pre_t = None
-    if pre_metric is not None:
-        pre_t = grid._metric_tensor(pre_metric, da.dims, x)
     out_dims = tuple(out_dim if d == in_dim else d for d in da.dims)
-    post_t = None
-    if post_metric_fn is not None:
-        out_shape = list(x.shape)
-        out_shape[axis_num] = x.shape[axis_num] + lo + hi - 1
-        probe = _ShapeProbe(out_dims, out_shape)
-        post_da = post_metric_fn(probe)
-        post_t = grid._metric_tensor(post_da, out_dims, x)
-    out = ops.stencil2(
-        x, axis_num, op, lo, hi, ax_padding if (lo or hi) else None,
-        fills[ax_name] if fills[ax_name] is not None else 0.0, pre=pre_t, post=post_t,
-    )
+    out_shape = list(da.shape)
+    out_shape[axis_num] = da.shape[axis_num] + lo + hi - 1
+    post_da = post_metric_fn(_ShapeProbe(out_dims, out_shape)) if post_metric_fn is not None else None
+    bc = ax_padding if (lo or hi) else None
+    fv = fills[ax_name] if fills[ax_name] is not None else 0.0
+
+    if not da.is_device and isinstance(da.data, np.ndarray) and da.data.dtype in (np.float32, np.float64):
+        # host field: stream slabs H2D -> kernel -> D2H inside the library (xg_stencil2_host)
+        try:
+            out = ops.stencil2_host(
+                da.data, axis_num, op, lo, hi, bc, fv,
+                pre=None if pre_metric is None else grid._metric_host(pre_metric, da.dims, da.data.dtype),
+                post=None if post_da is None else grid._metric_host(post_da, out_dims, da.data.dtype),
+                device=grid._device_for(da).index,
+            )
+            return DataArray(out, dims=out_dims, name=da.name, attrs=da.attrs)
+        except NotImplementedError:
+            pass  # e.g. periodic halo + pre-metric along the outermost axis: whole-field path below
+
+    x, was_host = as_device_tensor(da.data, grid._device_for(da))
+    pre_t = grid._metric_tensor(pre_metric, da.dims, x) if pre_metric is not None else None
+    post_t = grid._metric_tensor(post_da, out_dims, x) if post_da is not None else None
+    out = ops.stencil2(x, axis_num, op, lo, hi, bc, fv, pre=pre_t, post=post_t)
     return DataArray(result_like(out, was_host), dims=out_dims, name=da.name, attrs=da.attrs)
 
 
