@@ -92,6 +92,9 @@ typedef enum {
 XG_API int xg_version(void);
 XG_API const char* xg_last_error(void);
 
+/* Number of kernels this library has launched in this process (all threads). */
+XG_API long long xg_launch_count(void);
+
 /* Device properties the host side needs for planning (SM count, L2 bytes). */
 XG_API int xg_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t* hbm_bytes);
 

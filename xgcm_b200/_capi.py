@@ -31,6 +31,7 @@ _vp = C.c_void_p
 SIGNATURES = {
     "xg_version": (C.c_int, []),
     "xg_last_error": (C.c_char_p, []),
+    "xg_launch_count": (C.c_longlong, []),
     "xg_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), _i64p, _i64p]),
     "xg_stencil2": (
         C.c_int,

@@ -4,9 +4,12 @@
 
 #include <string>
 
+#include <atomic>
+
 #include "xg_common.cuh"
 
 static thread_local std::string g_last_error;
+static std::atomic<long long> g_launches{0};
 
 void xg_set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -20,8 +23,11 @@ int xg_check_launch(const char* what) {
   if (e != cudaSuccess) {
     return xg_fail(XG_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
   }
+  g_launches.fetch_add(1, std::memory_order_relaxed);
   return XG_OK;
 }
+
+extern "C" long long xg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 extern "C" int xg_version(void) { return XG_VERSION; }
 
