@@ -157,7 +157,8 @@ def oracle_step(a, pool=None, nchunks=1):
             return oracle.stencil2(op, a, axis_i, lo, hi, bc, 0.0 if fill is None else fill)
         # dask="parallelized" analogue: chunk a broadcast (non-operated) dim, one task per chunk
         chunk_axis = 0 if axis_i != 0 else 1
-        bounds = np.linspace(0, a.shape[chunk_axis], nchunks + 1).astype(int)
+        nch = max(1, min(nchunks, a.shape[chunk_axis]))
+        bounds = np.linspace(0, a.shape[chunk_axis], nch + 1).astype(int)
         out = np.empty(a.shape, a.dtype)
 
         def task(i):
@@ -165,7 +166,7 @@ def oracle_step(a, pool=None, nchunks=1):
             sl[chunk_axis] = slice(bounds[i], bounds[i + 1])
             out[tuple(sl)] = oracle.stencil2(op, a[tuple(sl)], axis_i, lo, hi, bc, 0.0 if fill is None else fill)
 
-        list(pool.map(task, range(nchunks)))
+        list(pool.map(task, range(nch)))
         return out
 
     axis_index = {"Z": 0, "Y": 1, "X": 2}
@@ -191,7 +192,7 @@ def run_reference(args):
     shape = tuple(args.shape)
     a = np.empty(shape, DTYPE)
     ops.fill_uniform_host(a.reshape(-1), SEED)
-    nchunks = max(1, min(cores, shape[0]))
+    nchunks = cores
     with ThreadPoolExecutor(max_workers=cores) as pool:
         for _ in range(args.warmup):
             oracle_step(a, pool, nchunks)
