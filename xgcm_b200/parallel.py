@@ -1,0 +1,148 @@
+"""Multi-GPU: one process per GPU (torch.distributed, NCCL over NVLink), sharding as the path allows.
+
+The hot path shards naturally: every operator acts along ONE of X / Y / Z, so any
+other dimension — normally ``time`` — is a pure batch dimension.  The production layout is
+therefore *contiguous blocks of time steps per rank with NO collective on the data path*
+(``shard_bounds`` / ``shard_dataarray``); this is the reference's "broadcast-dim chunks" case
+(docs/grid_ufuncs.md:341-376).
+
+Only when the operated axis itself is sharded is there a real exchange step — the analogue of
+the reference's ``dask.array.map_overlap(depth=1)`` (xgcm/grid_ufunc.py:1057-1133): each rank
+sends ONE boundary plane to a neighbour and receives one (``exchange_halo``; NCCL send/recv over
+NVLink on GPUs, gloo on CPU for tests), and the received plane enters the fused stencil kernel
+through its ``halo_lo`` / ``halo_hi`` operands (``sharded_stencil2``).  Same restrictions as the
+reference: no ``inner`` / ``outer`` outputs (grid_ufunc.py:1136-1159), no cumsum (grid.py:813-816).
+"""
+
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous block ``[start, stop)`` of ``n`` items owned by ``rank`` (block size ceil(n/world))."""
+    if world < 1 or not 0 <= rank < world:
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    block = -(-n // world)
+    start = min(n, rank * block)
+    return start, min(n, start + block)
+
+
+def shard_dataarray(da, dim: str, rank: Optional[int] = None, world: Optional[int] = None):
+    """This rank's contiguous block of ``da`` along ``dim`` (e.g. ``time``)."""
+    rank = dist.get_rank() if rank is None else rank
+    world = dist.get_world_size() if world is None else world
+    start, stop = shard_bounds(da.sizes[dim], world, rank)
+    return da.isel({dim: slice(start, stop)})
+
+
+def _plane(x: torch.Tensor, axis: int, index: int) -> torch.Tensor:
+    return x.select(axis, index).contiguous()
+
+
+def exchange_halo(
+    x: torch.Tensor,
+    axis: int,
+    lo: int,
+    hi: int,
+    periodic: bool,
+    group=None,
+    edge_scale_lo: Optional[torch.Tensor] = None,
+    edge_scale_hi: Optional[torch.Tensor] = None,
+) -> Tuple[Optional[torch.Tensor], Optional[torch.Tensor]]:
+    """One ring step: returns ``(halo_lo, halo_hi)`` planes for this rank's shard of ``axis``.
+
+    ``halo_lo`` (needed when ``lo``) is the previous rank's LAST plane, ``halo_hi`` (when ``hi``)
+    the next rank's FIRST plane.  The ring closes only when ``periodic``; otherwise the edge
+    ranks get ``None`` and synthesise the boundary locally (fill / extend in the kernel).
+    ``edge_scale_*``: optional metric planes multiplied into the plane before sending (the halo
+    must carry ``field * metric`` like the reference's padded array, grid.py:806-808).
+    """
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return None, None  # the kernel's own boundary handling covers the single-shard case
+    prev_rank, next_rank = (rank - 1) % world, (rank + 1) % world
+    has_prev = periodic or rank > 0
+    has_next = periodic or rank < world - 1
+    ops = []
+    recv_lo = recv_hi = None
+    keep = []
+    if lo:
+        # my last plane goes to the next rank; I receive the previous rank's last plane
+        if has_next:
+            send = _plane(x, axis, x.shape[axis] - 1)
+            if edge_scale_hi is not None:
+                send = _scale(send, edge_scale_hi)
+            keep.append(send)
+            ops.append(dist.P2POp(dist.isend, send, _global_rank(next_rank, group), group))
+        if has_prev:
+            recv_lo = torch.empty_like(_plane(x, axis, 0))
+            ops.append(dist.P2POp(dist.irecv, recv_lo, _global_rank(prev_rank, group), group))
+    if hi:
+        if has_prev:
+            send = _plane(x, axis, 0)
+            if edge_scale_lo is not None:
+                send = _scale(send, edge_scale_lo)
+            keep.append(send)
+            ops.append(dist.P2POp(dist.isend, send, _global_rank(prev_rank, group), group))
+        if has_next:
+            recv_hi = torch.empty_like(_plane(x, axis, 0))
+            ops.append(dist.P2POp(dist.irecv, recv_hi, _global_rank(next_rank, group), group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):  # one ncclGroupStart/End on GPUs
+            req.wait()
+    return recv_lo, recv_hi
+
+
+def _global_rank(group_rank: int, group) -> int:
+    if group is None:
+        return group_rank
+    return dist.get_global_rank(group, group_rank)
+
+
+def _scale(plane: torch.Tensor, metric_plane: torch.Tensor) -> torch.Tensor:
+    if plane.is_cuda:
+        from . import ops
+
+        return ops.binary("mul", plane, metric_plane.to(plane.dtype), tuple(plane.shape))
+    return plane * metric_plane  # CPU tensors only occur in the gloo plumbing tests
+
+
+def sharded_stencil2(
+    x_local: torch.Tensor,
+    axis: int,
+    op: str,
+    lo: int,
+    hi: int,
+    padding: Optional[str],
+    fill_value: float = 0.0,
+    pre: Optional[torch.Tensor] = None,
+    post: Optional[torch.Tensor] = None,
+    group=None,
+) -> torch.Tensor:
+    """``xg_stencil2`` on a field whose operated ``axis`` is split across the ranks of ``group``
+    (contiguous blocks, rank order = axis order).  ``pre`` / ``post`` are the LOCAL shards of the
+    metrics.  One plane per neighbour crosses NVLink; everything else is the single-GPU kernel."""
+    from . import ops
+
+    if lo + hi != 1:
+        # grid_ufunc.py:1136-1159: shifting to inner/outer would change the chunk length
+        raise NotImplementedError(
+            "a sharded operated axis supports only length-preserving shifts (center<->left/right), "
+            "like map_overlap in the reference"
+        )
+    axis = axis % x_local.dim()
+    scale_lo = scale_hi = None
+    if pre is not None:
+        pre_b = pre.expand(x_local.shape) if pre.dim() == x_local.dim() else pre
+        scale_lo = pre_b.select(axis, 0)
+        scale_hi = pre_b.select(axis, x_local.shape[axis] - 1)
+    halo_lo, halo_hi = exchange_halo(
+        x_local, axis, lo, hi, padding == "periodic", group, edge_scale_lo=scale_lo, edge_scale_hi=scale_hi
+    )
+    return ops.stencil2(x_local, axis, op, lo, hi, padding, fill_value, pre=pre, post=post,
+                        halo_lo=halo_lo, halo_hi=halo_hi)
