@@ -51,8 +51,8 @@ WORKLOAD = ("C3 (BASELINE configs[2]): Grid.diff + Grid.interp along X(periodic)
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--shape", type=int, nargs=3, default=list(SHAPE))
     ap.add_argument("--no-e2e", action="store_true")
@@ -104,7 +104,7 @@ class ClockSampler:
         try:
             self.out = open(self.path, "w")
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits", "-lms", "50"],
                 stdout=self.out, stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None

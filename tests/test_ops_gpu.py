@@ -206,8 +206,11 @@ def test_vinterp_linear_matches_reference_port(dtype, shape, axis):
             np.testing.assert_array_equal(got, want)
 
 
-@pytest.mark.parametrize("dtype,rtol", [(np.float32, 2e-6), (np.float64, 1e-12)])
+@pytest.mark.parametrize("dtype,rtol", [(np.float32, 5e-5), (np.float64, 1e-12)])
 def test_vinterp_log(dtype, rtol):
+    """method="log": np.log on float32 (numpy's SIMD polynomial) and CUDA logf are both within a few
+    ulp but not bit-identical; a 1-ulp difference in log(theta) is amplified by 1/(log spacing) in the
+    interpolation weight (here up to ~1.4e-5 abs).  fp64 stays within 1e-12."""
     from xgcm_b200 import ops
 
     rng = np.random.default_rng(23)

@@ -72,7 +72,7 @@ def test_reference_numba_golden_vectors():
                 assert got.dtype == want.dtype
                 np.testing.assert_array_equal(got, want)
         got = interp_1d_linear(phi, g[f"log_theta|{tag}"], g[f"log_target|{tag}"], mask_edges=True, logarithmic=True)
-        tol = 2e-6 if tag == "float32" else 1e-12
+        tol = 5e-5 if tag == "float32" else 1e-12  # logf vs numpy SIMD log, see test_ops_gpu.test_vinterp_log
         np.testing.assert_allclose(got, g[f"out|{tag}|1|0|1"], rtol=tol, atol=tol, equal_nan=True)
 
 

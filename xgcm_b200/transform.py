@@ -70,7 +70,9 @@ def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, ta
     tg_t, _ = as_device_tensor(target_theta_levels.data, x.device)
     out = ops.vinterp_linear(x, th_t, tg_t, axis_num, mask_edges, bypass_checks, logarithmic)
     out_dims = tuple(d for d in phi.dims if d != phi_dim) + (target_dim,)
-    coords = {k: c for k, c in phi.coords.items() if all(d in out_dims for d in c.dims) and k != target_dim}
+    # like xr.apply_ufunc with exclude_dims: nothing that lives on the consumed core dim survives
+    coords = {k: c for k, c in phi.coords.items()
+              if phi_dim not in c.dims and k != target_dim and all(d in out_dims for d in c.dims)}
     for k, c in target_theta_levels.coords.items():
         if all(d in out_dims for d in c.dims):
             coords[k] = c
