@@ -144,12 +144,15 @@ XG_API int xg_wreduce(int dtype, const void* in, const void* weight,
  * Linear interpolation of phi (defined on theta) onto target levels, per
  * column along `axis`; output dimension is appended LAST (transform.py:233-249).
  * phi: `shape`; theta: broadcast against phi via theta_strides (a shared 1-D
- * coordinate has stride 1 on `axis` and 0 elsewhere); target: m levels.
+ * coordinate has stride 1 on `axis` and 0 elsewhere); target: m levels, either one
+ * shared contiguous vector (target_strides == NULL) or one vector per column:
+ * target_strides[d] (d != axis) = stride over column dim d, target_strides[axis] =
+ * stride between consecutive levels.
  * out: shape-without-axis + (m,).  fp64 arithmetic, rounded once.
  */
 XG_API int xg_vinterp_linear(int dtype, const void* phi, const void* theta,
                       const int64_t* theta_strides, const void* target,
-                      int64_t m, void* out, int ndim, const int64_t* shape,
+                      const int64_t* target_strides, int64_t m, void* out, int ndim, const int64_t* shape,
                       int axis, int mask_edges, int bypass_checks,
                       int logarithmic, void* stream);
 

@@ -49,7 +49,7 @@ SIGNATURES = {
     ),
     "xg_vinterp_linear": (
         C.c_int,
-        [C.c_int, _vp, _vp, _i64p, _vp, C.c_int64, _vp, C.c_int, _i64p, C.c_int, C.c_int,
+        [C.c_int, _vp, _vp, _i64p, _vp, _i64p, C.c_int64, _vp, C.c_int, _i64p, C.c_int, C.c_int,
          C.c_int, C.c_int, _vp],
     ),
     "xg_pad": (

@@ -67,6 +67,7 @@ int xg_collapse_view(int ndim, const int64_t* shape, int axis, XgView* v) {
 static int collapse_groups(const int64_t* shape, const int64_t* strides, int d0,
                            int d1, XgGroups* g, const char* what) {
   g->n = 0;
+  g->small = 0;
   for (int k = 0; k < XG_MAXG; ++k) {
     g->size[k] = 1;
     g->stride[k] = 0;
@@ -93,6 +94,21 @@ static int collapse_groups(const int64_t* shape, const int64_t* strides, int d0,
     g->stride[g->n] = st;
     g->n++;
   }
+  int64_t total = 1;
+  bool small = true;
+  for (int k = 0; k < g->n; ++k) {
+    if (g->size[k] >= (1ll << 31)) small = false;
+    if (total > (1ll << 31) / (g->size[k] > 0 ? g->size[k] : 1)) small = false;
+    total *= g->size[k];
+  }
+  // the flat index handed to xg_groups_offset may exceed `total` only through broadcast
+  // leading dims that were merged away, so bound it by the caller-visible extent as well
+  int64_t extent = 1;
+  for (int d = d0; d < d1; ++d) {
+    if (shape[d] > 0 && extent > (1ll << 31) / shape[d]) small = false;
+    extent *= shape[d] > 0 ? shape[d] : 1;
+  }
+  g->small = small ? 1 : 0;
   return XG_OK;
 }
 

@@ -30,6 +30,7 @@ struct ScanArgs {
   T fill;
   XgOperand pre, post;
   int64_t nvec_inner;
+  bool small_index;  // outer * nvec_inner < 2^31
 };
 
 template <typename T>
@@ -52,27 +53,37 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
   typedef XgPack<T, VEC> Pack;
   const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (g >= a.outer * a.nvec_inner) return;
-  const int64_t o = g / a.nvec_inner;
-  const int64_t i = (g - o * a.nvec_inner) * VEC;
+  int64_t o, iv;
+  xg_divmod(g, a.nvec_inner, a.small_index, o, iv);
+  const int64_t i = iv * VEC;
   const T* ibase = a.in + o * a.n * a.inner + i;
   T* obase = a.out + o * a.n_out * a.inner + i;
+  const bool has_pre = MET && a.pre.ptr != nullptr;
+  const bool has_post = MET && a.post.ptr != nullptr;
   int64_t pre_base = 0, post_base = 0;
+  XgInnerOff<VEC> pre_io, post_io;
   if (MET) {
-    if (a.pre.ptr) pre_base = xg_groups_offset(a.pre.outer, o);
-    if (a.post.ptr) post_base = xg_groups_offset(a.post.outer, o);
+    if (has_pre) {
+      pre_base = xg_groups_offset(a.pre.outer, o);
+      pre_io = xg_inner_off<VEC>(a.pre, i);
+    }
+    if (has_post) {
+      post_base = xg_groups_offset(a.post.outer, o);
+      post_io = xg_inner_off<VEC>(a.post, i);
+    }
   }
   auto loadA = [&](int64_t k) -> Pack {
     Pack v = xg_ld_stream<T, VEC>(ibase + k * a.inner);
-    if (MET && a.pre.ptr) {
-      Pack m = xg_ld_operand<T, VEC>(a.pre, pre_base + k * a.pre.axis_stride, i);
+    if (has_pre) {
+      Pack m = xg_ld_operand_at<T, VEC>(a.pre, pre_base + k * a.pre.axis_stride, pre_io);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] * m.v[q];
     }
     return v;
   };
   auto store = [&](int64_t j_out, Pack v) {
-    if (MET && a.post.ptr) {
-      Pack m = xg_ld_operand<T, VEC>(a.post, post_base + j_out * a.post.axis_stride, i);
+    if (has_post) {
+      Pack m = xg_ld_operand_at<T, VEC>(a.post, post_base + j_out * a.post.axis_stride, post_io);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] / m.v[q];
     }
@@ -92,19 +103,30 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
     if (k == a.k_last) cl = acc;
     if (k >= a.k_first && k <= a.k_last) store(a.pad_lo + (k - a.k_first), acc);
   };
+  auto kof = [&](int64_t kk) -> int64_t { return a.reverse ? (a.n - 1 - kk) : kk; };
 
+  // software pipeline: the loads of chunk c+1 are in flight while chunk c is summed (the adds
+  // are serial by construction, so memory-level parallelism has to come from prefetch depth)
   int64_t kk = 0;
-  for (; kk + U <= a.n; kk += U) {
-    Pack v[U];
+  const int64_t nfull = (a.n / U) * U;
+  if (nfull > 0) {
+    Pack cur[U], nxt[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) v[u] = loadA(a.reverse ? (a.n - 1 - (kk + u)) : (kk + u));
+    for (int u = 0; u < U; ++u) cur[u] = loadA(kof(u));
+    for (; kk + U < nfull; kk += U) {
 #pragma unroll
-    for (int u = 0; u < U; ++u) step(a.reverse ? (a.n - 1 - (kk + u)) : (kk + u), v[u]);
+      for (int u = 0; u < U; ++u) nxt[u] = loadA(kof(kk + U + u));
+#pragma unroll
+      for (int u = 0; u < U; ++u) step(kof(kk + u), cur[u]);
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = nxt[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) step(kof(kk + u), cur[u]);
+    kk += U;
   }
-  for (; kk < a.n; ++kk) {
-    const int64_t k = a.reverse ? (a.n - 1 - kk) : kk;
-    step(k, loadA(k));
-  }
+  for (; kk < a.n; ++kk) step(kof(kk), loadA(kof(kk)));
+
   if (a.k_last - a.k_first < 1) {  // a single kept cell: "next" is the edge itself
     cf1 = cf;
     cl1 = cl;
@@ -128,47 +150,96 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
 // ------------------------------------------------------------------ innermost axis
 constexpr int kRowWarps = 4;
 constexpr int kTile = 32;
+constexpr int kStages = 2;
+
+// 4- / 8-byte asynchronous global->shared copy (LDGSTS): the tile of the NEXT step is in flight
+// while the current one is scanned, at no register cost
+template <typename T>
+__device__ __forceinline__ void cp_async_elem(T* smem_dst, const T* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if constexpr (sizeof(T) == 4)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+template <typename T>
+struct RowTileSmem {
+  T tile[kRowWarps][kStages][kTile][kTile + 1];
+  int64_t pre_off[kRowWarps][kTile];
+  int64_t post_off[kRowWarps][kTile];
+};
 
 template <typename T, bool MET>
 __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> a) {
-  __shared__ T tile_s[kRowWarps][kTile][kTile + 1];
-  __shared__ int64_t pre_off_s[kRowWarps][kTile];
-  __shared__ int64_t post_off_s[kRowWarps][kTile];
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  RowTileSmem<T>& sm = *reinterpret_cast<RowTileSmem<T>*>(smem_raw);
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int64_t unit = (int64_t)blockIdx.x * kRowWarps + w;
   const int64_t r0 = unit * kTile;
   if (r0 >= a.outer) return;  // warp-uniform
-  T(*tile)[kTile + 1] = tile_s[w];
   const int64_t my_row = r0 + lane;
   const bool row_ok = my_row < a.outer;
   const int nrows = (int)((a.outer - r0 < kTile) ? (a.outer - r0) : kTile);
   if (MET) {
-    pre_off_s[w][lane] = (a.pre.ptr && row_ok) ? xg_groups_offset(a.pre.outer, my_row) : 0;
-    post_off_s[w][lane] = (a.post.ptr && row_ok) ? xg_groups_offset(a.post.outer, my_row) : 0;
+    sm.pre_off[w][lane] = (a.pre.ptr && row_ok) ? xg_groups_offset(a.pre.outer, my_row) : 0;
+    sm.post_off[w][lane] = (a.post.ptr && row_ok) ? xg_groups_offset(a.post.outer, my_row) : 0;
   }
   __syncwarp();
   const T* prep = reinterpret_cast<const T*>(a.pre.ptr);
   const T* postp = reinterpret_cast<const T*>(a.post.ptr);
+  const T* in0 = a.in + r0 * a.n;
+
+  const int64_t ntile = xg_ceil_div(a.n, kTile);
+  auto tile_c0 = [&](int64_t tt) -> int64_t { return (a.reverse ? (ntile - 1 - tt) : tt) * kTile; };
+  // coalesced: one 32-element row segment per instruction, all 32 rows in flight at once
+  auto issue = [&](int64_t tt, int stage) {
+    const int64_t kcol = tile_c0(tt) + lane;
+    T(*tile)[kTile + 1] = sm.tile[w][stage];
+    if (kcol < a.n) {
+#pragma unroll 8
+      for (int rr = 0; rr < kTile; ++rr) {
+        if (rr < nrows) cp_async_elem<T>(&tile[rr][lane], in0 + (int64_t)rr * a.n + kcol);
+        else tile[rr][lane] = T(0);
+      }
+    } else {
+#pragma unroll 8
+      for (int rr = 0; rr < kTile; ++rr) tile[rr][lane] = T(0);
+    }
+    cp_async_commit();
+  };
 
   T acc = T(0), cf = T(0), cf1 = T(0), cl1 = T(0), cl = T(0);
-  const int64_t ntile = xg_ceil_div(a.n, kTile);
+  issue(0, 0);
   for (int64_t tt = 0; tt < ntile; ++tt) {
-    const int64_t c0 = (a.reverse ? (ntile - 1 - tt) : tt) * kTile;
-    const int64_t kcol = c0 + lane;
-    const bool col_ok = kcol < a.n;
-    // coalesced load: one 32-element row segment per instruction, 32 independent loads
-#pragma unroll 8
-    for (int rr = 0; rr < kTile; ++rr) {
-      T v = T(0);
-      if (rr < nrows && col_ok) {
-        v = __ldcs(a.in + (r0 + rr) * a.n + kcol);
-        if (MET && prep) v = v * __ldg(prep + pre_off_s[w][rr] + kcol * a.pre.axis_stride);
-      }
-      tile[rr][lane] = v;
+    const int stage = (int)(tt % kStages);
+    if (tt + 1 < ntile) {
+      issue(tt + 1, (int)((tt + 1) % kStages));
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncwarp();
-    // serial scan: lane = row
+    T(*tile)[kTile + 1] = sm.tile[w][stage];
+    const int64_t c0 = tile_c0(tt);
+    const int64_t kcol = c0 + lane;
+    const bool col_ok = kcol < a.n;
+    if (MET && prep) {  // metric multiply with coalesced metric loads (lane = column)
+      if (col_ok) {
+#pragma unroll 8
+        for (int rr = 0; rr < kTile; ++rr)
+          if (rr < nrows)
+            tile[rr][lane] = tile[rr][lane] * __ldg(prep + sm.pre_off[w][rr] + kcol * a.pre.axis_stride);
+      }
+      __syncwarp();
+    }
+    // serial scan: lane = row (row pitch 33 words: conflict-free)
     if (row_ok) {
 #pragma unroll 8
       for (int cc = 0; cc < kTile; ++cc) {
@@ -188,16 +259,17 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> 
     // coalesced store of the kept cells (shifted by pad_lo - k_first)
     if (col_ok && kcol >= a.k_first && kcol <= a.k_last) {
       const int64_t j_out = a.pad_lo + (kcol - a.k_first);
+      T* out0 = a.out + r0 * a.n_out + j_out;
 #pragma unroll 8
       for (int rr = 0; rr < kTile; ++rr) {
         if (rr < nrows) {
           T v = tile[rr][lane];
-          if (MET && postp) v = v / __ldg(postp + post_off_s[w][rr] + j_out * a.post.axis_stride);
-          __stcs(a.out + (r0 + rr) * a.n_out + j_out, v);
+          if (MET && postp) v = v / __ldg(postp + sm.post_off[w][rr] + j_out * a.post.axis_stride);
+          __stcs(out0 + (int64_t)rr * a.n_out, v);
         }
       }
     }
-    __syncwarp();
+    __syncwarp();  // the stage is overwritten by the copy issued two iterations later
   }
   if (!row_ok) return;
   if (a.k_last - a.k_first < 1) {
@@ -206,13 +278,13 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> 
   }
   if (a.pad_lo) {
     T h = halo_value<T>(true, a.bc, a.fill, cf, cf1, cl1, cl);
-    if (MET && postp) h = h / __ldg(postp + post_off_s[w][lane]);
+    if (MET && postp) h = h / __ldg(postp + sm.post_off[w][lane]);
     a.out[my_row * a.n_out] = h;
   }
   if (a.pad_hi) {
     T h = halo_value<T>(false, a.bc, a.fill, cf, cf1, cl1, cl);
     if (MET && postp)
-      h = h / __ldg(postp + post_off_s[w][lane] + (a.n_out - 1) * a.post.axis_stride);
+      h = h / __ldg(postp + sm.post_off[w][lane] + (a.n_out - 1) * a.post.axis_stride);
     a.out[my_row * a.n_out + a.n_out - 1] = h;
   }
 }
@@ -227,6 +299,7 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
     if (vec_ok && a.outer * (a.inner / VEC) < 148 * 512) vec_ok = false;
     if (vec_ok) {
       a.nvec_inner = a.inner / VEC;
+      a.small_index = a.outer * a.nvec_inner < (1ll << 31);
       const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
       if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
       k_scan_strided<T, VEC, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
@@ -234,6 +307,7 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
       a.pre.vec_ok = 0;
       a.post.vec_ok = 0;
       a.nvec_inner = a.inner;
+      a.small_index = a.outer * a.nvec_inner < (1ll << 31);
       const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
       if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
       k_scan_strided<T, 1, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
@@ -243,7 +317,12 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
   const int64_t units = xg_ceil_div(a.outer, kTile);
   const int64_t blocks = xg_ceil_div(units, kRowWarps);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
-  k_scan_rows<T, MET><<<(unsigned)blocks, kRowWarps * 32, 0, st>>>(a);
+  const size_t smem = sizeof(RowTileSmem<T>);
+  {  // > 48 KiB for fp64: opt in (per device, cheap)
+    cudaError_t e = cudaFuncSetAttribute(k_scan_rows<T, MET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  }
+  k_scan_rows<T, MET><<<(unsigned)blocks, kRowWarps * 32, smem, st>>>(a);
   return xg_check_launch("xg_cumscan(rows)");
 }
 
@@ -274,6 +353,7 @@ int cumscan_typed(const void* in, void* out, int ndim, const int64_t* shape, int
   a.skipna = skipna ? 1 : 0;
   a.fill = static_cast<T>(fill);
   a.nvec_inner = 0;
+  a.small_index = false;
   if (kept == 0 && (pad_lo || pad_hi) && bc != XG_BC_FILL)
     return xg_fail(XG_EINVAL, "xg_cumscan: cannot wrap/extend an empty axis");
   if (v.outer == 0 || v.inner == 0 || a.n_out == 0) return XG_OK;

@@ -33,6 +33,7 @@ struct StencilArgs {
   int J;               // cells marched per warp-unit (strided kernel)
   int64_t nseg, nwc;   // segments along the axis, warp-columns (or row chunks)
   int64_t nunits;      // total warp-units
+  bool small_units;    // nunits < 2^31: 32-bit unit decomposition
   XgOperand pre, post;
   int pre_axis_vec_ok, post_axis_vec_ok;  // row kernels: metric vector loads along x
   const T* halo_lo;
@@ -53,10 +54,9 @@ k_stencil_strided(const StencilArgs<T> a) {
       (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (unit >= a.nunits) return;
   const int lane = threadIdx.x & 31;
-  const int64_t wc = unit % a.nwc;
-  const int64_t t = unit / a.nwc;
-  const int64_t seg = t % a.nseg;
-  const int64_t o = t / a.nseg;
+  int64_t wc, t, seg, o;
+  xg_divmod(unit, a.nwc, a.small_units, t, wc);
+  xg_divmod(t, a.nseg, a.small_units, o, seg);
   const int64_t i = (wc * 32 + lane) * VEC;
   if (i >= a.inner) return;
 
@@ -65,109 +65,95 @@ k_stencil_strided(const StencilArgs<T> a) {
 
   const T* ibase = a.in + o * a.n * a.inner + i;
   T* obase = a.out + o * a.n_out * a.inner + i;
+  const bool has_pre = MET && a.pre.ptr != nullptr;
+  const bool has_post = MET && a.post.ptr != nullptr;
   int64_t pre_base = 0, post_base = 0;
+  XgInnerOff<VEC> pre_io, post_io;
   if (MET) {
-    if (a.pre.ptr) pre_base = xg_groups_offset(a.pre.outer, o);
-    if (a.post.ptr) post_base = xg_groups_offset(a.post.outer, o);
+    // everything that depends only on (o, i) is hoisted out of the march
+    if (has_pre) {
+      pre_base = xg_groups_offset(a.pre.outer, o);
+      pre_io = xg_inner_off<VEC>(a.pre, i);
+    }
+    if (has_post) {
+      post_base = xg_groups_offset(a.post.outer, o);
+      post_io = xg_inner_off<VEC>(a.post, i);
+    }
   }
 
   // A[s] = in[s] * pre[s], s in range
   auto loadA = [&](int64_t s) -> Pack {
     Pack v = xg_ld_stream<T, VEC>(ibase + s * a.inner);
-    if (MET && a.pre.ptr) {
-      Pack m = xg_ld_operand<T, VEC>(a.pre, pre_base + s * a.pre.axis_stride, i);
+    if (has_pre) {
+      Pack m = xg_ld_operand_at<T, VEC>(a.pre, pre_base + s * a.pre.axis_stride, pre_io);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) v.v[k] = v.v[k] * m.v[k];
     }
     return v;
   };
-  auto splat = [&](T x) -> Pack {
-    Pack v;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) v.v[k] = x;
-    return v;
-  };
-  // P[k]: the padded array, k in [0, n + lo + hi)
-  auto loadP = [&](int64_t k) -> Pack {
-    int64_t s = k - a.lo;
-    if (s < 0) {
-      if (a.halo_lo) return xg_ld_cached<T, VEC>(a.halo_lo + o * a.inner + i);
-      if (a.bc == XG_BC_FILL) return splat(a.fill);
-      if (a.bc == XG_BC_PERIODIC) {
-        s += a.n;
-      } else if (a.bc == XG_BC_EXTEND) {
-        s = 0;
-      } else {  // extrapolate: 2*A[0] - A[1]
-        Pack a0 = loadA(0), a1 = loadA(a.n > 1 ? 1 : 0), r;
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) r.v[q] = T(2) * a0.v[q] - a1.v[q];
-        return r;
-      }
-    } else if (s >= a.n) {
-      if (a.halo_hi) return xg_ld_cached<T, VEC>(a.halo_hi + o * a.inner + i);
-      if (a.bc == XG_BC_FILL) return splat(a.fill);
-      if (a.bc == XG_BC_PERIODIC) {
-        s -= a.n;
-      } else if (a.bc == XG_BC_EXTEND) {
-        s = a.n - 1;
-      } else {
-        Pack a0 = loadA(a.n - 1), a1 = loadA(a.n > 1 ? a.n - 2 : 0), r;
-#pragma unroll
-        for (int q = 0; q < VEC; ++q) r.v[q] = T(2) * a0.v[q] - a1.v[q];
-        return r;
-      }
-    }
-    return loadA(s);
-  };
   auto emit = [&](int64_t j, const Pack& lo_v, const Pack& hi_v) {
     Pack r;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) r.v[k] = xg_apply_op<T, OP>(lo_v.v[k], hi_v.v[k]);
-    if (MET && a.post.ptr) {
-      Pack m = xg_ld_operand<T, VEC>(a.post, post_base + j * a.post.axis_stride, i);
+    if (has_post) {
+      Pack m = xg_ld_operand_at<T, VEC>(a.post, post_base + j * a.post.axis_stride, post_io);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / m.v[k];
     }
     xg_st_stream<T, VEC>(obase + j * a.inner, r);
   };
 
-  // rows touched: P[j0 .. j1]; interior iff every s = k - lo lies in [0, n)
-  const bool interior = (j0 - a.lo >= 0) && (j1 - a.lo < a.n);
+  // P[k] with the boundary rule; only ever needed for the first row of the first segment
+  // (s = -1) and the last row of the last segment (s = n)
+  auto loadP = [&](int64_t k) -> Pack {
+    int64_t s = k - a.lo;
+    if (s >= 0 && s < a.n) return loadA(s);
+    const bool low = s < 0;
+    const T* halo = low ? a.halo_lo : a.halo_hi;
+    Pack r;
+    if (halo) return xg_ld_cached<T, VEC>(halo + o * a.inner + i);
+    if (a.bc == XG_BC_FILL) {
+#pragma unroll
+      for (int k2 = 0; k2 < VEC; ++k2) r.v[k2] = a.fill;
+      return r;
+    }
+    if (a.bc == XG_BC_PERIODIC) return loadA(low ? s + a.n : s - a.n);
+    if (a.bc == XG_BC_EXTEND) return loadA(low ? 0 : a.n - 1);
+    // extrapolate: 2*A[edge] - A[next]
+    const int64_t e = low ? 0 : a.n - 1;
+    const int64_t e2 = a.n > 1 ? (low ? 1 : a.n - 2) : e;
+    Pack a0 = loadA(e), a1 = loadA(e2);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) r.v[q] = T(2) * a0.v[q] - a1.v[q];
+    return r;
+  };
+
+  // Row j needs P[j] (carried in registers) and P[j+1] = A[j+1-lo].  Since lo <= 1 the source
+  // index j+1-lo is never negative; it is in range while j < n+lo-1.  So the whole march is the
+  // branch-free unrolled loop, plus one boundary-aware load at each end.
+  Pack prev = loadP(j0);
+  const int64_t jm = (j1 < a.n + a.lo - 1) ? j1 : (a.n + a.lo - 1);
   int64_t j = j0;
-  if (interior) {
-    Pack prev = loadA(j0 - a.lo);
-    for (; j + U <= j1; j += U) {
-      Pack cur[U];
+  for (; j + U <= jm; j += U) {
+    Pack cur[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) cur[u] = loadA(j + u + 1 - a.lo);
+    for (int u = 0; u < U; ++u) cur[u] = loadA(j + u + 1 - a.lo);
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        emit(j + u, prev, cur[u]);
-        prev = cur[u];
-      }
+    for (int u = 0; u < U; ++u) {
+      emit(j + u, prev, cur[u]);
+      prev = cur[u];
     }
-    for (; j < j1; ++j) {
-      Pack cur = loadA(j + 1 - a.lo);
-      emit(j, prev, cur);
-      prev = cur;
-    }
-  } else {
-    Pack prev = loadP(j0);
-    for (; j + U <= j1; j += U) {
-      Pack cur[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) cur[u] = loadP(j + u + 1);
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        emit(j + u, prev, cur[u]);
-        prev = cur[u];
-      }
-    }
-    for (; j < j1; ++j) {
-      Pack cur = loadP(j + 1);
-      emit(j, prev, cur);
-      prev = cur;
-    }
+  }
+  for (; j < jm; ++j) {
+    Pack cur = loadA(j + 1 - a.lo);
+    emit(j, prev, cur);
+    prev = cur;
+  }
+#pragma unroll 1
+  for (; j < j1; ++j) {  // at most one row: the upper halo
+    Pack cur = loadP(j + 1);
+    emit(j, prev, cur);
+    prev = cur;
   }
 }
 
@@ -265,8 +251,8 @@ k_stencil_row_vec(const StencilArgs<T> a) {
       (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
   if (unit >= a.nunits) return;  // warp-uniform
   const int lane = threadIdx.x & 31;
-  const int64_t c = unit % a.nwc;
-  const int64_t r = unit / a.nwc;
+  int64_t c, r;
+  xg_divmod(unit, a.nwc, a.small_units, r, c);
   const int64_t nv = a.n / VEC;
   RowAccess<T, MET> ra(a, r);
   T* orow = a.out + r * a.n;  // n_out == n
@@ -347,6 +333,7 @@ int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
   a.J = J;
   a.nseg = xg_ceil_div(a.n_out, J);
   a.nunits = a.outer * a.nseg * a.nwc;
+  a.small_units = a.nunits < (1ll << 31);
   const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2: grid too large");
   k_stencil_strided<T, VEC, OP, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
@@ -359,6 +346,7 @@ int launch_row_vec(StencilArgs<T>& a, cudaStream_t st) {
   const int64_t nv = a.n / VEC;
   a.nwc = xg_ceil_div(nv, 32 * U);
   a.nunits = a.outer * a.nwc;
+  a.small_units = a.nunits < (1ll << 31);
   const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2: grid too large");
   k_stencil_row_vec<T, VEC, OP, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
@@ -442,6 +430,7 @@ int stencil2_typed(int op, const void* in, void* out, int ndim, const int64_t* s
   a.halo_hi = static_cast<const T*>(halo_hi);
   a.J = 0;
   a.nseg = a.nwc = a.nunits = 0;
+  a.small_units = false;
   if (v.n == 0) return xg_fail(XG_EINVAL, "xg_stencil2: empty operated axis");
   if (v.outer == 0 || v.inner == 0 || a.n_out <= 0) return XG_OK;  // nothing to write
 

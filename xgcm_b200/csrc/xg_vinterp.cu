@@ -5,9 +5,20 @@
 // and flip (:27-31), np.interp (:33; numba's port of numpy's arr_interp incl.
 // binary_search_with_guess and the NaN retry), edge masking (:35-41).  All
 // arithmetic is fp64 and rounded once to the field dtype, as in the reference.
-// The guess-carrying search is reproduced literally so that columns whose theta
-// contains NaNs (where np.interp's answer depends on the probe sequence) give
-// the same values.
+//
+// Two kernels:
+//   k_vinterp_shared   theta AND target are shared 1-D vectors (the default
+//       `Grid.transform(da, 'Z', levels)` case: theta = the depth coordinate).
+//       The search is column independent, so each block computes the plan
+//       (interval index j, fp64 x, mask) of every target ONCE into shared memory —
+//       by parallel bisection when theta is NaN-free and sorted (then the guess
+//       path of np.interp cannot change the answer), otherwise by one thread
+//       replaying binary_search_with_guess literally — and the columns only do
+//       slope * (x - xj) + yj with the interval memoised (one fp64 divide per
+//       interval actually used, not per target).
+//   k_vinterp_columns  theta (or target) varies per column: lane = column,
+//       literal guess-carrying search per column so that NaN-containing or
+//       non-monotonic theta give the reference's (path dependent) values.
 //
 // Layout: a warp owns 32 adjacent columns (lane = column, coalesced along the
 // contiguous dim for every level); the outputs of 32 targets x 32 columns are
@@ -21,18 +32,20 @@
 
 namespace {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 8;
 constexpr int kTile = 32;
 constexpr int LIKELY_IN_CACHE_SIZE = 8;
 
 template <typename T>
 struct InterpArgs {
   const T* phi;
-  const T* target;
   T* out;
   int64_t outer, n, inner, m;
   XgOperand theta;
+  XgOperand target;  // levels: shared 1-D vector or one vector per column (axis_stride = level stride)
   int mask_edges, bypass_checks, logarithmic;
+  int64_t ntiles;    // column tiles of 32
+  bool small_cols;   // outer * inner < 2^31
 };
 
 template <typename T>
@@ -42,65 +55,228 @@ __device__ __forceinline__ float xg_log<float>(float x) { return logf(x); }
 template <>
 __device__ __forceinline__ double xg_log<double>(double x) { return log(x); }
 
-template <typename T>
-struct Column {
-  const T* phi;     // + k * phi_stride
-  const T* theta;   // + k * theta_stride
-  int64_t phi_stride, theta_stride, n;
-  bool flip, logarithmic;
-  __device__ __forceinline__ T theta_raw(int64_t k) const {
-    T v = __ldg(theta + k * theta_stride);
-    return logarithmic ? xg_log<T>(v) : v;  // transform.py:82-84, in the field dtype
-  }
-  __device__ __forceinline__ double X(int64_t k) const {
-    return (double)theta_raw(flip ? n - 1 - k : k);
-  }
-  __device__ __forceinline__ double Y(int64_t k) const {
-    return (double)__ldg(phi + (flip ? n - 1 - k : k) * phi_stride);
-  }
-};
-
-// numba/np: binary_search_with_guess (compiled_base.c), literal port
-template <typename T>
-__device__ int64_t search_with_guess(double key, const Column<T>& c, int64_t len, int64_t guess) {
-  int64_t imin = 0, imax = len;
-  if (key > c.X(len - 1)) return len;
-  if (key < c.X(0)) return -1;
+// numba/np binary_search_with_guess (compiled_base.c), literal port over an accessor X(k)
+template <typename F>
+__device__ __forceinline__ int search_with_guess(double key, F X, int len, int guess) {
+  int imin = 0, imax = len;
+  if (key > X(len - 1)) return len;
+  if (key < X(0)) return -1;
   if (len <= 4) {
-    int64_t i = 1;
-    while (i < len && key >= c.X(i)) ++i;
+    int i = 1;
+    while (i < len && key >= X(i)) ++i;
     return i - 1;
   }
   if (guess > len - 3) guess = len - 3;
   if (guess < 1) guess = 1;
-  if (key < c.X(guess)) {
-    if (key < c.X(guess - 1)) {
+  if (key < X(guess)) {
+    if (key < X(guess - 1)) {
       imax = guess - 1;
-      if (guess > LIKELY_IN_CACHE_SIZE && key >= c.X(guess - LIKELY_IN_CACHE_SIZE))
+      if (guess > LIKELY_IN_CACHE_SIZE && key >= X(guess - LIKELY_IN_CACHE_SIZE))
         imin = guess - LIKELY_IN_CACHE_SIZE;
     } else {
       return guess - 1;
     }
   } else {
-    if (key < c.X(guess + 1)) return guess;
-    if (key < c.X(guess + 2)) return guess + 1;
+    if (key < X(guess + 1)) return guess;
+    if (key < X(guess + 2)) return guess + 1;
     imin = guess + 2;
-    if (guess < len - LIKELY_IN_CACHE_SIZE - 1 && key < c.X(guess + LIKELY_IN_CACHE_SIZE))
+    if (guess < len - LIKELY_IN_CACHE_SIZE - 1 && key < X(guess + LIKELY_IN_CACHE_SIZE))
       imax = guess + LIKELY_IN_CACHE_SIZE;
   }
   while (imin < imax) {
-    const int64_t imid = imin + ((imax - imin) >> 1);
-    if (key >= c.X(imid)) imin = imid + 1;
+    const int imid = imin + ((imax - imin) >> 1);
+    if (key >= X(imid)) imin = imid + 1;
     else imax = imid;
   }
   return imin - 1;
 }
 
+// the arithmetic of np.interp for one target given its interval (fp64, no contraction)
+__device__ __forceinline__ double interp_value(double x, double xj, double xj1, double yj, double yj1,
+                                               double slope) {
+  double res = slope * (x - xj) + yj;
+  if (res != res) {
+    res = slope * (x - xj1) + yj1;
+    if (res != res && yj == yj1) res = yj;
+  }
+  return res;
+}
+
+// transposed write-out of a 32-column x nt-target tile
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32) k_vinterp(const InterpArgs<T> a) {
+__device__ __forceinline__ void store_tile(T (*tile)[kTile + 1], T* out, int64_t col0, int ncol_here,
+                                           int64_t m, int64_t t0, int nt, int lane) {
+  __syncwarp();
+  if (lane < nt) {
+    T* o = out + col0 * m + t0 + lane;
+#pragma unroll 4
+    for (int cc = 0; cc < ncol_here; ++cc) __stcs(o + (int64_t)cc * m, tile[cc][lane]);
+  }
+  __syncwarp();
+}
+
+// ---------------------------------------------------------------------------
+// shared theta / shared target
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs<T> a) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int n = (int)a.n, m = (int)a.m;
+  // layout: X[n] | xt[m] | tile[kWarps][32][33] | j[m] | flags
+  double* Xs = reinterpret_cast<double*>(smem_raw);
+  double* xt = Xs + n;
+  T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(xt + m);
+  int* js = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
+                                   sizeof(T) * kWarps * kTile * (kTile + 1));
+  int* flags = js + m;  // [0]=flip [1]=fast_ok ; masks are folded into js (see below)
+  unsigned char* masked = reinterpret_cast<unsigned char*>(flags + 2);
+  const int tid = threadIdx.x;
+  const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
+  const T* target = reinterpret_cast<const T*>(a.target.ptr);
+  const int64_t tstride = a.theta.axis_stride;
+
+  // ---- plan, once per block -------------------------------------------------
+  for (int k = tid; k < n; k += blockDim.x) {
+    T v = __ldg(theta + k * tstride);
+    if (a.logarithmic) v = xg_log<T>(v);  // transform.py:82-84, in the field dtype
+    Xs[k] = (double)v;
+  }
+  __syncthreads();
+  __shared__ double s_tmin, s_tmax;
+  if (tid == 0) {
+    int flip = 0;
+    if (!a.bypass_checks) {  // transform.py:27-31
+      int kf = 0, kl = n - 1;
+      while (kf < n && Xs[kf] != Xs[kf]) ++kf;
+      while (kl >= 0 && Xs[kl] != Xs[kl]) --kl;
+      if (kf < n && Xs[kl] < Xs[kf]) flip = 1;
+    }
+    bool any = false, nan = false, sorted = true;
+    double tmin = 0.0, tmax = 0.0, prev = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double v = Xs[flip ? n - 1 - k : k];
+      if (v != v) { nan = true; continue; }
+      if (!any) { tmin = tmax = v; any = true; }
+      else { tmin = v < tmin ? v : tmin; tmax = v > tmax ? v : tmax; if (v < prev) sorted = false; }
+      prev = v;
+    }
+    if (!any) tmin = tmax = NAN;
+    s_tmin = tmin;
+    s_tmax = tmax;
+    flags[0] = flip;
+    flags[1] = (!nan && sorted) ? 1 : 0;
+  }
+  __syncthreads();
+  const int flip = flags[0];
+  if (flip) {  // reverse in place
+    for (int k = tid; k < n / 2; k += blockDim.x) {
+      const double t0 = Xs[k];
+      Xs[k] = Xs[n - 1 - k];
+      Xs[n - 1 - k] = t0;
+    }
+    __syncthreads();
+  }
+  auto X = [&](int k) -> double { return Xs[k]; };
+  for (int t = tid; t < m; t += blockDim.x) {
+    T v = __ldg(target + t * a.target.axis_stride);
+    if (a.logarithmic) v = xg_log<T>(v);
+    const double x = (double)v;
+    xt[t] = x;
+    masked[t] = (a.mask_edges && (x < s_tmin || x > s_tmax)) ? 1 : 0;  // transform.py:38-41
+    if (flags[1] && n > 1 && x == x) {
+      // NaN-free sorted theta: binary_search_with_guess returns the largest j with X[j] <= x
+      // whatever the guess, so every target can be searched independently
+      int j;
+      if (x > Xs[n - 1]) j = n;
+      else if (x < Xs[0]) j = -1;
+      else {
+        int lo = 0, hi = n;
+        while (lo < hi) {
+          const int mid = lo + ((hi - lo) >> 1);
+          if (x >= Xs[mid]) lo = mid + 1;
+          else hi = mid;
+        }
+        j = lo - 1;
+      }
+      js[t] = j;
+    }
+  }
+  __syncthreads();
+  if (!flags[1] && n > 1 && tid == 0) {  // literal replay (guess carried from target to target)
+    int guess = 0;
+    for (int t = 0; t < m; ++t) {
+      const double x = xt[t];
+      if (x != x) { js[t] = 0; continue; }
+      const int j = search_with_guess(x, X, n, guess);
+      guess = j;
+      js[t] = j;
+    }
+  }
+  __syncthreads();
+
+  // ---- columns ----------------------------------------------------------------
+  const int w = tid >> 5, lane = tid & 31;
+  T(*tile)[kTile + 1] = tiles[w];
+  const int64_t ncols = a.outer * a.inner;
+  for (int64_t ct = (int64_t)blockIdx.x * kWarps + w; ct < a.ntiles; ct += (int64_t)gridDim.x * kWarps) {
+    const int64_t col0 = ct * kTile;
+    const int64_t col = col0 + lane;
+    const bool col_ok = col < ncols;
+    const int ncol_here = (int)((ncols - col0 < kTile) ? (ncols - col0) : kTile);
+    const T* phi = a.phi;
+    if (col_ok) {
+      int64_t o, i;
+      xg_divmod(col, a.inner, a.small_cols, o, i);
+      phi = a.phi + o * a.n * a.inner + i;
+    }
+    auto Y = [&](int k) -> double { return (double)__ldg(phi + (int64_t)(flip ? n - 1 - k : k) * a.inner); };
+    int cj = -2;  // memoised interval
+    double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
+    const double y_first = col_ok ? Y(0) : 0.0;
+    const double y_last = col_ok ? Y(n - 1) : 0.0;
+    for (int t0 = 0; t0 < m; t0 += kTile) {
+      const int nt = (m - t0 < kTile) ? (m - t0) : kTile;
+      if (col_ok) {
+        for (int tt = 0; tt < nt; ++tt) {
+          const int t = t0 + tt;
+          const double x = xt[t];
+          double res;
+          if (n == 1) res = y_first;  // np.interp: dx.size == 1 -> full(dy[0])
+          else if (x != x) res = x;
+          else {
+            const int j = js[t];
+            if (j == -1) res = y_first;
+            else if (j >= n - 1) res = y_last;  // j == n (right of range) or j == n-1
+            else {
+              if (j != cj) {
+                cj = j;
+                xj = Xs[j];
+                xj1 = Xs[j + 1];
+                yj = Y(j);
+                yj1 = Y(j + 1);
+                slope = (yj1 - yj) / (xj1 - xj);
+              }
+              res = (xj == x) ? yj : interp_value(x, xj, xj1, yj, yj1, slope);
+            }
+          }
+          if (masked[t]) res = NAN;
+          tile[lane][tt] = (T)res;
+        }
+      }
+      store_tile<T>(tile, a.out, col0, ncol_here, a.m, t0, nt, lane);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// per-column theta and / or target
+// ---------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kWarps * 32) k_vinterp_columns(const InterpArgs<T> a) {
   __shared__ T tile_s[kWarps][kTile][kTile + 1];
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int n = (int)a.n, m = (int)a.m;
   const int64_t ncols = a.outer * a.inner;
   const int64_t col0 = ((int64_t)blockIdx.x * kWarps + w) * kTile;
   if (col0 >= ncols) return;  // warp-uniform
@@ -109,103 +285,104 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp(const InterpArgs<T> a) 
   const bool col_ok = col < ncols;
   const int ncol_here = (int)((ncols - col0 < kTile) ? (ncols - col0) : kTile);
 
-  Column<T> c;
-  c.n = a.n;
-  c.flip = false;
-  c.logarithmic = a.logarithmic != 0;
-  c.phi_stride = a.inner;
-  c.theta_stride = a.theta.axis_stride;
-  c.phi = a.phi;
-  c.theta = reinterpret_cast<const T*>(a.theta.ptr);
-  double tmin = 0.0, tmax = 0.0;
+  const T* phi = a.phi;
+  const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
+  const T* tgt = reinterpret_cast<const T*>(a.target.ptr);
+  const int64_t ts = a.theta.axis_stride, ps = a.inner;
+  const bool logarithmic = a.logarithmic != 0;
+  bool flip = false;
+  T tmin = T(0), tmax = T(0);
   if (col_ok) {
-    const int64_t o = col / a.inner;
-    const int64_t i = col - o * a.inner;
-    c.phi = a.phi + o * a.n * a.inner + i;
+    int64_t o, i;
+    xg_divmod(col, a.inner, a.small_cols, o, i);
+    phi = a.phi + o * a.n * a.inner + i;
     int64_t toff = xg_groups_offset(a.theta.outer, o);
     if (a.theta.inner_mode == XG_IM_CONTIG) toff += i;
     else if (a.theta.inner_mode == XG_IM_GENERIC) toff += xg_groups_offset(a.theta.inner, i);
-    c.theta = reinterpret_cast<const T*>(a.theta.ptr) + toff;
-    if (!a.bypass_checks) {
-      // transform.py:27-31: sign test on the NaN-filtered theta
-      int64_t kf = 0, kl = a.n - 1;
-      while (kf < a.n && xg_isnan(c.theta_raw(kf))) ++kf;
-      while (kl >= 0 && xg_isnan(c.theta_raw(kl))) --kl;
-      if (kf < a.n && c.theta_raw(kl) < c.theta_raw(kf)) c.flip = true;
+    theta += toff;
+    int64_t goff = xg_groups_offset(a.target.outer, o);
+    if (a.target.inner_mode == XG_IM_CONTIG) goff += i;
+    else if (a.target.inner_mode == XG_IM_GENERIC) goff += xg_groups_offset(a.target.inner, i);
+    tgt += goff;
+  }
+  // raw (unflipped) theta in the field dtype; comparisons in T are exact for T -> double
+  auto TH = [&](int k) -> T {
+    T v = __ldg(theta + (int64_t)k * ts);
+    return logarithmic ? xg_log<T>(v) : v;
+  };
+  if (col_ok) {
+    if (!a.bypass_checks) {  // transform.py:27-31: sign test on the NaN-filtered theta
+      int kf = 0, kl = n - 1;
+      while (kf < n && xg_isnan(TH(kf))) ++kf;
+      while (kl >= 0 && xg_isnan(TH(kl))) --kl;
+      if (kf < n && TH(kl) < TH(kf)) flip = true;
     }
-    if (a.mask_edges) {
-      // transform.py:36-37 nanmax / nanmin (NaN if the column is all-NaN)
+    if (a.mask_edges) {  // transform.py:36-37 nanmax / nanmin (NaN if the column is all-NaN)
       bool any = false;
-      for (int64_t k = 0; k < a.n; ++k) {
-        const double v = (double)c.theta_raw(k);
-        if (v != v) continue;
+      for (int k = 0; k < n; ++k) {
+        const T v = TH(k);
+        if (xg_isnan(v)) continue;
         if (!any) { tmin = tmax = v; any = true; }
         else { tmin = v < tmin ? v : tmin; tmax = v > tmax ? v : tmax; }
       }
-      if (!any) tmin = tmax = NAN;
+      if (!any) tmin = tmax = T(NAN);
     }
   }
+  auto X = [&](int k) -> double { return (double)TH(flip ? n - 1 - k : k); };
+  auto Y = [&](int k) -> double { return (double)__ldg(phi + (int64_t)(flip ? n - 1 - k : k) * ps); };
 
-  int64_t guess = 0;
-  for (int64_t t0 = 0; t0 < a.m; t0 += kTile) {
-    const int nt = (int)((a.m - t0 < kTile) ? (a.m - t0) : kTile);
+  int guess = 0, cj = -2;
+  double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
+  for (int t0 = 0; t0 < m; t0 += kTile) {
+    const int nt = (m - t0 < kTile) ? (m - t0) : kTile;
     if (col_ok) {
       for (int tt = 0; tt < nt; ++tt) {
-        T xt = __ldg(a.target + t0 + tt);
-        if (c.logarithmic) xt = xg_log<T>(xt);
-        const double x = (double)xt;
+        T xv = __ldg(tgt + (int64_t)(t0 + tt) * a.target.axis_stride);
+        if (logarithmic) xv = xg_log<T>(xv);
+        const double x = (double)xv;
         double res;
-        if (a.n == 1) {
-          res = c.Y(0);  // np.interp: dx.size == 1 -> full(dy[0])
+        if (n == 1) {
+          res = Y(0);  // np.interp: dx.size == 1 -> full(dy[0])
         } else if (x != x) {
           res = x;
         } else {
-          const int64_t j = search_with_guess<T>(x, c, a.n, guess);
+          const int j = search_with_guess(x, X, n, guess);
           guess = j;
-          if (j == -1) res = c.Y(0);
-          else if (j == a.n) res = c.Y(a.n - 1);
-          else if (j == a.n - 1) res = c.Y(j);
+          if (j == -1) res = Y(0);
+          else if (j >= n - 1) res = Y(n - 1);
           else {
-            const double xj = c.X(j);
-            const double yj = c.Y(j);
-            if (xj == x) {
-              res = yj;
-            } else {
-              const double xj1 = c.X(j + 1);
-              const double yj1 = c.Y(j + 1);
-              const double slope = (yj1 - yj) / (xj1 - xj);
-              res = slope * (x - xj) + yj;
-              if (res != res) {
-                res = slope * (x - xj1) + yj1;
-                if (res != res && yj == yj1) res = yj;
-              }
+            if (j != cj) {
+              cj = j;
+              xj = X(j);
+              xj1 = X(j + 1);
+              yj = Y(j);
+              yj1 = Y(j + 1);
+              slope = (yj1 - yj) / (xj1 - xj);
             }
+            res = (xj == x) ? yj : interp_value(x, xj, xj1, yj, yj1, slope);
           }
         }
-        if (a.mask_edges && (x < tmin || x > tmax)) res = NAN;  // transform.py:38-41
+        if (a.mask_edges && (xv < tmin || xv > tmax)) res = NAN;  // transform.py:38-41
         tile[lane][tt] = (T)res;
       }
     }
-    __syncwarp();
-    if (lane < nt) {
-      for (int cc = 0; cc < ncol_here; ++cc)
-        __stcs(a.out + (col0 + cc) * a.m + t0 + lane, tile[cc][lane]);
-    }
-    __syncwarp();
+    store_tile<T>(tile, a.out, col0, ncol_here, a.m, t0, nt, lane);
   }
 }
 
 template <typename T>
 int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strides,
-                  const void* target, int64_t m, void* out, int ndim, const int64_t* shape,
-                  int axis, int mask_edges, int bypass_checks, int logarithmic, cudaStream_t st) {
+                  const void* target, const int64_t* target_strides, int64_t m, void* out,
+                  int ndim, const int64_t* shape, int axis, int mask_edges, int bypass_checks,
+                  int logarithmic, cudaStream_t st) {
   XgView v;
   int rc = xg_collapse_view(ndim, shape, axis, &v);
   if (rc) return rc;
   if (v.n == 0) return xg_fail(XG_EINVAL, "xg_vinterp_linear: array of sample points is empty");
+  if (v.n >= (1ll << 31) || m >= (1ll << 31))
+    return xg_fail(XG_EINVAL, "xg_vinterp_linear: more than 2^31 levels");
   InterpArgs<T> a;
   a.phi = static_cast<const T*>(phi);
-  a.target = static_cast<const T*>(target);
   a.out = static_cast<T*>(out);
   a.outer = v.outer;
   a.n = v.n;
@@ -217,32 +394,66 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
   rc = xg_make_operand(theta, theta_strides, ndim, shape, axis, 1, sizeof(T), &a.theta,
                        "xg_vinterp_linear(theta)");
   if (rc) return rc;
+  {
+    int64_t tshape[XG_MAX_NDIM], tstr[XG_MAX_NDIM];
+    for (int d = 0; d < ndim; ++d) {
+      tshape[d] = shape[d];
+      tstr[d] = target_strides ? target_strides[d] : 0;
+    }
+    tshape[axis] = m;
+    if (!target_strides) tstr[axis] = 1;
+    rc = xg_make_operand(target, tstr, ndim, tshape, axis, 1, sizeof(T), &a.target,
+                         "xg_vinterp_linear(target)");
+    if (rc) return rc;
+    if (m == 1) a.target.axis_stride = 0;
+  }
   if (shape[axis] > 1 && a.theta.axis_stride == 0)
     return xg_fail(XG_EINVAL, "xg_vinterp_linear: theta must vary along the operated axis");
   const int64_t ncols = v.outer * v.inner;
   if (ncols == 0 || m == 0) return XG_OK;
-  const int64_t blocks = xg_ceil_div(xg_ceil_div(ncols, kTile), kWarps);
+  a.ntiles = xg_ceil_div(ncols, kTile);
+  a.small_cols = ncols < (1ll << 31);
+
+  auto all_bcast = [](const XgOperand& op) {
+    bool outer0 = true;
+    for (int k = 0; k < op.outer.n; ++k) outer0 = outer0 && op.outer.stride[k] == 0;
+    return outer0 && op.inner_mode == XG_IM_BCAST;
+  };
+  const size_t plan_bytes = (size_t)(v.n + m) * sizeof(double) +
+                            sizeof(T) * kWarps * kTile * (kTile + 1) + (size_t)(m + 2) * sizeof(int) +
+                            (size_t)m + 16;
+  if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)plan_bytes);
+    if (e != cudaSuccess)
+      return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    int64_t blocks = xg_ceil_div(a.ntiles, kWarps);
+    if (blocks > 148 * 8) blocks = 148 * 8;  // persistent-ish: the plan is amortised over many tiles
+    k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
+    return xg_check_launch("xg_vinterp_linear(shared)");
+  }
+  const int64_t blocks = xg_ceil_div(a.ntiles, kWarps);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_vinterp_linear: grid too large");
-  k_vinterp<T><<<(unsigned)blocks, kWarps * 32, 0, st>>>(a);
-  return xg_check_launch("xg_vinterp_linear");
+  k_vinterp_columns<T><<<(unsigned)blocks, kWarps * 32, 0, st>>>(a);
+  return xg_check_launch("xg_vinterp_linear(columns)");
 }
 
 }  // namespace
 
 extern "C" int xg_vinterp_linear(int dtype, const void* phi, const void* theta,
-                                 const int64_t* theta_strides, const void* target, int64_t m,
-                                 void* out, int ndim, const int64_t* shape, int axis,
-                                 int mask_edges, int bypass_checks, int logarithmic,
-                                 void* stream) {
+                                 const int64_t* theta_strides, const void* target,
+                                 const int64_t* target_strides, int64_t m, void* out, int ndim,
+                                 const int64_t* shape, int axis, int mask_edges, int bypass_checks,
+                                 int logarithmic, void* stream) {
   if (!phi || !theta || !theta_strides || !target || !out || !shape)
     return xg_fail(XG_EINVAL, "xg_vinterp_linear: null pointer");
   if (m < 0) return xg_fail(XG_EINVAL, "xg_vinterp_linear: negative number of target levels");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == XG_F32)
-    return vinterp_typed<float>(phi, theta, theta_strides, target, m, out, ndim, shape, axis,
-                                mask_edges, bypass_checks, logarithmic, st);
+    return vinterp_typed<float>(phi, theta, theta_strides, target, target_strides, m, out, ndim,
+                                shape, axis, mask_edges, bypass_checks, logarithmic, st);
   if (dtype == XG_F64)
-    return vinterp_typed<double>(phi, theta, theta_strides, target, m, out, ndim, shape, axis,
-                                 mask_edges, bypass_checks, logarithmic, st);
+    return vinterp_typed<double>(phi, theta, theta_strides, target, target_strides, m, out, ndim,
+                                 shape, axis, mask_edges, bypass_checks, logarithmic, st);
   return xg_fail(XG_EINVAL, "xg_vinterp_linear: dtype must be XG_F32 or XG_F64");
 }

@@ -26,6 +26,7 @@ struct ReduceArgs {
   int mode, skipna;
   XgOperand w;
   int64_t nvec_inner;
+  bool small_index;
 };
 
 template <typename T, int VEC, bool HASW, int U>
@@ -33,11 +34,16 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
   typedef XgPack<T, VEC> Pack;
   const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (g >= a.outer * a.nvec_inner) return;
-  const int64_t o = g / a.nvec_inner;
-  const int64_t i = (g - o * a.nvec_inner) * VEC;
+  int64_t o, iv;
+  xg_divmod(g, a.nvec_inner, a.small_index, o, iv);
+  const int64_t i = iv * VEC;
   const T* ibase = a.in + o * a.n * a.inner + i;
   int64_t w_base = 0;
-  if (HASW) w_base = xg_groups_offset(a.w.outer, o);
+  XgInnerOff<VEC> w_io;
+  if (HASW) {
+    w_base = xg_groups_offset(a.w.outer, o);
+    w_io = xg_inner_off<VEC>(a.w, i);
+  }
   Pack num, den;
 #pragma unroll
   for (int q = 0; q < VEC; ++q) num.v[q] = den.v[q] = T(0);
@@ -64,14 +70,14 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       v[u] = xg_ld_stream<T, VEC>(ibase + (k + u) * a.inner);
-      if (HASW) m[u] = xg_ld_operand<T, VEC>(a.w, w_base + (k + u) * a.w.axis_stride, i);
+      if (HASW) m[u] = xg_ld_operand_at<T, VEC>(a.w, w_base + (k + u) * a.w.axis_stride, w_io);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) step(v[u], m[u]);
   }
   for (; k < a.n; ++k) {
     Pack v = xg_ld_stream<T, VEC>(ibase + k * a.inner), m;
-    if (HASW) m = xg_ld_operand<T, VEC>(a.w, w_base + k * a.w.axis_stride, i);
+    if (HASW) m = xg_ld_operand_at<T, VEC>(a.w, w_base + k * a.w.axis_stride, w_io);
     step(v, m);
   }
   Pack r;
@@ -128,6 +134,7 @@ int reduce_launch(ReduceArgs<T>& a, cudaStream_t st) {
     if (vec_ok && a.outer * (a.inner / VEC) < 148 * 512) vec_ok = false;
     a.nvec_inner = vec_ok ? a.inner / VEC : a.inner;
     if (!vec_ok) a.w.vec_ok = 0;
+    a.small_index = a.outer * a.nvec_inner < (1ll << 31);
     const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
     if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_wreduce: grid too large");
     if (vec_ok)
@@ -158,6 +165,7 @@ int wreduce_typed(const void* in, const void* weight, const int64_t* w_strides, 
   a.mode = mode;
   a.skipna = skipna ? 1 : 0;
   a.nvec_inner = 0;
+  a.small_index = false;
   rc = xg_make_operand(weight, w_strides, ndim, shape, axis, VEC, sizeof(T), &a.w,
                        "xg_wreduce(weight)");
   if (rc) return rc;

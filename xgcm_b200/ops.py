@@ -257,7 +257,9 @@ def vinterp_linear(phi: torch.Tensor, theta: torch.Tensor, target: torch.Tensor,
                    mask_edges: bool = False, bypass_checks: bool = False,
                    logarithmic: bool = False) -> torch.Tensor:
     """Per-column linear interpolation onto ``target`` levels; new dim LAST
-    (transform.py:15-85).  ``theta`` broadcasts against ``phi``."""
+    (transform.py:15-85).  ``theta`` broadcasts against ``phi``.  ``target`` is either a
+    shared 1-D level vector or an array whose leading dims broadcast against the column
+    dims of ``phi`` (shape-without-axis) and whose LAST dim holds the levels."""
     lib = _capi.load()
     _require_cuda(phi, "phi")
     _require_cuda(theta, "theta")
@@ -266,19 +268,33 @@ def vinterp_linear(phi: torch.Tensor, theta: torch.Tensor, target: torch.Tensor,
     if not (phi.dtype == theta.dtype == target.dtype == torch.float32):
         phi, theta, target = phi.to(torch.float64), theta.to(torch.float64), target.to(torch.float64)
     phi = phi.contiguous()
-    target = target.contiguous()
-    if target.dim() != 1:
-        raise ValueError("target levels must be 1-D")
     axis = _norm_axis(axis, phi.dim())
     shape = list(phi.shape)
+    m = int(target.shape[-1]) if target.dim() else 1
     keep, th_ptr, th_st = _operand(theta, shape, phi, "theta")
-    out_shape = [s for d, s in enumerate(shape) if d != axis] + [int(target.numel())]
+    col_shape = [s for d, s in enumerate(shape) if d != axis]
+    tg_st = None
+    if target.dim() <= 1:
+        target = target.reshape(-1).contiguous()
+    else:
+        try:
+            tb = target.expand(tuple(col_shape) + (m,))
+        except RuntimeError as err:
+            raise ValueError(
+                f"target of shape {tuple(target.shape)} does not broadcast to columns {tuple(col_shape)} + (m,)"
+            ) from err
+        st = list(tb.stride())
+        col_st = [0 if s == 1 else t for s, t in zip(col_shape, st[:-1])]
+        full = col_st[:axis] + [st[-1]] + col_st[axis:]
+        tg_st = _capi.i64_array(full)
+        target = tb
+    out_shape = col_shape + [m]
     out = torch.empty(out_shape, dtype=phi.dtype, device=phi.device)
     if out.numel():
         with torch.cuda.device(phi.device):
             rc = lib.xg_vinterp_linear(
-                _dtype_code(phi), phi.data_ptr(), th_ptr, th_st, target.data_ptr(),
-                int(target.numel()), out.data_ptr(), phi.dim(), _capi.i64_array(shape), axis,
+                _dtype_code(phi), phi.data_ptr(), th_ptr, th_st, target.data_ptr(), tg_st,
+                m, out.data_ptr(), phi.dim(), _capi.i64_array(shape), axis,
                 int(bool(mask_edges)), int(bool(bypass_checks)), int(bool(logarithmic)),
                 _stream_ptr(phi),
             )
