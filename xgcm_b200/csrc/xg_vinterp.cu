@@ -271,14 +271,16 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
 // ---------------------------------------------------------------------------
 // per-column theta and / or target
 // ---------------------------------------------------------------------------
+constexpr int kWarpsCol = 4;  // static smem: 4 x 32 x 33 x 8 B = 33 KiB for fp64
+
 template <typename T>
-__global__ void __launch_bounds__(kWarps * 32) k_vinterp_columns(const InterpArgs<T> a) {
-  __shared__ T tile_s[kWarps][kTile][kTile + 1];
+__global__ void __launch_bounds__(kWarpsCol * 32) k_vinterp_columns(const InterpArgs<T> a) {
+  __shared__ T tile_s[kWarpsCol][kTile][kTile + 1];
   const int w = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int n = (int)a.n, m = (int)a.m;
   const int64_t ncols = a.outer * a.inner;
-  const int64_t col0 = ((int64_t)blockIdx.x * kWarps + w) * kTile;
+  const int64_t col0 = ((int64_t)blockIdx.x * kWarpsCol + w) * kTile;
   if (col0 >= ncols) return;  // warp-uniform
   T(*tile)[kTile + 1] = tile_s[w];
   const int64_t col = col0 + lane;
@@ -432,9 +434,9 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
     k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
     return xg_check_launch("xg_vinterp_linear(shared)");
   }
-  const int64_t blocks = xg_ceil_div(a.ntiles, kWarps);
+  const int64_t blocks = xg_ceil_div(a.ntiles, kWarpsCol);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_vinterp_linear: grid too large");
-  k_vinterp_columns<T><<<(unsigned)blocks, kWarps * 32, 0, st>>>(a);
+  k_vinterp_columns<T><<<(unsigned)blocks, kWarpsCol * 32, 0, st>>>(a);
   return xg_check_launch("xg_vinterp_linear(columns)");
 }
 
