@@ -204,43 +204,58 @@ __device__ __forceinline__ XgPack<T, VEC> xg_ld_operand(const XgOperand& m,
   return r;
 }
 
-// Per-thread inner offsets of an operand for the VEC elements starting at flat inner index i:
+// Per-thread view of a broadcast operand for the VEC elements starting at flat inner index i:
 // computed ONCE per thread (i is fixed while a thread marches along the axis), so the per-row
-// cost of a fused metric is one (vector) load and VEC multiplies / divides.
-template <int VEC>
-struct XgInnerOff {
-  int64_t off[VEC];
+// cost of a fused metric is one (vector) load and VEC multiplies / divides.  Kept small on
+// purpose (a pointer + VEC-1 32-bit deltas): register pressure decides the occupancy of the
+// fused kernels.
+template <typename T, int VEC>
+struct XgOperandView {
+  const T* p0;       // operand pointer + outer offset + inner offset of element 0
+  int d[VEC];        // element k sits at p0[d[k]] (d[0] = 0); generic mode only
+  int mode;          // XG_IM_* ; CONTIG with `vec` -> one 16-byte load
   bool vec;
 };
 
-template <int VEC>
-__device__ __forceinline__ XgInnerOff<VEC> xg_inner_off(const XgOperand& m, int64_t i) {
-  XgInnerOff<VEC> r;
+template <typename T, int VEC>
+__device__ __forceinline__ XgOperandView<T, VEC> xg_operand_view(const XgOperand& m, int64_t outer_off,
+                                                                 int64_t i) {
+  XgOperandView<T, VEC> r;
+  const T* p = reinterpret_cast<const T*>(m.ptr) + outer_off;
+  r.mode = m.inner_mode;
   r.vec = false;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) r.d[k] = 0;
   if (m.inner_mode == XG_IM_BCAST) {
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) r.off[k] = 0;
+    r.p0 = p;
   } else if (m.inner_mode == XG_IM_CONTIG) {
+    r.p0 = p + i;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r.off[k] = i + k;
+    for (int k = 0; k < VEC; ++k) r.d[k] = k;
     r.vec = VEC > 1 && m.vec_ok;
   } else {
+    const int64_t o0 = xg_groups_offset(m.inner, i);
+    r.p0 = p + o0;
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r.off[k] = xg_groups_offset(m.inner, i + k);
+    for (int k = 1; k < VEC; ++k) r.d[k] = (int)(xg_groups_offset(m.inner, i + k) - o0);
   }
   return r;
 }
 
+// the operand's VEC values `row_off` elements further along the operated axis
 template <typename T, int VEC>
-__device__ __forceinline__ XgPack<T, VEC> xg_ld_operand_at(const XgOperand& m, int64_t base,
-                                                           const XgInnerOff<VEC>& io) {
-  const T* p = reinterpret_cast<const T*>(m.ptr) + base;
+__device__ __forceinline__ XgPack<T, VEC> xg_ld_view(const XgOperandView<T, VEC>& v, int64_t row_off) {
+  const T* p = v.p0 + row_off;
   XgPack<T, VEC> r;
-  if (io.vec) {
-    r = xg_ld_cached<T, VEC>(p + io.off[0]);
+  if (v.mode == XG_IM_BCAST) {
+    const T s = __ldg(p);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r.v[k] = s;
+  } else if (v.vec) {
+    r = xg_ld_cached<T, VEC>(p);
   } else {
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) r.v[k] = __ldg(p + io.off[k]);
+    for (int k = 0; k < VEC; ++k) r.v[k] = __ldg(p + v.d[k]);
   }
   return r;
 }

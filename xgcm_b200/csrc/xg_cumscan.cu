@@ -60,22 +60,15 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
   T* obase = a.out + o * a.n_out * a.inner + i;
   const bool has_pre = MET && a.pre.ptr != nullptr;
   const bool has_post = MET && a.post.ptr != nullptr;
-  int64_t pre_base = 0, post_base = 0;
-  XgInnerOff<VEC> pre_io, post_io;
+  XgOperandView<T, VEC> pre_v, post_v;
   if (MET) {
-    if (has_pre) {
-      pre_base = xg_groups_offset(a.pre.outer, o);
-      pre_io = xg_inner_off<VEC>(a.pre, i);
-    }
-    if (has_post) {
-      post_base = xg_groups_offset(a.post.outer, o);
-      post_io = xg_inner_off<VEC>(a.post, i);
-    }
+    if (has_pre) pre_v = xg_operand_view<T, VEC>(a.pre, xg_groups_offset(a.pre.outer, o), i);
+    if (has_post) post_v = xg_operand_view<T, VEC>(a.post, xg_groups_offset(a.post.outer, o), i);
   }
   auto loadA = [&](int64_t k) -> Pack {
     Pack v = xg_ld_stream<T, VEC>(ibase + k * a.inner);
     if (has_pre) {
-      Pack m = xg_ld_operand_at<T, VEC>(a.pre, pre_base + k * a.pre.axis_stride, pre_io);
+      Pack m = xg_ld_view<T, VEC>(pre_v, k * a.pre.axis_stride);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] * m.v[q];
     }
@@ -83,7 +76,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
   };
   auto store = [&](int64_t j_out, Pack v) {
     if (has_post) {
-      Pack m = xg_ld_operand_at<T, VEC>(a.post, post_base + j_out * a.post.axis_stride, post_io);
+      Pack m = xg_ld_view<T, VEC>(post_v, j_out * a.post.axis_stride);
 #pragma unroll
       for (int q = 0; q < VEC; ++q) v.v[q] = v.v[q] / m.v[q];
     }
@@ -94,38 +87,51 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
 #pragma unroll
   for (int q = 0; q < VEC; ++q) acc.v[q] = cf.v[q] = cf1.v[q] = cl1.v[q] = cl.v[q] = T(0);
 
-  auto step = [&](int64_t k, const Pack& v) {
+  const int n = (int)a.n;  // < 2^31, checked on the host
+  const int k_first = (int)a.k_first, k_last = (int)a.k_last;
+  auto kof = [&](int kk) -> int { return a.reverse ? (n - 1 - kk) : kk; };
+  // the ends of the trimmed cumsum (needed by the halo rules) live in the first / last three
+  // rows; only those rows pay for the bookkeeping
+  auto step_slow = [&](int kk, const Pack& v) {
+    const int k = kof(kk);
 #pragma unroll
     for (int q = 0; q < VEC; ++q) acc.v[q] = acc.v[q] + nan_to_zero(v.v[q], a.skipna);
-    if (k == a.k_first) cf = acc;
-    if (k == a.k_first + 1) cf1 = acc;
-    if (k == a.k_last - 1) cl1 = acc;
-    if (k == a.k_last) cl = acc;
-    if (k >= a.k_first && k <= a.k_last) store(a.pad_lo + (k - a.k_first), acc);
+    if (k == k_first) cf = acc;
+    if (k == k_first + 1) cf1 = acc;
+    if (k == k_last - 1) cl1 = acc;
+    if (k == k_last) cl = acc;
+    if (k >= k_first && k <= k_last) store(a.pad_lo + (k - k_first), acc);
   };
-  auto kof = [&](int64_t kk) -> int64_t { return a.reverse ? (a.n - 1 - kk) : kk; };
+  auto step_fast = [&](int kk, const Pack& v) {  // interior rows are always kept
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) acc.v[q] = acc.v[q] + nan_to_zero(v.v[q], a.skipna);
+    store(a.pad_lo + (kof(kk) - k_first), acc);
+  };
 
+  int kk = 0;
+  const int head = n < 3 ? n : 3;
+  for (; kk < head; ++kk) step_slow(kk, loadA(kof(kk)));
+  const int mid_end = n - 3;  // rows [3, n-3) are interior
   // software pipeline: the loads of chunk c+1 are in flight while chunk c is summed (the adds
   // are serial by construction, so memory-level parallelism has to come from prefetch depth)
-  int64_t kk = 0;
-  const int64_t nfull = (a.n / U) * U;
-  if (nfull > 0) {
+  if (mid_end - kk >= U) {
     Pack cur[U], nxt[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) cur[u] = loadA(kof(u));
-    for (; kk + U < nfull; kk += U) {
+    for (int u = 0; u < U; ++u) cur[u] = loadA(kof(kk + u));
+    for (; kk + 2 * U <= mid_end; kk += U) {
 #pragma unroll
       for (int u = 0; u < U; ++u) nxt[u] = loadA(kof(kk + U + u));
 #pragma unroll
-      for (int u = 0; u < U; ++u) step(kof(kk + u), cur[u]);
+      for (int u = 0; u < U; ++u) step_fast(kk + u, cur[u]);
 #pragma unroll
       for (int u = 0; u < U; ++u) cur[u] = nxt[u];
     }
 #pragma unroll
-    for (int u = 0; u < U; ++u) step(kof(kk + u), cur[u]);
+    for (int u = 0; u < U; ++u) step_fast(kk + u, cur[u]);
     kk += U;
   }
-  for (; kk < a.n; ++kk) step(kof(kk), loadA(kof(kk)));
+  for (; kk < mid_end; ++kk) step_fast(kk, loadA(kof(kk)));
+  for (; kk < n; ++kk) step_slow(kk, loadA(kof(kk)));
 
   if (a.k_last - a.k_first < 1) {  // a single kept cell: "next" is the edge itself
     cf1 = cf;
@@ -296,7 +302,7 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
   if (a.inner > 1) {
     bool vec_ok = (a.inner % VEC == 0) && ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
     // few columns: prefer 4x more (scalar) threads over 16-byte accesses
-    if (vec_ok && a.outer * (a.inner / VEC) < 148 * 512) vec_ok = false;
+    if (vec_ok && a.outer * (a.inner / VEC) < 148 * 64) vec_ok = false;
     if (vec_ok) {
       a.nvec_inner = a.inner / VEC;
       a.small_index = a.outer * a.nvec_inner < (1ll << 31);
@@ -345,6 +351,7 @@ int cumscan_typed(const void* in, void* out, int ndim, const int64_t* shape, int
   a.k_last = v.n - 1 - ((trim == XG_TRIM_DROP_LAST) ? 1 : 0);
   const int64_t kept = a.k_last - a.k_first + 1;
   if (kept < 0) return xg_fail(XG_EINVAL, "xg_cumscan: operated axis too short to trim");
+  if (v.n >= (1ll << 31)) return xg_fail(XG_EINVAL, "xg_cumscan: operated axis longer than 2^31");
   a.n_out = kept + pad_lo + pad_hi;
   a.reverse = reverse ? 1 : 0;
   a.pad_lo = pad_lo;

@@ -47,7 +47,7 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 // strided-axis kernel
 // ---------------------------------------------------------------------------
 template <typename T, int VEC, int OP, bool MET, int U>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)  // <= 64 registers: 4 CTAs (1024 threads) per SM
 k_stencil_strided(const StencilArgs<T> a) {
   typedef XgPack<T, VEC> Pack;
   const int64_t unit =
@@ -67,25 +67,18 @@ k_stencil_strided(const StencilArgs<T> a) {
   T* obase = a.out + o * a.n_out * a.inner + i;
   const bool has_pre = MET && a.pre.ptr != nullptr;
   const bool has_post = MET && a.post.ptr != nullptr;
-  int64_t pre_base = 0, post_base = 0;
-  XgInnerOff<VEC> pre_io, post_io;
+  XgOperandView<T, VEC> pre_v, post_v;
   if (MET) {
     // everything that depends only on (o, i) is hoisted out of the march
-    if (has_pre) {
-      pre_base = xg_groups_offset(a.pre.outer, o);
-      pre_io = xg_inner_off<VEC>(a.pre, i);
-    }
-    if (has_post) {
-      post_base = xg_groups_offset(a.post.outer, o);
-      post_io = xg_inner_off<VEC>(a.post, i);
-    }
+    if (has_pre) pre_v = xg_operand_view<T, VEC>(a.pre, xg_groups_offset(a.pre.outer, o), i);
+    if (has_post) post_v = xg_operand_view<T, VEC>(a.post, xg_groups_offset(a.post.outer, o), i);
   }
 
   // A[s] = in[s] * pre[s], s in range
   auto loadA = [&](int64_t s) -> Pack {
     Pack v = xg_ld_stream<T, VEC>(ibase + s * a.inner);
     if (has_pre) {
-      Pack m = xg_ld_operand_at<T, VEC>(a.pre, pre_base + s * a.pre.axis_stride, pre_io);
+      Pack m = xg_ld_view<T, VEC>(pre_v, s * a.pre.axis_stride);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) v.v[k] = v.v[k] * m.v[k];
     }
@@ -96,7 +89,7 @@ k_stencil_strided(const StencilArgs<T> a) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) r.v[k] = xg_apply_op<T, OP>(lo_v.v[k], hi_v.v[k]);
     if (has_post) {
-      Pack m = xg_ld_operand_at<T, VEC>(a.post, post_base + j * a.post.axis_stride, post_io);
+      Pack m = xg_ld_view<T, VEC>(post_v, j * a.post.axis_stride);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / m.v[k];
     }

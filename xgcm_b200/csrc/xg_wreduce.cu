@@ -38,12 +38,8 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
   xg_divmod(g, a.nvec_inner, a.small_index, o, iv);
   const int64_t i = iv * VEC;
   const T* ibase = a.in + o * a.n * a.inner + i;
-  int64_t w_base = 0;
-  XgInnerOff<VEC> w_io;
-  if (HASW) {
-    w_base = xg_groups_offset(a.w.outer, o);
-    w_io = xg_inner_off<VEC>(a.w, i);
-  }
+  XgOperandView<T, VEC> w_v;
+  if (HASW) w_v = xg_operand_view<T, VEC>(a.w, xg_groups_offset(a.w.outer, o), i);
   Pack num, den;
 #pragma unroll
   for (int q = 0; q < VEC; ++q) num.v[q] = den.v[q] = T(0);
@@ -70,14 +66,14 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       v[u] = xg_ld_stream<T, VEC>(ibase + (k + u) * a.inner);
-      if (HASW) m[u] = xg_ld_operand_at<T, VEC>(a.w, w_base + (k + u) * a.w.axis_stride, w_io);
+      if (HASW) m[u] = xg_ld_view<T, VEC>(w_v, (k + u) * a.w.axis_stride);
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) step(v[u], m[u]);
   }
   for (; k < a.n; ++k) {
     Pack v = xg_ld_stream<T, VEC>(ibase + k * a.inner), m;
-    if (HASW) m = xg_ld_operand_at<T, VEC>(a.w, w_base + k * a.w.axis_stride, w_io);
+    if (HASW) m = xg_ld_view<T, VEC>(w_v, k * a.w.axis_stride);
     step(v, m);
   }
   Pack r;
@@ -131,7 +127,7 @@ int reduce_launch(ReduceArgs<T>& a, cudaStream_t st) {
   constexpr int U = 8;
   if (a.inner > 1) {
     bool vec_ok = (a.inner % VEC == 0) && ((uintptr_t)a.in % 16 == 0) && ((uintptr_t)a.out % 16 == 0);
-    if (vec_ok && a.outer * (a.inner / VEC) < 148 * 512) vec_ok = false;
+    if (vec_ok && a.outer * (a.inner / VEC) < 148 * 64) vec_ok = false;
     a.nvec_inner = vec_ok ? a.inner / VEC : a.inner;
     if (!vec_ok) a.w.vec_ok = 0;
     a.small_index = a.outer * a.nvec_inner < (1ll << 31);
