@@ -118,18 +118,25 @@ __device__ __forceinline__ void store_tile(T (*tile)[kTile + 1], T* out, int64_t
 // ---------------------------------------------------------------------------
 // shared theta / shared target
 // ---------------------------------------------------------------------------
+// what a column has to do for one target, decided once per block
+enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NANX = 4, PK_MASKED = 5 };
+
+struct __align__(16) PlanEntry {
+  double x;    // the target level in fp64 (after the optional log)
+  int j;       // interval index (PK_INTERP / PK_EXACT)
+  int kind;
+};
+
 template <typename T>
 __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = (int)a.n, m = (int)a.m;
-  // layout: X[n] | xt[m] | tile[kWarps][32][33] | j[m] | flags
-  double* Xs = reinterpret_cast<double*>(smem_raw);
-  double* xt = Xs + n;
-  T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(xt + m);
-  int* js = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
-                                   sizeof(T) * kWarps * kTile * (kTile + 1));
-  int* flags = js + m;  // [0]=flip [1]=fast_ok ; masks are folded into js (see below)
-  unsigned char* masked = reinterpret_cast<unsigned char*>(flags + 2);
+  // layout: plan[m] | X[n] | tile[kWarps][32][33] | flags
+  PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem_raw);
+  double* Xs = reinterpret_cast<double*>(plan + m);
+  T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(Xs + n);
+  int* flags = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
+                                      sizeof(T) * kWarps * kTile * (kTile + 1));
   const int tid = threadIdx.x;
   const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
   const T* target = reinterpret_cast<const T*>(a.target.ptr);
@@ -177,39 +184,58 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
     __syncthreads();
   }
   auto X = [&](int k) -> double { return Xs[k]; };
-  for (int t = tid; t < m; t += blockDim.x) {
+  auto classify = [&](int t, double x, int j) {
+    PlanEntry e;
+    e.x = x;
+    e.j = 0;
+    if (a.mask_edges && (x < s_tmin || x > s_tmax)) e.kind = PK_MASKED;  // transform.py:38-41
+    else if (n == 1) e.kind = PK_FIRST;  // np.interp: dx.size == 1 -> full(dy[0])
+    else if (x != x) e.kind = PK_NANX;
+    else if (j == -1) e.kind = PK_FIRST;
+    else if (j >= n - 1) e.kind = PK_LAST;  // right of the range, or exactly the last node
+    else {
+      e.j = j;
+      if (Xs[j] == x) e.kind = PK_EXACT;
+      else e.kind = PK_INTERP;
+    }
+    plan[t] = e;
+  };
+  auto load_target = [&](int t) -> double {
     T v = __ldg(target + t * a.target.axis_stride);
     if (a.logarithmic) v = xg_log<T>(v);
-    const double x = (double)v;
-    xt[t] = x;
-    masked[t] = (a.mask_edges && (x < s_tmin || x > s_tmax)) ? 1 : 0;  // transform.py:38-41
-    if (flags[1] && n > 1 && x == x) {
-      // NaN-free sorted theta: binary_search_with_guess returns the largest j with X[j] <= x
-      // whatever the guess, so every target can be searched independently
-      int j;
-      if (x > Xs[n - 1]) j = n;
-      else if (x < Xs[0]) j = -1;
-      else {
-        int lo = 0, hi = n;
-        while (lo < hi) {
-          const int mid = lo + ((hi - lo) >> 1);
-          if (x >= Xs[mid]) lo = mid + 1;
-          else hi = mid;
+    return (double)v;
+  };
+  if (flags[1] || n == 1) {
+    // NaN-free sorted theta: binary_search_with_guess returns the largest j with X[j] <= x
+    // whatever the guess, so every target can be searched independently
+    for (int t = tid; t < m; t += blockDim.x) {
+      const double x = load_target(t);
+      int j = 0;
+      if (n > 1 && x == x) {
+        if (x > Xs[n - 1]) j = n;
+        else if (x < Xs[0]) j = -1;
+        else {
+          int lo = 0, hi = n;
+          while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if (x >= Xs[mid]) lo = mid + 1;
+            else hi = mid;
+          }
+          j = lo - 1;
         }
-        j = lo - 1;
       }
-      js[t] = j;
+      classify(t, x, j);
     }
-  }
-  __syncthreads();
-  if (!flags[1] && n > 1 && tid == 0) {  // literal replay (guess carried from target to target)
+  } else if (tid == 0) {  // literal replay (guess carried from target to target)
     int guess = 0;
     for (int t = 0; t < m; ++t) {
-      const double x = xt[t];
-      if (x != x) { js[t] = 0; continue; }
-      const int j = search_with_guess(x, X, n, guess);
-      guess = j;
-      js[t] = j;
+      const double x = load_target(t);
+      int j = 0;
+      if (x == x) {
+        j = search_with_guess(x, X, n, guess);
+        guess = j;
+      }
+      classify(t, x, j);
     }
   }
   __syncthreads();
@@ -238,28 +264,21 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
       const int nt = (m - t0 < kTile) ? (m - t0) : kTile;
       if (col_ok) {
         for (int tt = 0; tt < nt; ++tt) {
-          const int t = t0 + tt;
-          const double x = xt[t];
+          const PlanEntry e = plan[t0 + tt];  // one 16-byte broadcast read
           double res;
-          if (n == 1) res = y_first;  // np.interp: dx.size == 1 -> full(dy[0])
-          else if (x != x) res = x;
-          else {
-            const int j = js[t];
-            if (j == -1) res = y_first;
-            else if (j >= n - 1) res = y_last;  // j == n (right of range) or j == n-1
-            else {
-              if (j != cj) {
-                cj = j;
-                xj = Xs[j];
-                xj1 = Xs[j + 1];
-                yj = Y(j);
-                yj1 = Y(j + 1);
-                slope = (yj1 - yj) / (xj1 - xj);
-              }
-              res = (xj == x) ? yj : interp_value(x, xj, xj1, yj, yj1, slope);
+          if (e.kind <= PK_EXACT) {
+            if (e.j != cj) {
+              cj = e.j;
+              xj = Xs[cj];
+              xj1 = Xs[cj + 1];
+              yj = Y(cj);
+              yj1 = Y(cj + 1);
+              slope = (yj1 - yj) / (xj1 - xj);
             }
-          }
-          if (masked[t]) res = NAN;
+            res = (e.kind == PK_INTERP) ? interp_value(e.x, xj, xj1, yj, yj1, slope) : yj;
+          } else if (e.kind == PK_FIRST) res = y_first;
+          else if (e.kind == PK_LAST) res = y_last;
+          else res = NAN;  // NaN target, or masked edge
           tile[lane][tt] = (T)res;
         }
       }
@@ -421,9 +440,8 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
     for (int k = 0; k < op.outer.n; ++k) outer0 = outer0 && op.outer.stride[k] == 0;
     return outer0 && op.inner_mode == XG_IM_BCAST;
   };
-  const size_t plan_bytes = (size_t)(v.n + m) * sizeof(double) +
-                            sizeof(T) * kWarps * kTile * (kTile + 1) + (size_t)(m + 2) * sizeof(int) +
-                            (size_t)m + 16;
+  const size_t plan_bytes = (size_t)m * sizeof(PlanEntry) + (size_t)v.n * sizeof(double) +
+                            sizeof(T) * kWarps * kTile * (kTile + 1) + 4 * sizeof(int);
   if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan_bytes);
