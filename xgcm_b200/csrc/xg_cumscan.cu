@@ -209,10 +209,16 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> 
     const int64_t kcol = tile_c0(tt) + lane;
     T(*tile)[kTile + 1] = sm.tile[w][stage];
     if (kcol < a.n) {
+      const T* src = in0 + kcol;
+      if (nrows == kTile) {
+#pragma unroll
+        for (int rr = 0; rr < kTile; ++rr) cp_async_elem<T>(&tile[rr][lane], src + (int64_t)rr * a.n);
+      } else {
 #pragma unroll 8
-      for (int rr = 0; rr < kTile; ++rr) {
-        if (rr < nrows) cp_async_elem<T>(&tile[rr][lane], in0 + (int64_t)rr * a.n + kcol);
-        else tile[rr][lane] = T(0);
+        for (int rr = 0; rr < kTile; ++rr) {
+          if (rr < nrows) cp_async_elem<T>(&tile[rr][lane], src + (int64_t)rr * a.n);
+          else tile[rr][lane] = T(0);
+        }
       }
     } else {
 #pragma unroll 8
@@ -222,6 +228,9 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> 
   };
 
   T acc = T(0), cf = T(0), cf1 = T(0), cl1 = T(0), cl = T(0);
+  const int n = (int)a.n;  // < 2^31, checked on the host
+  const int k_first = (int)a.k_first, k_last = (int)a.k_last;
+  const int shift = a.pad_lo - k_first;  // j_out = k + shift
   issue(0, 0);
   for (int64_t tt = 0; tt < ntile; ++tt) {
     const int stage = (int)(tt % kStages);
@@ -233,46 +242,71 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> 
     }
     __syncwarp();
     T(*tile)[kTile + 1] = sm.tile[w][stage];
-    const int64_t c0 = tile_c0(tt);
-    const int64_t kcol = c0 + lane;
-    const bool col_ok = kcol < a.n;
+    const int c0 = (int)tile_c0(tt);
+    const int kcol = c0 + lane;
+    const bool col_ok = kcol < n;
+    // tiles holding one of the recorded ends of the trimmed cumsum (first / last two cells) or
+    // the ragged end of the row take the careful path; every other tile is branch-free
+    const bool interior = (c0 > k_first + 1) && (c0 + kTile - 1 < k_last - 1) && (c0 + kTile <= n);
     if (MET && prep) {  // metric multiply with coalesced metric loads (lane = column)
       if (col_ok) {
 #pragma unroll 8
         for (int rr = 0; rr < kTile; ++rr)
           if (rr < nrows)
-            tile[rr][lane] = tile[rr][lane] * __ldg(prep + sm.pre_off[w][rr] + kcol * a.pre.axis_stride);
+            tile[rr][lane] = tile[rr][lane] * __ldg(prep + sm.pre_off[w][rr] + (int64_t)kcol * a.pre.axis_stride);
       }
       __syncwarp();
     }
     // serial scan: lane = row (row pitch 33 words: conflict-free)
     if (row_ok) {
-#pragma unroll 8
-      for (int cc = 0; cc < kTile; ++cc) {
-        const int c = a.reverse ? (kTile - 1 - cc) : cc;
-        const int64_t k = c0 + c;
-        if (k < a.n) {
-          acc = acc + nan_to_zero(tile[lane][c], a.skipna);
-          tile[lane][c] = acc;
-          if (k == a.k_first) cf = acc;
-          if (k == a.k_first + 1) cf1 = acc;
-          if (k == a.k_last - 1) cl1 = acc;
-          if (k == a.k_last) cl = acc;
+      if (interior) {
+        if (a.reverse) {
+#pragma unroll
+          for (int c = kTile - 1; c >= 0; --c) {
+            acc = acc + nan_to_zero(tile[lane][c], a.skipna);
+            tile[lane][c] = acc;
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kTile; ++c) {
+            acc = acc + nan_to_zero(tile[lane][c], a.skipna);
+            tile[lane][c] = acc;
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int cc = 0; cc < kTile; ++cc) {
+          const int c = a.reverse ? (kTile - 1 - cc) : cc;
+          const int k = c0 + c;
+          if (k < n) {
+            acc = acc + nan_to_zero(tile[lane][c], a.skipna);
+            tile[lane][c] = acc;
+            if (k == k_first) cf = acc;
+            if (k == k_first + 1) cf1 = acc;
+            if (k == k_last - 1) cl1 = acc;
+            if (k == k_last) cl = acc;
+          }
         }
       }
     }
     __syncwarp();
     // coalesced store of the kept cells (shifted by pad_lo - k_first)
-    if (col_ok && kcol >= a.k_first && kcol <= a.k_last) {
-      const int64_t j_out = a.pad_lo + (kcol - a.k_first);
-      T* out0 = a.out + r0 * a.n_out + j_out;
+    if (col_ok && kcol >= k_first && kcol <= k_last) {
+      const int j_out = kcol + shift;
+      T* optr = a.out + r0 * a.n_out + j_out;
+      if (MET && postp) {
 #pragma unroll 8
-      for (int rr = 0; rr < kTile; ++rr) {
-        if (rr < nrows) {
-          T v = tile[rr][lane];
-          if (MET && postp) v = v / __ldg(postp + sm.post_off[w][rr] + j_out * a.post.axis_stride);
-          __stcs(out0 + (int64_t)rr * a.n_out, v);
+        for (int rr = 0; rr < kTile; ++rr) {
+          if (rr < nrows) {
+            const T v = tile[rr][lane] / __ldg(postp + sm.post_off[w][rr] + (int64_t)j_out * a.post.axis_stride);
+            __stcs(optr + (int64_t)rr * a.n_out, v);
+          }
         }
+      } else if (nrows == kTile) {
+#pragma unroll
+        for (int rr = 0; rr < kTile; ++rr) __stcs(optr + (int64_t)rr * a.n_out, tile[rr][lane]);
+      } else {
+        for (int rr = 0; rr < nrows; ++rr) __stcs(optr + (int64_t)rr * a.n_out, tile[rr][lane]);
       }
     }
     __syncwarp();  // the stage is overwritten by the copy issued two iterations later

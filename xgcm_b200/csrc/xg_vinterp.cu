@@ -32,7 +32,7 @@
 
 namespace {
 
-constexpr int kWarps = 8;
+constexpr int kWarps = 4;
 constexpr int kTile = 32;
 constexpr int LIKELY_IN_CACHE_SIZE = 8;
 
@@ -118,6 +118,19 @@ __device__ __forceinline__ void store_tile(T (*tile)[kTile + 1], T* out, int64_t
 // ---------------------------------------------------------------------------
 // shared theta / shared target
 // ---------------------------------------------------------------------------
+// 4- / 8-byte asynchronous global->shared copies (LDGSTS) for the staged column tiles
+template <typename T>
+__device__ __forceinline__ void vi_cp_async(T* smem_dst, const T* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  if constexpr (sizeof(T) == 4)
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
+  else
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void vi_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void vi_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // what a column has to do for one target, decided once per block
 enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NANX = 4, PK_MASKED = 5 };
 
@@ -127,16 +140,20 @@ struct __align__(16) PlanEntry {
   int kind;
 };
 
-template <typename T>
+// STAGED: the phi values of the next 32-column tile stream into shared memory (cp.async, all n
+// levels in flight at once) while the current tile is computed, so no lane ever waits on DRAM
+// in the dependent interval -> slope -> value chain.
+template <typename T, bool STAGED>
 __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = (int)a.n, m = (int)a.m;
-  // layout: plan[m] | X[n] | tile[kWarps][32][33] | flags
+  // layout: plan[m] | X[n] | tile[kWarps][32][33] | flags[4] | phi stages [kWarps][2][n][32]
   PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem_raw);
   double* Xs = reinterpret_cast<double*>(plan + m);
   T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(Xs + n);
   int* flags = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
                                       sizeof(T) * kWarps * kTile * (kTile + 1));
+  T* phis_all = reinterpret_cast<T*>(flags + 4);
   const int tid = threadIdx.x;
   const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
   const T* target = reinterpret_cast<const T*>(a.target.ptr);
@@ -244,18 +261,50 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
   const int w = tid >> 5, lane = tid & 31;
   T(*tile)[kTile + 1] = tiles[w];
   const int64_t ncols = a.outer * a.inner;
-  for (int64_t ct = (int64_t)blockIdx.x * kWarps + w; ct < a.ntiles; ct += (int64_t)gridDim.x * kWarps) {
+  const int64_t tile_stride = (int64_t)gridDim.x * kWarps;
+  T* phis = phis_all + (size_t)w * 2 * n * kTile;  // this warp's two stages [2][n][32]
+  auto column_base = [&](int64_t ct) -> const T* {
+    const int64_t col = ct * kTile + lane;
+    if (col >= ncols) return nullptr;
+    int64_t o, i;
+    xg_divmod(col, a.inner, a.small_cols, o, i);
+    return a.phi + o * a.n * a.inner + i;
+  };
+  auto issue_tile = [&](int64_t ct, int st) {
+    const T* src = column_base(ct);
+    T* dst = phis + (size_t)st * n * kTile + lane;
+    if (src) {
+#pragma unroll 5
+      for (int k = 0; k < n; ++k) vi_cp_async<T>(dst + k * kTile, src + (int64_t)k * a.inner);
+    }
+    vi_cp_commit();
+  };
+  int64_t ct = (int64_t)blockIdx.x * kWarps + w;
+  int stage = 0;
+  if (STAGED && ct < a.ntiles) issue_tile(ct, 0);
+  for (; ct < a.ntiles; ct += tile_stride) {
     const int64_t col0 = ct * kTile;
     const int64_t col = col0 + lane;
     const bool col_ok = col < ncols;
     const int ncol_here = (int)((ncols - col0 < kTile) ? (ncols - col0) : kTile);
     const T* phi = a.phi;
-    if (col_ok) {
-      int64_t o, i;
-      xg_divmod(col, a.inner, a.small_cols, o, i);
-      phi = a.phi + o * a.n * a.inner + i;
+    const T* staged = phis + (size_t)stage * n * kTile + lane;
+    if (STAGED) {
+      if (ct + tile_stride < a.ntiles) {
+        issue_tile(ct + tile_stride, stage ^ 1);
+        vi_cp_wait<1>();
+      } else {
+        vi_cp_wait<0>();
+      }
+      __syncwarp();
+    } else if (col_ok) {
+      phi = column_base(ct);
     }
-    auto Y = [&](int k) -> double { return (double)__ldg(phi + (int64_t)(flip ? n - 1 - k : k) * a.inner); };
+    auto Y = [&](int k) -> double {
+      const int kk = flip ? n - 1 - k : k;
+      if (STAGED) return (double)staged[kk * kTile];
+      return (double)__ldg(phi + (int64_t)kk * a.inner);
+    };
     int cj = -2;  // memoised interval
     double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
     const double y_first = col_ok ? Y(0) : 0.0;
@@ -284,6 +333,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
       }
       store_tile<T>(tile, a.out, col0, ncol_here, a.m, t0, nt, lane);
     }
+    stage ^= 1;
   }
 }
 
@@ -442,14 +492,22 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
   };
   const size_t plan_bytes = (size_t)m * sizeof(PlanEntry) + (size_t)v.n * sizeof(double) +
                             sizeof(T) * kWarps * kTile * (kTile + 1) + 4 * sizeof(int);
+  const size_t stage_bytes = sizeof(T) * (size_t)kWarps * 2 * (size_t)v.n * kTile;
   if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)plan_bytes);
+    const bool staged = plan_bytes + stage_bytes <= 110 * 1024;  // two CTAs per SM
+    const size_t smem = plan_bytes + (staged ? stage_bytes : 0);
+    cudaError_t e =
+        staged ? cudaFuncSetAttribute(k_vinterp_shared<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+               : cudaFuncSetAttribute(k_vinterp_shared<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess)
       return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     int64_t blocks = xg_ceil_div(a.ntiles, kWarps);
-    if (blocks > 148 * 8) blocks = 148 * 8;  // persistent-ish: the plan is amortised over many tiles
-    k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
+    const int64_t cap = staged ? 148 * 2 : 148 * 8;  // persistent: the plan is amortised over many tiles
+    if (blocks > cap) blocks = cap;
+    if (staged)
+      k_vinterp_shared<T, true><<<(unsigned)blocks, kWarps * 32, smem, st>>>(a);
+    else
+      k_vinterp_shared<T, false><<<(unsigned)blocks, kWarps * 32, smem, st>>>(a);
     return xg_check_launch("xg_vinterp_linear(shared)");
   }
   const int64_t blocks = xg_ceil_div(a.ntiles, kWarpsCol);
