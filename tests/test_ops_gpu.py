@@ -76,7 +76,7 @@ def _cumscan_cases():
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
-@pytest.mark.parametrize("shape", [(1,), (2,), (33,), (100,), (5, 40), (6, 20, 36), (3, 4, 10, 16), (40, 3), (70, 1, 5), (2, 3600)])
+@pytest.mark.parametrize("shape", [(1,), (2,), (33,), (100,), (5, 40), (6, 20, 36), (3, 4, 10, 16), (40, 3), (70, 1, 5), (2, 3600), (33, 520), (3, 2, 1032)])
 def test_cumscan_bit_exact(dtype, shape):
     """Sequential order => bit-equal to np.cumsum for every shift of grid.py:1326-1383."""
     from xgcm_b200 import ops
@@ -110,6 +110,24 @@ def test_cumscan_metrics_and_nan(dtype):
                 want = oracle.cumscan(a, axis, rev, trim, plo, phi, "extend" if (plo or phi) else None, 0.0, pre, post, skipna)
                 got = ops.cumscan(_t(a), axis, rev, trim, plo, phi, "extend", 0.0, _t(pre), _t(post), skipna).cpu().numpy()
                 np.testing.assert_array_equal(got, want)
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_cumscan_wide_rows_metrics(dtype):
+    """Innermost-axis scan through the 16-byte tile kernel, with metrics, NaNs, reverse, ragged rows."""
+    from xgcm_b200 import ops
+
+    shape = (37, 776)
+    a = _field(shape, dtype, seed=31, nan_frac=0.02)
+    rng = np.random.default_rng(32)
+    pre = (1 + rng.random((1, shape[1]))).astype(dtype)
+    for (rev, trim, plo, phi) in _cumscan_cases():
+        n_out = shape[1] - (0 if trim == "none" else 1) + plo + phi
+        post = (1 + rng.random((shape[0], n_out))).astype(dtype)
+        for bc in ("fill", "extend", "periodic"):
+            want = oracle.cumscan(a, 1, rev, trim, plo, phi, bc if (plo or phi) else None, 0.5, pre, post, True)
+            got = ops.cumscan(_t(a), 1, rev, trim, plo, phi, bc, 0.5, _t(pre), _t(post), True).cpu().numpy()
+            np.testing.assert_array_equal(got, want)
 
 
 def test_cumscan_known_answers():

@@ -329,6 +329,192 @@ __global__ void __launch_bounds__(kRowWarps * 32) k_scan_rows(const ScanArgs<T> 
   }
 }
 
+// ------------------------------------------------------------------ innermost axis, wide tiles
+// Same algorithm with 16-byte shared / global accesses: a tile is 32 rows x 32 chunks of 16 B
+// (128 fp32 or 64 fp64 columns).  Per byte moved this issues 4x fewer LDGSTS / LDS / STS / STG
+// than the 32x32 scalar tile, which is what bounds that kernel (MIO throughput, see
+// profiles/).  Chunks are XOR-swizzled with the row index so that both the row-wise copies
+// (lane = chunk) and the lane-per-row scan (lane = row, LDS.128) are bank-conflict free.
+constexpr int kWideWarps = 2;
+constexpr int kChunks = 32;  // 16-byte chunks per tile row
+
+struct __align__(16) Chunk16 {
+  unsigned int w[4];
+};
+
+template <typename T>
+struct WideSmem {
+  Chunk16 tile[kWideWarps][kStages][kTile][kChunks];
+  int64_t pre_off[kWideWarps][kTile];
+  int64_t post_off[kWideWarps][kTile];
+};
+
+__device__ __forceinline__ void cp_async_16(void* smem_dst, const void* gsrc) {
+  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(gsrc) : "memory");
+}
+
+template <typename T, bool MET>
+__global__ void __launch_bounds__(kWideWarps * 32) k_scan_rows_wide(const ScanArgs<T> a) {
+  constexpr int E = 16 / sizeof(T);       // elements per chunk
+  constexpr int TW = kChunks * E;         // tile width in elements
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  WideSmem<T>& sm = *reinterpret_cast<WideSmem<T>*>(smem_raw);
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int64_t unit = (int64_t)blockIdx.x * kWideWarps + w;
+  const int64_t r0 = unit * kTile;
+  if (r0 >= a.outer) return;  // warp-uniform
+  const int64_t my_row = r0 + lane;
+  const bool row_ok = my_row < a.outer;
+  const int nrows = (int)((a.outer - r0 < kTile) ? (a.outer - r0) : kTile);
+  if (MET) {
+    sm.pre_off[w][lane] = (a.pre.ptr && row_ok) ? xg_groups_offset(a.pre.outer, my_row) : 0;
+    sm.post_off[w][lane] = (a.post.ptr && row_ok) ? xg_groups_offset(a.post.outer, my_row) : 0;
+  }
+  __syncwarp();
+  const T* prep = reinterpret_cast<const T*>(a.pre.ptr);
+  const T* postp = reinterpret_cast<const T*>(a.post.ptr);
+  const T* in0 = a.in + r0 * a.n;
+  const int n = (int)a.n;
+  const int k_first = (int)a.k_first, k_last = (int)a.k_last;
+  const int shift = a.pad_lo - k_first;  // j_out = k + shift
+  const bool wide_store = (shift == 0) && (a.n_out % E == 0) && (((uintptr_t)a.out & 15) == 0) && !(MET && postp);
+  const int ntile = (n + TW - 1) / TW;
+  auto tile_c0 = [&](int tt) -> int { return (a.reverse ? (ntile - 1 - tt) : tt) * TW; };
+
+  // row-wise copy: lane = chunk; chunk q of row rr lands in physical slot q ^ (rr & 31)
+  auto issue = [&](int tt, int stage) {
+    const int kc = tile_c0(tt) + lane * E;  // first element of this lane's chunk
+    Chunk16(*tile)[kChunks] = sm.tile[w][stage];
+    if (kc < n) {  // rows are multiples of E long: a chunk is entirely in or out
+      const T* src = in0 + kc;
+#pragma unroll 8
+      for (int rr = 0; rr < kTile; ++rr)
+        if (rr < nrows) cp_async_16(&tile[rr][lane ^ rr], src + (int64_t)rr * a.n);
+    }
+    cp_async_commit();
+  };
+
+  T acc = T(0), cf = T(0), cf1 = T(0), cl1 = T(0), cl = T(0);
+  issue(0, 0);
+  for (int tt = 0; tt < ntile; ++tt) {
+    const int stage = tt % kStages;
+    if (tt + 1 < ntile) {
+      issue(tt + 1, (tt + 1) % kStages);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncwarp();
+    Chunk16(*tile)[kChunks] = sm.tile[w][stage];
+    const int c0 = tile_c0(tt);
+    const int kc = c0 + lane * E;
+    const bool chunk_ok = kc < n;
+    const int nchunk = (n - c0 >= TW) ? kChunks : (n - c0) / E;  // valid chunks in this tile
+    const bool interior = (c0 > k_first + 1) && (c0 + TW - 1 < k_last - 1) && (nchunk == kChunks);
+    if (MET && prep) {  // metric multiply, lane = chunk (coalesced metric reads)
+      if (chunk_ok) {
+        for (int rr = 0; rr < nrows; ++rr) {
+          Chunk16 c = tile[rr][lane ^ rr];
+          T* v = reinterpret_cast<T*>(&c);
+          const T* mp = prep + sm.pre_off[w][rr] + (int64_t)kc * a.pre.axis_stride;
+#pragma unroll
+          for (int e = 0; e < E; ++e) v[e] = v[e] * __ldg(mp + (int64_t)e * a.pre.axis_stride);
+          tile[rr][lane ^ rr] = c;
+        }
+      }
+      __syncwarp();
+    }
+    // serial scan: lane = row, one 16-byte chunk per shared-memory access
+    if (row_ok) {
+      if (interior) {
+#pragma unroll 8
+        for (int qq = 0; qq < kChunks; ++qq) {
+          const int q = a.reverse ? (kChunks - 1 - qq) : qq;
+          Chunk16 c = tile[lane][q ^ lane];
+          T* v = reinterpret_cast<T*>(&c);
+          if (a.reverse) {
+#pragma unroll
+            for (int e = E - 1; e >= 0; --e) { acc = acc + nan_to_zero(v[e], a.skipna); v[e] = acc; }
+          } else {
+#pragma unroll
+            for (int e = 0; e < E; ++e) { acc = acc + nan_to_zero(v[e], a.skipna); v[e] = acc; }
+          }
+          tile[lane][q ^ lane] = c;
+        }
+      } else {
+        for (int qq = 0; qq < nchunk; ++qq) {
+          const int q = a.reverse ? (nchunk - 1 - qq) : qq;
+          Chunk16 c = tile[lane][q ^ lane];
+          T* v = reinterpret_cast<T*>(&c);
+#pragma unroll
+          for (int ee = 0; ee < E; ++ee) {
+            const int e = a.reverse ? (E - 1 - ee) : ee;
+            const int k = c0 + q * E + e;
+            acc = acc + nan_to_zero(v[e], a.skipna);
+            v[e] = acc;
+            if (k == k_first) cf = acc;
+            if (k == k_first + 1) cf1 = acc;
+            if (k == k_last - 1) cl1 = acc;
+            if (k == k_last) cl = acc;
+          }
+          tile[lane][q ^ lane] = c;
+        }
+      }
+    }
+    __syncwarp();
+    // store: lane = chunk
+    if (chunk_ok) {
+      if (wide_store && interior) {
+        T* optr = a.out + r0 * a.n_out + kc;
+        if (nrows == kTile) {
+#pragma unroll 8
+          for (int rr = 0; rr < kTile; ++rr)
+            __stcs(reinterpret_cast<uint4*>(optr + (int64_t)rr * a.n_out),
+                   *reinterpret_cast<const uint4*>(&tile[rr][lane ^ rr]));
+        } else {
+          for (int rr = 0; rr < nrows; ++rr)
+            __stcs(reinterpret_cast<uint4*>(optr + (int64_t)rr * a.n_out),
+                   *reinterpret_cast<const uint4*>(&tile[rr][lane ^ rr]));
+        }
+      } else {
+        for (int rr = 0; rr < nrows; ++rr) {
+          Chunk16 c = tile[rr][lane ^ rr];
+          const T* v = reinterpret_cast<const T*>(&c);
+#pragma unroll
+          for (int e = 0; e < E; ++e) {
+            const int k = kc + e;
+            if (k >= k_first && k <= k_last) {
+              const int j_out = k + shift;
+              T val = v[e];
+              if (MET && postp) val = val / __ldg(postp + sm.post_off[w][rr] + (int64_t)j_out * a.post.axis_stride);
+              __stcs(a.out + (r0 + rr) * a.n_out + j_out, val);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
+  if (!row_ok) return;
+  if (a.k_last - a.k_first < 1) {
+    cf1 = cf;
+    cl1 = cl;
+  }
+  if (a.pad_lo) {
+    T h = halo_value<T>(true, a.bc, a.fill, cf, cf1, cl1, cl);
+    if (MET && postp) h = h / __ldg(postp + sm.post_off[w][lane]);
+    a.out[my_row * a.n_out] = h;
+  }
+  if (a.pad_hi) {
+    T h = halo_value<T>(false, a.bc, a.fill, cf, cf1, cl1, cl);
+    if (MET && postp)
+      h = h / __ldg(postp + sm.post_off[w][lane] + (a.n_out - 1) * a.post.axis_stride);
+    a.out[my_row * a.n_out + a.n_out - 1] = h;
+  }
+}
+
 template <typename T, bool MET>
 int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
   constexpr int VEC = XgVecWidth<T>::value;
@@ -355,6 +541,16 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
     return xg_check_launch("xg_cumscan(strided)");
   }
   const int64_t units = xg_ceil_div(a.outer, kTile);
+  constexpr int E = 16 / sizeof(T);
+  if (a.n % E == 0 && a.n >= 4 * E * kChunks && ((uintptr_t)a.in & 15) == 0) {
+    const int64_t wblocks = xg_ceil_div(units, kWideWarps);
+    if (wblocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
+    const size_t wsmem = sizeof(WideSmem<T>);
+    cudaError_t e = cudaFuncSetAttribute(k_scan_rows_wide<T, MET>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wsmem);
+    if (e != cudaSuccess) return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    k_scan_rows_wide<T, MET><<<(unsigned)wblocks, kWideWarps * 32, wsmem, st>>>(a);
+    return xg_check_launch("xg_cumscan(rows, wide)");
+  }
   const int64_t blocks = xg_ceil_div(units, kRowWarps);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
   const size_t smem = sizeof(RowTileSmem<T>);
