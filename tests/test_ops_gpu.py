@@ -241,6 +241,26 @@ def test_vinterp_log(dtype, rtol):
     np.testing.assert_allclose(got, want, rtol=rtol, atol=rtol, equal_nan=True)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_vinterp_shared_slope_division_is_correctly_rounded(dtype):
+    """The shared-theta kernel forms slope = dy/dx from a precomputed reciprocal plus FMA corrections;
+    it must round exactly like the reference's fp64 division: many columns, wide dynamic range,
+    zeros, NaNs, non power-of-two spacings."""
+    from xgcm_b200 import ops
+
+    rng = np.random.default_rng(77)
+    ncol, n = 200_000, 5
+    phi = (rng.standard_normal((n, ncol)) * 10.0 ** rng.integers(-12, 12, size=(n, ncol))).astype(dtype)
+    phi[:, :50] = 0.0
+    phi[2, 50:80] = np.nan
+    phi[1, 100:200] = phi[2, 100:200]  # dy == 0
+    theta = np.array([0.1, 0.7, 1.9, 3.0000001, 7.3], dtype=dtype).reshape(n, 1)
+    target = np.array([0.05, 0.1, 0.33, 0.7000001, 1.0, 2.5, 3.0, 3.5, 7.0, 7.3, 9.0], dtype=dtype)
+    want = oracle.vinterp_linear(phi, np.broadcast_to(theta, phi.shape), target, 0, True)
+    got = ops.vinterp_linear(_t(phi), _t(theta), _t(target), 0, True).cpu().numpy()
+    np.testing.assert_array_equal(got, want)
+
+
 def test_vinterp_mixed_dtypes_promote_like_numba():
     """transform.py:15-22: float32 loop only if phi, theta, target are ALL float32."""
     from xgcm_b200 import ops

@@ -103,6 +103,23 @@ __device__ __forceinline__ double interp_value(double x, double xj, double xj1, 
   return res;
 }
 
+// Correctly rounded a / b from r = RN(1/b) with five fp64 operations instead of the ~30 of the
+// generic division (Markstein's FMA-based sequence: q0 = RN(a r) is within 2 ulp, the first
+// correction makes it faithful, and for a faithful q with r within half an ulp of 1/b the second
+// correction q + RN(a - b q) r rounds to exactly RN(a / b)).  Only valid when no intermediate
+// can leave the normal range; the caller guards the exponents of a and b and falls back to `/`.
+__device__ __forceinline__ double div_with_recip(double a, double b, double r) {
+  const double q0 = a * r;
+  const double e0 = fma(-b, q0, a);
+  const double q1 = fma(e0, r, q0);
+  const double e1 = fma(-b, q1, a);
+  return fma(e1, r, q1);
+}
+__device__ __forceinline__ bool exponent_safe(double v) {
+  const double m = fabs(v);
+  return m >= 0x1p-400 && m <= 0x1p400;  // false for 0, NaN, inf
+}
+
 // transposed write-out of a 32-column x nt-target tile
 template <typename T>
 __device__ __forceinline__ void store_tile(T (*tile)[kTile + 1], T* out, int64_t col0, int ncol_here,
@@ -148,10 +165,11 @@ template <typename T, bool STAGED>
 __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = (int)a.n, m = (int)a.m;
-  // layout: plan[m] | X[n] | tile[kWarps][32][33] | flags[4] | phi stages [kWarps][2][n][32]
+  // layout: plan[m] | X[n] | rdx[n] | tile[kWarps][32][33] | flags[4] | phi stages [kWarps][2][n][32]
   PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem_raw);
   double* Xs = reinterpret_cast<double*>(plan + m);
-  T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(Xs + n);
+  double* rdx = Xs + n;  // RN(1 / (X[j+1] - X[j])) or 0 when the fast division must not be used
+  T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(rdx + n);
   int* flags = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
                                       sizeof(T) * kWarps * kTile * (kTile + 1));
   T* phis_all = reinterpret_cast<T*>(flags + 4);
@@ -200,6 +218,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
       Xs[n - 1 - k] = t0;
     }
     __syncthreads();
+  }
+  for (int j = tid; j < n; j += blockDim.x) {
+    double r = 0.0;
+    if (j + 1 < n) {
+      const double dxj = Xs[j + 1] - Xs[j];
+      if (exponent_safe(dxj)) r = 1.0 / dxj;
+    }
+    rdx[j] = r;
   }
   auto X = [&](int k) -> double { return Xs[k]; };
   auto classify = [&](int t, double x, int j) {
@@ -335,7 +361,8 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
               xj1 = Xs[cj + 1];
               yj = Y(cj);
               yj1 = Y(cj + 1);
-              slope = (yj1 - yj) / (xj1 - xj);
+              const double dyj = yj1 - yj, dxj = xj1 - xj, r = rdx[cj];
+              slope = (r != 0.0 && exponent_safe(dyj)) ? div_with_recip(dyj, dxj, r) : dyj / dxj;
             }
             res = (e.kind == PK_INTERP) ? interp_value(e.x, xj, xj1, yj, yj1, slope) : yj;
           } else if (e.kind == PK_FIRST) res = y_first;
@@ -503,7 +530,7 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
     for (int k = 0; k < op.outer.n; ++k) outer0 = outer0 && op.outer.stride[k] == 0;
     return outer0 && op.inner_mode == XG_IM_BCAST;
   };
-  const size_t plan_bytes = (size_t)m * sizeof(PlanEntry) + (size_t)v.n * sizeof(double) +
+  const size_t plan_bytes = (size_t)m * sizeof(PlanEntry) + 2 * (size_t)v.n * sizeof(double) +
                             sizeof(T) * kWarps * kTile * (kTile + 1) + 4 * sizeof(int);
   const size_t stage_bytes = sizeof(T) * (size_t)kWarps * 2 * (size_t)v.n * kTile;
   if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
