@@ -136,43 +136,31 @@ __device__ __forceinline__ void store_tile(T (*tile)[kTile + 1], T* out, int64_t
 // ---------------------------------------------------------------------------
 // shared theta / shared target
 // ---------------------------------------------------------------------------
-// 4- / 8-byte asynchronous global->shared copies (LDGSTS) for the staged column tiles
-template <typename T>
-__device__ __forceinline__ void vi_cp_async(T* smem_dst, const T* gsrc) {
-  const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
-  if constexpr (sizeof(T) == 4)
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(gsrc) : "memory");
-  else
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void vi_cp_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void vi_cp_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+// what a column has to do for a run of consecutive targets, decided once per block
+enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NAN = 4 };
 
-// what a column has to do for one target, decided once per block
-enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NANX = 4, PK_MASKED = 5 };
-
-struct __align__(16) PlanEntry {
-  double x;    // the target level in fp64 (after the optional log)
-  int j;       // interval index (PK_INTERP / PK_EXACT)
+struct __align__(16) Run {
+  int t_begin, t_end;  // targets [t_begin, t_end) — never crosses a multiple of 32
+  int j;               // interval index (PK_INTERP / PK_EXACT)
   int kind;
 };
 
-// STAGED: the phi values of the next 32-column tile stream into shared memory (cp.async, all n
-// levels in flight at once) while the current tile is computed, so no lane ever waits on DRAM
-// in the dependent interval -> slope -> value chain.
-template <typename T, bool STAGED>
+template <typename T>
 __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs<T> a) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = (int)a.n, m = (int)a.m;
-  // layout: plan[m] | X[n] | rdx[n] | tile[kWarps][32][33] | flags[4] | phi stages [kWarps][2][n][32]
-  PlanEntry* plan = reinterpret_cast<PlanEntry*>(smem_raw);
-  double* Xs = reinterpret_cast<double*>(plan + m);
+  const int nchunk = (m + kTile - 1) / kTile;
+  // layout: runs[m + nchunk] | xt[m] | X[n] | rdx[n] | tile[kWarps][32][33] | tj[m] tk[m] chunk_run[nchunk+1] flags[4]
+  Run* runs = reinterpret_cast<Run*>(smem_raw);
+  double* xt = reinterpret_cast<double*>(runs + (m + nchunk));
+  double* Xs = xt + m;
   double* rdx = Xs + n;  // RN(1 / (X[j+1] - X[j])) or 0 when the fast division must not be used
   T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(rdx + n);
-  int* flags = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
-                                      sizeof(T) * kWarps * kTile * (kTile + 1));
-  T* phis_all = reinterpret_cast<T*>(flags + 4);
+  int* tj = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
+                                   sizeof(T) * kWarps * kTile * (kTile + 1));
+  int* tk = tj + m;
+  int* chunk_run = tk + m;
+  int* flags = chunk_run + nchunk + 1;
   const int tid = threadIdx.x;
   const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
   const T* target = reinterpret_cast<const T*>(a.target.ptr);
@@ -229,20 +217,19 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
   }
   auto X = [&](int k) -> double { return Xs[k]; };
   auto classify = [&](int t, double x, int j) {
-    PlanEntry e;
-    e.x = x;
-    e.j = 0;
-    if (a.mask_edges && (x < s_tmin || x > s_tmax)) e.kind = PK_MASKED;  // transform.py:38-41
-    else if (n == 1) e.kind = PK_FIRST;  // np.interp: dx.size == 1 -> full(dy[0])
-    else if (x != x) e.kind = PK_NANX;
-    else if (j == -1) e.kind = PK_FIRST;
-    else if (j >= n - 1) e.kind = PK_LAST;  // right of the range, or exactly the last node
+    int kind, jj = 0;
+    if (a.mask_edges && (x < s_tmin || x > s_tmax)) kind = PK_NAN;  // transform.py:38-41
+    else if (n == 1) kind = PK_FIRST;  // np.interp: dx.size == 1 -> full(dy[0])
+    else if (x != x) kind = PK_NAN;    // np.interp: a NaN target stays NaN
+    else if (j == -1) kind = PK_FIRST;
+    else if (j >= n - 1) kind = PK_LAST;  // right of the range, or exactly the last node
     else {
-      e.j = j;
-      if (Xs[j] == x) e.kind = PK_EXACT;
-      else e.kind = PK_INTERP;
+      jj = j;
+      kind = (Xs[j] == x) ? PK_EXACT : PK_INTERP;
     }
-    plan[t] = e;
+    xt[t] = x;
+    tj[t] = jj;
+    tk[t] = kind;
   };
   auto load_target = [&](int t) -> double {
     T v = __ldg(target + t * a.target.axis_stride);
@@ -283,97 +270,96 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
     }
   }
   __syncthreads();
+  if (tid == 0) {  // group consecutive targets with the same work into runs, split at tile edges
+    int nr = 0;
+    for (int t = 0; t < m; ++t) {
+      const bool fresh = (t % kTile == 0) || tk[t] != runs[nr - 1].kind ||
+                         (tk[t] <= PK_EXACT && tj[t] != runs[nr - 1].j);
+      if (t % kTile == 0) chunk_run[t / kTile] = nr;
+      if (fresh) {
+        runs[nr].t_begin = t;
+        runs[nr].t_end = t + 1;
+        runs[nr].j = tj[t];
+        runs[nr].kind = tk[t];
+        ++nr;
+      } else {
+        runs[nr - 1].t_end = t + 1;
+      }
+    }
+    chunk_run[nchunk] = nr;
+  }
+  __syncthreads();
 
   // ---- columns ----------------------------------------------------------------
   const int w = tid >> 5, lane = tid & 31;
   T(*tile)[kTile + 1] = tiles[w];
   const int64_t ncols = a.outer * a.inner;
   const int64_t tile_stride = (int64_t)gridDim.x * kWarps;
-  T* phis = phis_all + (size_t)w * 2 * n * kTile;  // this warp's two stages [2][n][32]
-  auto column_base = [&](int64_t ct) -> const T* {
-    const int64_t col = ct * kTile + lane;
-    if (col >= ncols) return nullptr;
-    int64_t o, i;
-    xg_divmod(col, a.inner, a.small_cols, o, i);
-    return a.phi + o * a.n * a.inner + i;
-  };
-  auto issue_tile = [&](int64_t ct, int st) {
-    const T* src = column_base(ct);
-    T* dst = phis + (size_t)st * n * kTile + lane;
-    if (src) {
-#pragma unroll 5
-      for (int k = 0; k < n; ++k) vi_cp_async<T>(dst + k * kTile, src + (int64_t)k * a.inner);
-    }
-    vi_cp_commit();
-  };
-  int64_t ct = (int64_t)blockIdx.x * kWarps + w;
-  int stage = 0;
-  if (STAGED && ct < a.ntiles) issue_tile(ct, 0);
-  for (; ct < a.ntiles; ct += tile_stride) {
+  const int64_t step = flip ? -a.inner : a.inner;  // phi pointer step for j -> j + 1
+  for (int64_t ct = (int64_t)blockIdx.x * kWarps + w; ct < a.ntiles; ct += tile_stride) {
     const int64_t col0 = ct * kTile;
     const int64_t col = col0 + lane;
     const bool col_ok = col < ncols;
     const int ncol_here = (int)((ncols - col0 < kTile) ? (ncols - col0) : kTile);
-    const T* phi = a.phi;
-    const T* staged = phis + (size_t)stage * n * kTile + lane;
-    if (STAGED) {
-      if (ct + tile_stride < a.ntiles) {
-        issue_tile(ct + tile_stride, stage ^ 1);
-        vi_cp_wait<1>();
-      } else {
-        vi_cp_wait<0>();
-      }
-      __syncwarp();
-    } else if (col_ok) {
-      phi = column_base(ct);
-    }
-    auto Y = [&](int k) -> double {
-      const int kk = flip ? n - 1 - k : k;
-      if (STAGED) return (double)staged[kk * kTile];
-      return (double)__ldg(phi + (int64_t)kk * a.inner);
-    };
-    int cj = -2;  // memoised interval
-    double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
-    if (!STAGED && col_ok) {  // warm L1 with the first rows of this column tile
+    const T* phi0 = a.phi;  // -> Y(0) of this column
+    if (col_ok) {
+      int64_t o, i;
+      xg_divmod(col, a.inner, a.small_cols, o, i);
+      phi0 = a.phi + o * a.n * a.inner + i + (flip ? (int64_t)(n - 1) * a.inner : 0);
 #pragma unroll
-      for (int k = 1; k <= kPrefetchRows; ++k)
-        if (k < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(phi + (int64_t)(flip ? n - 1 - k : k) * a.inner));
+      for (int k = 1; k <= kPrefetchRows; ++k)  // warm L1 with the first rows of this column
+        if (k < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(phi0 + k * step));
     }
-    const double y_first = col_ok ? Y(0) : 0.0;
-    const double y_last = col_ok ? Y(n - 1) : 0.0;
-    for (int t0 = 0; t0 < m; t0 += kTile) {
+    int cj = -2;  // memoised interval
+    const T* pj1 = phi0;  // -> Y(cj + 1)
+    double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
+    const double y_first = col_ok ? (double)__ldg(phi0) : 0.0;
+    const double y_last = col_ok ? (double)__ldg(phi0 + (int64_t)(n - 1) * step) : 0.0;
+    for (int c = 0; c < nchunk; ++c) {
+      const int t0 = c * kTile;
       const int nt = (m - t0 < kTile) ? (m - t0) : kTile;
       if (col_ok) {
-        for (int tt = 0; tt < nt; ++tt) {
-          const PlanEntry e = plan[t0 + tt];  // one 16-byte broadcast read
-          double res;
-          if (e.kind <= PK_EXACT) {
-            if (e.j != cj) {
-              if (!STAGED) {
-                // targets normally ascend: pull the rows a few intervals ahead into L1 now so
-                // the next interval switches do not wait on DRAM
-                const int ahead = e.j + ((e.j > cj) ? kPrefetchRows : -kPrefetchRows);
-                if (ahead >= 0 && ahead < n)
-                  asm volatile("prefetch.global.L1 [%0];" ::"l"(phi + (int64_t)(flip ? n - 1 - ahead : ahead) * a.inner));
+        const int r_end = chunk_run[c + 1];
+        for (int r = chunk_run[c]; r < r_end; ++r) {
+          const Run run = runs[r];  // one 16-byte broadcast read
+          T* dst = &tile[lane][run.t_begin - t0];
+          const int len = run.t_end - run.t_begin;
+          if (run.kind <= PK_EXACT) {
+            if (run.j != cj) {
+              if (run.j == cj + 1 && cj >= 0) {  // the usual case: walk one interval up
+                yj = yj1;
+                xj = xj1;
+                pj1 += step;
+              } else {
+                pj1 = phi0 + (int64_t)(run.j + 1) * step;
+                yj = (double)__ldg(pj1 - step);
+                xj = Xs[run.j];
               }
-              cj = e.j;
-              xj = Xs[cj];
+              cj = run.j;
+              // targets normally ascend: pull a row a few intervals ahead into L1 now so the next
+              // interval switches do not wait on DRAM
+              if (cj + 1 + kPrefetchRows < n)
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(pj1 + kPrefetchRows * step));
+              yj1 = (double)__ldg(pj1);
               xj1 = Xs[cj + 1];
-              yj = Y(cj);
-              yj1 = Y(cj + 1);
-              const double dyj = yj1 - yj, dxj = xj1 - xj, r = rdx[cj];
-              slope = (r != 0.0 && exponent_safe(dyj)) ? div_with_recip(dyj, dxj, r) : dyj / dxj;
+              const double dyj = yj1 - yj, dxj = xj1 - xj, rr = rdx[cj];
+              slope = (rr != 0.0 && exponent_safe(dyj)) ? div_with_recip(dyj, dxj, rr) : dyj / dxj;
             }
-            res = (e.kind == PK_INTERP) ? interp_value(e.x, xj, xj1, yj, yj1, slope) : yj;
-          } else if (e.kind == PK_FIRST) res = y_first;
-          else if (e.kind == PK_LAST) res = y_last;
-          else res = NAN;  // NaN target, or masked edge
-          tile[lane][tt] = (T)res;
+            if (run.kind == PK_INTERP) {
+              const double* xp = xt + run.t_begin;
+              for (int q = 0; q < len; ++q) dst[q] = (T)interp_value(xp[q], xj, xj1, yj, yj1, slope);
+            } else {
+              const T v = (T)yj;
+              for (int q = 0; q < len; ++q) dst[q] = v;
+            }
+          } else {
+            const T v = (run.kind == PK_FIRST) ? (T)y_first : (run.kind == PK_LAST) ? (T)y_last : T(NAN);
+            for (int q = 0; q < len; ++q) dst[q] = v;
+          }
         }
       }
       store_tile<T>(tile, a.out, col0, ncol_here, a.m, t0, nt, lane);
     }
-    stage ^= 1;
   }
 }
 
@@ -530,27 +516,18 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
     for (int k = 0; k < op.outer.n; ++k) outer0 = outer0 && op.outer.stride[k] == 0;
     return outer0 && op.inner_mode == XG_IM_BCAST;
   };
-  const size_t plan_bytes = (size_t)m * sizeof(PlanEntry) + 2 * (size_t)v.n * sizeof(double) +
-                            sizeof(T) * kWarps * kTile * (kTile + 1) + 4 * sizeof(int);
-  const size_t stage_bytes = sizeof(T) * (size_t)kWarps * 2 * (size_t)v.n * kTile;
+  const int64_t nchunk = xg_ceil_div(m, kTile);
+  const size_t plan_bytes = (size_t)(m + nchunk) * sizeof(Run) + (size_t)(m + 2 * v.n) * sizeof(double) +
+                            sizeof(T) * kWarps * kTile * (kTile + 1) +
+                            (size_t)(2 * m + nchunk + 1 + 4) * sizeof(int);
   if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
-    // Staging was measured SLOWER on B200 (4.4 ms vs 3.0 ms at C5): its shared-memory footprint
-    // leaves 8 warps per SM, too few to cover the dependent fp64 chains.  Kept for reference,
-    // disabled; the direct path below prefetches the upcoming phi rows into L1 instead.
-    const bool staged = false && plan_bytes + stage_bytes <= 110 * 1024;
-    const size_t smem = plan_bytes + (staged ? stage_bytes : 0);
-    cudaError_t e =
-        staged ? cudaFuncSetAttribute(k_vinterp_shared<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
-               : cudaFuncSetAttribute(k_vinterp_shared<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)plan_bytes);
     if (e != cudaSuccess)
       return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
     int64_t blocks = xg_ceil_div(a.ntiles, kWarps);
-    const int64_t cap = staged ? 148 * 2 : 148 * 8;  // persistent: the plan is amortised over many tiles
-    if (blocks > cap) blocks = cap;
-    if (staged)
-      k_vinterp_shared<T, true><<<(unsigned)blocks, kWarps * 32, smem, st>>>(a);
-    else
-      k_vinterp_shared<T, false><<<(unsigned)blocks, kWarps * 32, smem, st>>>(a);
+    if (blocks > 148 * 8) blocks = 148 * 8;  // persistent-ish: the plan is amortised over many tiles
+    k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
     return xg_check_launch("xg_vinterp_linear(shared)");
   }
   const int64_t blocks = xg_ceil_div(a.ntiles, kWarpsCol);
