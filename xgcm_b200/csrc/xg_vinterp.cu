@@ -407,6 +407,7 @@ __global__ void __launch_bounds__(kWarpsCol * 32) k_vinterp_columns(const Interp
     T v = __ldg(theta + (int64_t)k * ts);
     return logarithmic ? xg_log<T>(v) : v;
   };
+  bool walk = false;  // this column's theta is NaN-free and sorted: the search is path independent
   if (col_ok) {
     if (!a.bypass_checks) {  // transform.py:27-31: sign test on the NaN-filtered theta
       int kf = 0, kl = n - 1;
@@ -414,19 +415,24 @@ __global__ void __launch_bounds__(kWarpsCol * 32) k_vinterp_columns(const Interp
       while (kl >= 0 && xg_isnan(TH(kl))) --kl;
       if (kf < n && TH(kl) < TH(kf)) flip = true;
     }
-    if (a.mask_edges) {  // transform.py:36-37 nanmax / nanmin (NaN if the column is all-NaN)
-      bool any = false;
-      for (int k = 0; k < n; ++k) {
-        const T v = TH(k);
-        if (xg_isnan(v)) continue;
-        if (!any) { tmin = tmax = v; any = true; }
-        else { tmin = v < tmin ? v : tmin; tmax = v > tmax ? v : tmax; }
-      }
-      if (!any) tmin = tmax = T(NAN);
+    // one pass over the column: nanmax / nanmin (transform.py:36-37; NaN if all-NaN) and whether
+    // the (possibly flipped) theta is NaN-free and non-decreasing
+    bool any = false, nan = false, sorted = true;
+    T prev = T(0);
+    for (int k = 0; k < n; ++k) {
+      const T v = TH(flip ? n - 1 - k : k);
+      if (xg_isnan(v)) { nan = true; continue; }
+      if (!any) { tmin = tmax = v; any = true; }
+      else { tmin = v < tmin ? v : tmin; tmax = v > tmax ? v : tmax; if (v < prev) sorted = false; }
+      prev = v;
     }
+    if (!any) tmin = tmax = T(NAN);
+    walk = !nan && sorted && n > 1;
   }
   auto X = [&](int k) -> double { return (double)TH(flip ? n - 1 - k : k); };
   auto Y = [&](int k) -> double { return (double)__ldg(phi + (int64_t)(flip ? n - 1 - k : k) * ps); };
+  const double x_first = (col_ok && walk) ? X(0) : 0.0;
+  const double x_last = (col_ok && walk) ? X(n - 1) : 0.0;
 
   int guess = 0, cj = -2;
   double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
@@ -443,13 +449,43 @@ __global__ void __launch_bounds__(kWarpsCol * 32) k_vinterp_columns(const Interp
         } else if (x != x) {
           res = x;
         } else {
-          const int j = search_with_guess(x, X, n, guess);
-          guess = j;
+          int j;
+          if (walk) {
+            // sorted NaN-free theta: binary_search_with_guess returns the largest j with
+            // X[j] <= x whatever its guess; targets usually ascend, so walk from the current
+            // interval (sequential, prefetch-friendly) and bisect only on a step backwards
+            if (x > x_last) j = n;
+            else if (x < x_first) j = -1;
+            else if (cj >= 0 && x >= xj) {
+              j = cj;
+              double xn = xj1;
+              while (j + 1 < n && xn <= x) {
+                ++j;
+                if (j + 1 < n) xn = X(j + 1);
+              }
+            } else {
+              int lo = 0, hi = n;
+              while (lo < hi) {
+                const int mid = lo + ((hi - lo) >> 1);
+                if (x >= X(mid)) lo = mid + 1;
+                else hi = mid;
+              }
+              j = lo - 1;
+            }
+          } else {
+            j = search_with_guess(x, X, n, guess);  // literal replay, guess carried along
+            guess = j;
+          }
           if (j == -1) res = Y(0);
           else if (j >= n - 1) res = Y(n - 1);
           else {
             if (j != cj) {
               cj = j;
+              if (walk && j + 1 + kPrefetchRows < n) {
+                const int64_t ahead = flip ? n - 1 - (j + 1 + kPrefetchRows) : j + 1 + kPrefetchRows;
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(phi + ahead * ps));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(theta + ahead * ts));
+              }
               xj = X(j);
               xj1 = X(j + 1);
               yj = Y(j);
