@@ -116,8 +116,9 @@ __device__ __forceinline__ double div_with_recip(double a, double b, double r) {
   return fma(e1, r, q1);
 }
 __device__ __forceinline__ bool exponent_safe(double v) {
-  const double m = fabs(v);
-  return m >= 0x1p-400 && m <= 0x1p400;  // false for 0, NaN, inf
+  // |v| in [2^-400, 2^400]: biased exponent in [623, 1423]; false for 0, subnormals, NaN, inf
+  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  return (e - 623u) <= 800u;
 }
 
 // transposed write-out of a 32-column x nt-target tile
@@ -326,24 +327,25 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
           const int len = run.t_end - run.t_begin;
           if (run.kind <= PK_EXACT) {
             if (run.j != cj) {
-              if (run.j == cj + 1 && cj >= 0) {  // the usual case: walk one interval up
-                yj = yj1;
-                xj = xj1;
-                pj1 += step;
-              } else {
-                pj1 = phi0 + (int64_t)(run.j + 1) * step;
-                yj = (double)__ldg(pj1 - step);
-                xj = Xs[run.j];
+              if (run.j != cj + 1 || cj < 0) {  // rare: a jump — re-seat on node j first
+                pj1 = phi0 + (int64_t)run.j * step;
+                yj1 = (double)__ldg(pj1);
+                xj1 = Xs[run.j];
               }
+              // the usual case: walk one interval up; (xj1, yj1) hold node j already
               cj = run.j;
+              yj = yj1;
+              xj = xj1;
+              pj1 += step;
+              yj1 = (double)__ldg(pj1);
+              xj1 = Xs[cj + 1];
               // targets normally ascend: pull a row a few intervals ahead into L1 now so the next
               // interval switches do not wait on DRAM
               if (cj + 1 + kPrefetchRows < n)
                 asm volatile("prefetch.global.L1 [%0];" ::"l"(pj1 + kPrefetchRows * step));
-              yj1 = (double)__ldg(pj1);
-              xj1 = Xs[cj + 1];
-              const double dyj = yj1 - yj, dxj = xj1 - xj, rr = rdx[cj];
-              slope = (rr != 0.0 && exponent_safe(dyj)) ? div_with_recip(dyj, dxj, rr) : dyj / dxj;
+              const double dyj = yj1 - yj, rr = rdx[cj];
+              if (rr != 0.0 && exponent_safe(dyj)) slope = div_with_recip(dyj, xj1 - xj, rr);
+              else slope = dyj / (xj1 - xj);
             }
             if (run.kind == PK_INTERP) {
               const double* xp = xt + run.t_begin;
