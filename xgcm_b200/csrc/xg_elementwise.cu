@@ -22,6 +22,7 @@ struct PadArgs {
   int lo, hi, bc;
   T fill;
   int64_t nvec_inner;  // vectors per row of `inner`
+  bool small;          // total output vectors < 2^31: 32-bit index math
 };
 
 template <typename T, int VEC>
@@ -30,10 +31,9 @@ __global__ void __launch_bounds__(kThreads) k_pad(const PadArgs<T> a) {
   const int64_t total = a.outer * a.n_out * a.nvec_inner;
   for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < total;
        g += (int64_t)gridDim.x * kThreads) {
-    const int64_t iv = g % a.nvec_inner;
-    const int64_t t = g / a.nvec_inner;
-    const int64_t k = t % a.n_out;
-    const int64_t o = t / a.n_out;
+    int64_t iv, t, k, o;
+    xg_divmod(g, a.nvec_inner, a.small, t, iv);
+    xg_divmod(t, a.n_out, a.small, o, k);
     const int64_t i = iv * VEC;
     const T* base = a.in + o * a.n * a.inner + i;
     int64_t s = k - a.lo;
@@ -91,6 +91,7 @@ int pad_typed(const void* in, void* out, int ndim, const int64_t* shape, int axi
   const bool vec_ok = (v.inner % VEC == 0) && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
   a.nvec_inner = vec_ok ? v.inner / VEC : v.inner;
   const int64_t total = a.outer * a.n_out * a.nvec_inner;
+  a.small = total < (1ll << 31);
   int64_t blocks = xg_ceil_div(total, kThreads);
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (vec_ok)
@@ -108,6 +109,7 @@ struct BinArgs {
   int64_t rows, n, nvec;
   XgOperand b;  // outer groups over rows, axis_stride along the last dim
   int b_vec_ok;
+  bool small;
 };
 
 template <typename T, int OP>
@@ -125,8 +127,9 @@ __global__ void __launch_bounds__(kThreads) k_binary(const BinArgs<T> a) {
   const T* bp = reinterpret_cast<const T*>(a.b.ptr);
   for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < total;
        g += (int64_t)gridDim.x * kThreads) {
-    const int64_t r = g / a.nvec;
-    const int64_t x0 = (g - r * a.nvec) * VEC;
+    int64_t r, xq;
+    xg_divmod(g, a.nvec, a.small, r, xq);
+    const int64_t x0 = xq * VEC;
     const int64_t boff = xg_groups_offset(a.b.outer, r);
     Pack va = xg_ld_stream<T, VEC>(a.a + r * a.n + x0);
     Pack vb;
@@ -150,6 +153,7 @@ __global__ void __launch_bounds__(kThreads) k_binary(const BinArgs<T> a) {
 template <typename T, int VEC>
 int binary_launch(int binop, BinArgs<T>& a, cudaStream_t st) {
   const int64_t total = a.rows * a.nvec;
+  a.small = total < (1ll << 31);
   int64_t blocks = xg_ceil_div(total, kThreads);
   if (blocks > 148 * 32) blocks = 148 * 32;
   switch (binop) {

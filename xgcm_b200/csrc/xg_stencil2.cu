@@ -47,7 +47,7 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 // strided-axis kernel
 // ---------------------------------------------------------------------------
 template <typename T, int VEC, int OP, bool MET, int U>
-__global__ void __launch_bounds__(kThreads, 4)  // <= 64 registers: 4 CTAs (1024 threads) per SM
+__global__ void __launch_bounds__(kThreads, MET ? 3 : 4)  // plain: <= 64 registers, 4 CTAs per SM; fused metrics: 3
 k_stencil_strided(const StencilArgs<T> a) {
   typedef XgPack<T, VEC> Pack;
   const int64_t unit =
@@ -128,12 +128,23 @@ k_stencil_strided(const StencilArgs<T> a) {
   const int64_t jm = (j1 < a.n + a.lo - 1) ? j1 : (a.n + a.lo - 1);
   int64_t j = j0;
   for (; j + U <= jm; j += U) {
-    Pack cur[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) cur[u] = loadA(j + u + 1 - a.lo);
+    Pack cur[U], pm[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      emit(j + u, prev, cur[u]);
+      cur[u] = loadA(j + u + 1 - a.lo);
+      // the divisor is fetched together with the field so its latency overlaps the field's
+      if (has_post) pm[u] = xg_ld_view<T, VEC>(post_v, (j + u) * a.post.axis_stride);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      Pack r;
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) r.v[k] = xg_apply_op<T, OP>(prev.v[k], cur[u].v[k]);
+      if (has_post) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / pm[u].v[k];
+      }
+      xg_st_stream<T, VEC>(obase + (j + u) * a.inner, r);
       prev = cur[u];
     }
   }
@@ -252,7 +263,7 @@ k_stencil_row_vec(const StencilArgs<T> a) {
   int64_t post_base = 0;
   if (MET && a.post.ptr) post_base = xg_groups_offset(a.post.outer, r);
 
-  Pack v[U];
+  Pack v[U], pm[U];
   bool act[U];
   int64_t x0[U];
 #pragma unroll
@@ -262,6 +273,8 @@ k_stencil_row_vec(const StencilArgs<T> a) {
     x0[u] = q * VEC;
     if (act[u]) {
       v[u] = xg_ld_stream<T, VEC>(ra.row + x0[u]);
+      // the divisor is fetched together with the field so its latency overlaps the field's
+      if (MET && a.post.ptr) pm[u] = row_metric<T, VEC>(a.post, post_base, x0[u], a.post_axis_vec_ok);
       if (MET && a.pre.ptr) {
         Pack m = row_metric<T, VEC>(a.pre, ra.pre_base, x0[u], a.pre_axis_vec_ok);
 #pragma unroll
@@ -302,9 +315,8 @@ k_stencil_row_vec(const StencilArgs<T> a) {
     }
     if (act[u]) {
       if (MET && a.post.ptr) {
-        Pack m = row_metric<T, VEC>(a.post, post_base, x0[u], a.post_axis_vec_ok);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) res.v[k] = res.v[k] / m.v[k];
+        for (int k = 0; k < VEC; ++k) res.v[k] = res.v[k] / pm[u].v[k];
       }
       xg_st_stream<T, VEC>(orow + x0[u], res);
     }
