@@ -47,7 +47,7 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 // strided-axis kernel
 // ---------------------------------------------------------------------------
 template <typename T, int VEC, int OP, bool MET, int U>
-__global__ void __launch_bounds__(kThreads, MET ? 3 : 4)  // plain: <= 64 registers, 4 CTAs per SM; fused metrics: 3
+__global__ void __launch_bounds__(kThreads, 4)  // <= 64 registers: 4 CTAs (1024 threads) per SM
 k_stencil_strided(const StencilArgs<T> a) {
   typedef XgPack<T, VEC> Pack;
   const int64_t unit =
@@ -128,24 +128,13 @@ k_stencil_strided(const StencilArgs<T> a) {
   const int64_t jm = (j1 < a.n + a.lo - 1) ? j1 : (a.n + a.lo - 1);
   int64_t j = j0;
   for (; j + U <= jm; j += U) {
-    Pack cur[U], pm[U];
+    Pack cur[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) cur[u] = loadA(j + u + 1 - a.lo);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      cur[u] = loadA(j + u + 1 - a.lo);
-      // the divisor is fetched together with the field so its latency overlaps the field's
-      if (has_post) pm[u] = xg_ld_view<T, VEC>(post_v, (j + u) * a.post.axis_stride);
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      Pack r;
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) r.v[k] = xg_apply_op<T, OP>(prev.v[k], cur[u].v[k]);
-      if (has_post) {
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / pm[u].v[k];
-      }
-      xg_st_stream<T, VEC>(obase + (j + u) * a.inner, r);
-      prev = cur[u];
+      emit(j + u, prev, cur[u]);  // (hoisting the divisor loads here was measured slower: it costs
+      prev = cur[u];              //  16 registers, i.e. one resident CTA per SM)
     }
   }
   for (; j < jm; ++j) {
