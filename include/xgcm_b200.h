@@ -14,6 +14,7 @@
  *                         + xgcm/grid.py:1411-1414 (metric divide)
  *   xg_wreduce         <- xgcm/grid.py:1598-1605 (integrate) and :1680-1685 (average)
  *   xg_vinterp_linear  <- xgcm/transform.py:15-41,44-85 (_interp_1d_linear)
+ *   xg_vinterp_conservative <- xgcm/transform.py:88-191 (_interp_1d_conservative)
  *   xg_pad             <- xgcm/padding.py:765-871 (pad) for callers that want the
  *                         padded array itself (custom grid ufuncs)
  *   xg_binary / xg_unary
@@ -155,6 +156,18 @@ XG_API int xg_vinterp_linear(int dtype, const void* phi, const void* theta,
                       const int64_t* target_strides, int64_t m, void* out, int ndim, const int64_t* shape,
                       int axis, int mask_edges, int bypass_checks,
                       int logarithmic, void* stream);
+
+/*
+ * Conservative remapping (transform.py:88-191): phi holds an extensive quantity per source
+ * cell (n cells along `axis`), theta the n + 1 cell bounds (broadcast via theta_strides),
+ * target_bins m ASCENDING bin edges (shared 1-D).  out: shape-without-axis + (m - 1,), bins
+ * reversed when flip_out (the caller was given decreasing edges).  Field-dtype arithmetic,
+ * contributions per bin added in source-cell order, bins that receive nothing are NaN.
+ */
+XG_API int xg_vinterp_conservative(int dtype, const void* phi, const void* theta,
+                            const int64_t* theta_strides, const void* target_bins,
+                            int64_t m, int flip_out, void* out, int ndim,
+                            const int64_t* shape, int axis, void* stream);
 
 /* The padded array itself (padding.py:765-871), one axis per call. */
 XG_API int xg_pad(int dtype, const void* in, void* out, int ndim,

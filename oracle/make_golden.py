@@ -10,7 +10,9 @@ Outputs (small, committed):
   tests/golden/gridops_table.json   signature + padding_width of each of those GridUFuncs
   tests/golden/interp1d_ref.npz     xgcm.transform.interp_1d_linear (numba gufunc) on random columns
                                     incl. NaN / decreasing theta, all flag combinations
-  tests/golden/transform_cases.json the linear / log entries of the `cases` dict of
+  tests/golden/conservative_ref.npz xgcm.transform.interp_1d_conservative (numba gufunc) incl. NaN bounds,
+                                    decreasing / kinked columns, decreasing bins
+  tests/golden/transform_cases.json the linear / log / conservative entries of the `cases` dict of
                                     xgcm/test/test_transform.py:41-683 (inputs + expected values)
 
 TEST INFRASTRUCTURE ONLY.
@@ -96,6 +98,31 @@ def interp1d_vectors(transform):
     return out
 
 
+def conservative_vectors(transform):
+    rng = np.random.default_rng(11)
+    out = {}
+    for dtype in (np.float32, np.float64):
+        ncol, n, m = 20, 11, 8
+        phi = rng.random((ncol, n)).astype(dtype)
+        theta = np.cumsum(0.3 + rng.random((ncol, n + 1)), axis=-1).astype(dtype)
+        theta[3:6] = theta[3:6, ::-1]            # decreasing columns
+        theta[7, 4:6] = theta[7, 4:6][::-1]      # a non-monotonic kink
+        theta[8, 0] = np.nan
+        theta[9, -1] = np.nan
+        theta[10, 3:5] = np.nan
+        theta[11, 5] = theta[11, 6]              # zero-thickness cell
+        phi[2, 4] = np.nan
+        bins = np.linspace(0.0, float(np.nanmax(theta)) + 0.5, m).astype(dtype)
+        tag = np.dtype(dtype).name
+        out[f"phi|{tag}"] = phi
+        out[f"theta|{tag}"] = theta
+        out[f"bins|{tag}"] = bins
+        with np.errstate(all="ignore"):
+            out[f"out|{tag}|up"] = np.stack([transform.interp_1d_conservative(phi[c], theta[c], bins) for c in range(ncol)])
+            out[f"out|{tag}|down"] = np.stack([transform.interp_1d_conservative(phi[c], theta[c], bins[::-1].copy()) for c in range(ncol)])
+    return out
+
+
 def transform_cases():
     src = (ref_loader.REFERENCE_ROOT / "xgcm" / "test" / "test_transform.py").read_text()
     start = src.index("cases = {")
@@ -120,7 +147,7 @@ def transform_cases():
     keep = {}
     for name, case in cases.items():
         method = case["transform_kwargs"].get("method", "linear")
-        if method not in ("linear", "log"):
+        if method not in ("linear", "log", "conservative"):
             continue
         keep[name] = conv(case)
     return keep
@@ -133,6 +160,7 @@ def main():
     np.savez_compressed(GOLDEN / "gridops_ref.npz", **vec)
     (GOLDEN / "gridops_table.json").write_text(json.dumps(table, indent=1, sort_keys=True))
     np.savez_compressed(GOLDEN / "interp1d_ref.npz", **interp1d_vectors(transform))
+    np.savez_compressed(GOLDEN / "conservative_ref.npz", **conservative_vectors(transform))
     (GOLDEN / "transform_cases.json").write_text(json.dumps(transform_cases(), indent=1, sort_keys=True))
     for p in sorted(GOLDEN.iterdir()):
         print(p.name, p.stat().st_size)

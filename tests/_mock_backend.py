@@ -76,7 +76,25 @@ def install(monkeypatch):
                        logarithmic=False):
         p = _np(phi)
         th = np.broadcast_to(_np(theta), p.shape)
-        return _t(oracle.vinterp_linear(p, th, _np(target), axis, mask_edges, bypass_checks, logarithmic))
+        tg = _np(target)
+        if tg.ndim <= 1:
+            return _t(oracle.vinterp_linear(p, th, tg.reshape(-1), axis, mask_edges, bypass_checks, logarithmic))
+        # one level vector per column: loop the oracle over the columns
+        pm = np.moveaxis(p, axis, -1)
+        tm = np.moveaxis(th, axis, -1)
+        tgb = np.broadcast_to(tg, pm.shape[:-1] + (tg.shape[-1],))
+        cols = pm.reshape(-1, pm.shape[-1])
+        out = [oracle.vinterp_linear(cols[c], tm.reshape(-1, tm.shape[-1])[c], tgb.reshape(-1, tg.shape[-1])[c],
+                                     0, mask_edges, bypass_checks, logarithmic) for c in range(cols.shape[0])]
+        return _t(np.stack(out).reshape(pm.shape[:-1] + (tg.shape[-1],)))
+
+    def vinterp_conservative(phi, theta, target_bins, axis):
+        p = _np(phi)
+        tshape = list(p.shape)
+        tshape[axis] += 1
+        return _t(oracle.vinterp_conservative(p, np.broadcast_to(_np(theta), tshape), _np(target_bins), axis))
+
+    monkeypatch.setattr(ops, "vinterp_conservative", vinterp_conservative)
 
     for name, fn in dict(stencil2=stencil2, stencil2_host=stencil2_host, pad=pad, binary=binary,
                          cumscan=cumscan, wreduce=wreduce, vinterp_linear=vinterp_linear).items():

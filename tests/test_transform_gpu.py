@@ -19,7 +19,80 @@ def _arr(v):
 
 def _cases():
     cases = json.load(open(os.path.join(GOLDEN, "transform_cases.json")))
-    return {k: v for k, v in cases.items() if "multidim_target" not in k}
+    return {k: v for k, v in cases.items()
+            if "multidim_target" not in k and v["transform_kwargs"]["method"] != "conservative"}
+
+
+def _conservative_cases():
+    cases = json.load(open(os.path.join(GOLDEN, "transform_cases.json")))
+    return {k: v for k, v in cases.items()
+            if "multidim_target" not in k and v["transform_kwargs"]["method"] == "conservative"}
+
+
+@pytest.mark.parametrize("name", sorted(_conservative_cases()))
+def test_reference_conservative_cases(name):
+    """xgcm/test/test_transform.py:428-640 + :1041-1069: Grid.transform(method="conservative")."""
+    c = _conservative_cases()[name]
+    sdim, scoord = c["source_coord"]
+    data_vars = {c["source_data"][0]: ((sdim,), _arr(c["source_data"][1]))}
+    if "source_additional_data" in c:
+        data_vars[c["source_additional_data"][0]] = ((c["source_additional_data_coord"][0],), _arr(c["source_additional_data"][1]))
+    coords = {sdim: _arr(scoord)}
+    if "source_bounds_coord" in c:
+        coords[c["source_bounds_coord"][0]] = _arr(c["source_bounds_coord"][1])
+    ds = xg.Dataset(data_vars=data_vars, coords=coords)
+    tdim, tvals = c["target_coord"]
+    target = xg.DataArray(_arr(c["target_data"][1]), dims=(tdim,), coords={tdim: _arr(tvals)}, name=c["target_data"][0])
+    kw = dict(c["transform_kwargs"])
+    if kw.get("target_data"):
+        kw["target_data"] = ds[kw["target_data"]]
+    grid = xg.Grid(ds, **c["grid_kwargs"])
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = grid.transform(ds[c["source_data"][0]], "Z", target, **kw)
+    want = _arr(c["expected_data"][1]).astype(float)
+    assert got.dims == (c["expected_coord"][0],)
+    np.testing.assert_allclose(got.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+    np.testing.assert_allclose(got.coords[c["expected_coord"][0]].values, _arr(c["expected_coord"][1]))
+    # an extensive quantity is conserved (test_transform.py:1036-1038)
+    np.testing.assert_allclose(np.nansum(got.values), np.nansum(_arr(c["source_data"][1])), rtol=1e-6)
+
+
+def test_conservative_reference_numba_golden_vectors():
+    """tests/golden/conservative_ref.npz: outputs of the reference's numba gufunc, bit-exact."""
+    from xgcm_b200.transform import interp_1d_conservative
+
+    g = np.load(os.path.join(GOLDEN, "conservative_ref.npz"))
+    for tag in ("float32", "float64"):
+        phi, theta, bins = g[f"phi|{tag}"], g[f"theta|{tag}"], g[f"bins|{tag}"]
+        for d, b in (("up", bins), ("down", bins[::-1].copy())):
+            got = interp_1d_conservative(phi, theta, b)
+            assert got.dtype == g[f"out|{tag}|{d}"].dtype
+            np.testing.assert_array_equal(got, g[f"out|{tag}|{d}"])
+    with pytest.raises(ValueError, match="not monotonic"):
+        interp_1d_conservative(g["phi|float64"], g["theta|float64"], np.array([0.0, 2.0, 1.0]))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_conservative_3d_field_vs_oracle(dtype):
+    rng = np.random.default_rng(12)
+    nz, ny, nx, m = 14, 6, 40, 11
+    a = rng.random((nz, ny, nx)).astype(dtype)
+    a[rng.random(a.shape) < 0.02] = np.nan
+    bounds = np.cumsum(0.5 + rng.random((nz + 1, ny, nx)), axis=0).astype(dtype)
+    bounds[:, 0, :5] = bounds[::-1, 0, :5]
+    bounds[3, 1, 7] = np.nan
+    ds = xg.Dataset(data_vars={"q": (("z", "y", "x"), a), "sig": (("zo", "y", "x"), bounds)},
+                    coords={"z": np.arange(nz) + 0.5, "zo": np.arange(nz + 1.0)})
+    grid = xg.Grid(ds, coords={"Z": {"center": "z", "outer": "zo"}})
+    bins = np.linspace(0, float(np.nanmax(bounds)) + 1, m).astype(dtype)
+    got = grid.transform(ds["q"], "Z", bins, target_data=ds["sig"], method="conservative")
+    assert got.dims == ("y", "x", "sig") and got.shape == (ny, nx, m - 1)
+    want = oracle.vinterp_conservative(a, bounds, bins, 0)
+    np.testing.assert_array_equal(got.values, want)
+    np.testing.assert_array_equal(got.coords["sig"].values, (bins[1:] + bins[:-1]) / 2)
 
 
 @pytest.mark.parametrize("name", sorted(_cases()))
@@ -56,6 +129,52 @@ def test_reference_transform_cases(name):
     np.testing.assert_allclose(mid.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
     np.testing.assert_allclose(got.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
     np.testing.assert_array_equal(got.coords[c["expected_coord"][0]].values, _arr(c["expected_coord"][1]))
+
+
+@pytest.mark.parametrize("name", ["linear_depth_depth_nomask_multidim_target", "linear_depth_depth_multidim_target"])
+def test_reference_multidim_target_cases(name):
+    """xgcm/test/test_transform.py:122-215: a 2-D target (one level vector per horizontal point)."""
+    c = json.load(open(os.path.join(GOLDEN, "transform_cases.json")))[name]
+    sdim, scoord = c["source_coord"]
+    ds = xg.Dataset(
+        data_vars={c["source_data"][0]: ((sdim,), _arr(c["source_data"][1])),
+                   c["source_additional_data"][0]: ((sdim,), _arr(c["source_additional_data"][1]))},
+        coords={sdim: _arr(scoord)},
+    )
+    tvals = np.array(c["target_data"][1], dtype=float)
+    target = xg.DataArray(tvals, dims=tuple(c["target_dims"]), name=c["target_data"][0])
+    kw = dict(c["transform_kwargs"])
+    kw["target_data"] = ds[kw["target_data"]]
+    grid = xg.Grid(ds, **c["grid_kwargs"])
+    got = grid.transform(ds[c["source_data"][0]], "Z", target, **kw)
+    want = np.array(c["expected_data"][1], dtype=float)
+    for ii in c.get("expected_data_mask_index", []):
+        want[tuple(ii)] = np.nan
+    assert got.dims == tuple(c["expected_dims"])
+    np.testing.assert_allclose(got.values, want, rtol=1e-6, equal_nan=True)
+    with pytest.raises(ValueError, match="target_dim"):
+        kw2 = dict(kw)
+        kw2.pop("target_dim")
+        grid.transform(ds[c["source_data"][0]], "Z", target, **kw2)
+
+
+def test_per_column_targets_3d():
+    """Terrain-following style targets: (Y, X, m) level array against a (Z, Y, X) field."""
+    rng = np.random.default_rng(8)
+    nz, ny, nx, m = 12, 5, 37, 9
+    a = rng.random((nz, ny, nx)).astype(np.float32)
+    depth = np.cumsum(1 + rng.random(nz)).astype(np.float32)
+    ds = xg.Dataset(data_vars={"t": (("z", "y", "x"), a)}, coords={"z": depth})
+    grid = xg.Grid(ds, coords={"Z": {"center": "z"}})
+    tg = (depth[0] + rng.random((ny, nx, m)) * (depth[-1] - depth[0]) * 1.2 - 0.5).astype(np.float32)
+    tg.sort(axis=-1)
+    got = grid.transform(ds["t"], "Z", xg.DataArray(tg, dims=("y", "x", "lev")), target_dim="lev")
+    assert got.dims == ("y", "x", "lev")
+    want = np.empty((ny, nx, m), np.float32)
+    for j in range(ny):
+        for i in range(nx):
+            want[j, i] = oracle.vinterp_linear(a[:, j, i], depth, tg[j, i], 0, True)
+    np.testing.assert_array_equal(got.values, want)
 
 
 def test_reference_numba_golden_vectors():
@@ -127,5 +246,5 @@ def test_transform_errors():
     grid = xg.Grid(ds, coords={"Z": {"center": "z"}})
     with pytest.raises(ValueError):
         grid.transform(ds["t"], "Z", [1, 2, 3])  # list target: must be ndarray / DataArray
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="outer"):
         grid.transform(ds["t"], "Z", np.arange(3.0), method="conservative")

@@ -52,6 +52,10 @@ SIGNATURES = {
         [C.c_int, _vp, _vp, _i64p, _vp, _i64p, C.c_int64, _vp, C.c_int, _i64p, C.c_int, C.c_int,
          C.c_int, C.c_int, _vp],
     ),
+    "xg_vinterp_conservative": (
+        C.c_int,
+        [C.c_int, _vp, _vp, _i64p, _vp, C.c_int64, C.c_int, _vp, C.c_int, _i64p, C.c_int, _vp],
+    ),
     "xg_pad": (
         C.c_int,
         [C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp],

@@ -302,6 +302,49 @@ def vinterp_linear(phi: torch.Tensor, theta: torch.Tensor, target: torch.Tensor,
     return out
 
 
+def vinterp_conservative(phi: torch.Tensor, theta: torch.Tensor, target_bins: torch.Tensor,
+                         axis: int) -> torch.Tensor:
+    """Conservative remapping of an extensive ``phi`` (n cells along ``axis``) bounded by
+    ``theta`` (n + 1 bounds along ``axis``, broadcast elsewhere) into the bins delimited by the
+    monotonic 1-D ``target_bins`` (transform.py:88-191).  New dim (m - 1 bins) LAST."""
+    lib = _capi.load()
+    _require_cuda(phi, "phi")
+    _require_cuda(theta, "theta")
+    _require_cuda(target_bins, "target_bins")
+    if not (phi.dtype == theta.dtype == target_bins.dtype == torch.float32):
+        phi, theta, target_bins = phi.to(torch.float64), theta.to(torch.float64), target_bins.to(torch.float64)
+    if target_bins.dim() != 1:
+        raise ValueError("target bins must be 1-D")
+    phi = phi.contiguous()
+    axis = _norm_axis(axis, phi.dim())
+    shape = list(phi.shape)
+    tshape = list(shape)
+    tshape[axis] = shape[axis] + 1
+    if theta.dim() == phi.dim() and theta.shape[axis] != tshape[axis]:
+        raise ValueError(
+            f"theta needs {tshape[axis]} cell bounds along the axis, got {theta.shape[axis]}"
+        )  # transform.py:162 assert phi.shape[-1] == theta.shape[-1] - 1
+    diffs = target_bins[1:] - target_bins[:-1]
+    if bool((diffs < 0).all()):  # transform.py:167-176
+        flip, bins = 1, torch.flip(target_bins, dims=(0,)).contiguous()
+    elif bool((diffs > 0).all()):
+        flip, bins = 0, target_bins.contiguous()
+    else:
+        raise ValueError("Target values are not monotonic")
+    keep, th_ptr, th_st = _operand(theta, tshape, phi, "theta")
+    m = int(bins.numel())
+    out_shape = [s for d, s in enumerate(shape) if d != axis] + [m - 1]
+    out = torch.empty(out_shape, dtype=phi.dtype, device=phi.device)
+    if out.numel():
+        with torch.cuda.device(phi.device):
+            rc = lib.xg_vinterp_conservative(
+                _dtype_code(phi), phi.data_ptr(), th_ptr, th_st, bins.data_ptr(), m, flip,
+                out.data_ptr(), phi.dim(), _capi.i64_array(shape), axis, _stream_ptr(phi),
+            )
+        _capi.check(rc)
+    return out
+
+
 def fill_uniform(out: torch.Tensor, seed: int, offset: int = 0) -> torch.Tensor:
     """Deterministic U(0,1) synthetic field keyed by (seed, offset + flat index)."""
     lib = _capi.load()

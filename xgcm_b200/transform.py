@@ -3,9 +3,8 @@
 Mid-level logic (argument checks, target parsing, naming, output dim order)
 follows the reference's ``xgcm/transform.py:279-514``; the per-column numerics
 (``_interp_1d_linear``, transform.py:15-41, a numba CPU gufunc in the reference)
-run in the ``xg_vinterp_linear`` CUDA kernel.  Methods ``linear`` and ``log`` are
-implemented; ``conservative`` (transform.py:88-191) is a "next" row of the scope
-table and raises ``NotImplementedError``.
+run in the ``xg_vinterp_linear`` CUDA kernel; ``method="conservative"``
+(transform.py:88-191, 252-276) runs in ``xg_vinterp_conservative``.
 """
 
 from __future__ import annotations
@@ -39,21 +38,113 @@ def interp_1d_linear(phi, theta, target_theta_levels, mask_edges=False, bypass_c
 def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, target_dim,
                          mask_edges=True, bypass_checks=False, logarithmic=False, suffix="",
                          grid=None):
-    """Labelled wrapper (transform.py:197-249): broadcast dims by name, new dim LAST."""
-    import torch
+    """Labelled wrapper (transform.py:197-249): broadcast dims by name, new dim LAST.
 
+    ``target_theta_levels`` may be 1-D (shared levels) or carry extra dims (one level vector per
+    column, e.g. terrain-following target depths); dims it has that ``phi`` lacks become
+    broadcast dims of the output, like ``xr.apply_ufunc`` does.
+    """
     from . import ops
     from .device import as_device_tensor, result_like
 
     if theta_dim not in theta.dims:
         raise ValueError(f"`target_data` must have the dimension {theta_dim!r} of the transform axis")
+    if target_dim not in target_theta_levels.dims:
+        raise ValueError(
+            f"The specified `target_dim` {target_dim} is not within the dimensions of the target: [{target_theta_levels.dims}]."
+        )
     device = grid._device_for(phi) if grid is not None else None
     x, host = as_device_tensor(phi.data, device)
-    axis_num = phi.get_axis_num(phi_dim)
-    # theta -> tensor broadcastable against phi's dims
+    # theta dims other than the core dim must already be dims of phi
     extra = [d for d in theta.dims if d not in phi.dims and d != theta_dim]
     if extra:
         raise ValueError(f"target data has dimensions {extra} that the data does not have")
+    tgt_other = [d for d in target_theta_levels.dims if d != target_dim]
+    new_dims = [d for d in tgt_other if d not in phi.dims]
+    for d in tgt_other:
+        if d in phi.dims and phi.sizes[d] != target_theta_levels.sizes[d]:
+            raise ValueError(f"conflicting sizes for dimension {d!r} between the data and the target")
+    work_dims = list(phi.dims) + new_dims  # phi gains broadcast dims the target introduces
+    if new_dims:
+        shape = list(x.shape) + [target_theta_levels.sizes[d] for d in new_dims]
+        x = x.reshape(list(x.shape) + [1] * len(new_dims)).expand(shape).contiguous()
+    axis_num = work_dims.index(phi_dim)
+    # theta -> tensor broadcastable against the working dims
+    th_dims = [d if d != theta_dim else phi_dim for d in theta.dims]
+    th_t, _ = as_device_tensor(theta.data, x.device)
+    present = [d for d in work_dims if d in th_dims]
+    perm = [th_dims.index(d) for d in present]
+    if perm != list(range(len(perm))):
+        th_t = th_t.permute(*perm)
+    sizes = dict(zip(th_dims, theta.shape))
+    if sizes[phi_dim] != phi.sizes[phi_dim]:
+        raise ValueError(
+            f"conflicting sizes for dimension {phi_dim!r}: {phi.sizes[phi_dim]} on the data, "
+            f"{sizes[phi_dim]} on the target data"
+        )
+    th_t = th_t.reshape([sizes[d] if d in th_dims else 1 for d in work_dims])
+    # target -> (column dims..., m)
+    col_dims = [d for d in work_dims if d != phi_dim]
+    tg_t, _ = as_device_tensor(target_theta_levels.data, x.device)
+    if tgt_other:
+        tdims = list(target_theta_levels.dims)
+        order = [d for d in col_dims if d in tdims] + [target_dim]
+        perm = [tdims.index(d) for d in order]
+        if perm != list(range(len(perm))):
+            tg_t = tg_t.permute(*perm)
+        tsz = target_theta_levels.sizes
+        tg_t = tg_t.reshape([tsz[d] if d in tdims else 1 for d in col_dims] + [tsz[target_dim]])
+    out = ops.vinterp_linear(x, th_t, tg_t, axis_num, mask_edges, bypass_checks, logarithmic)
+    out_dims = tuple(col_dims) + (target_dim,)
+    # like xr.apply_ufunc with exclude_dims: nothing that lives on the consumed core dim survives
+    coords = {k: c for k, c in phi.coords.items()
+              if phi_dim not in c.dims and k != target_dim and all(d in out_dims for d in c.dims)}
+    for k, c in target_theta_levels.coords.items():
+        if all(d in out_dims for d in c.dims):
+            coords[k] = c
+    res = DataArray(result_like(out, host), dims=out_dims, coords=coords)
+    if phi.name:
+        res.name = phi.name + suffix
+    return res
+
+
+def interp_1d_conservative(phi, theta, target_theta_bins):
+    """Array-level entry point with the reference's signature (transform.py:145-191):
+    ``phi[..., n], theta[..., n+1], bins[m] -> [..., m-1]`` along the LAST axis."""
+    from . import ops
+    from .device import as_device_tensor, result_like
+
+    p, host = as_device_tensor(phi)
+    th, _ = as_device_tensor(theta, p.device)
+    tb, _ = as_device_tensor(target_theta_bins, p.device)
+    if p.shape[-1] != th.shape[-1] - 1:
+        raise AssertionError("phi needs one value per cell: phi.shape[-1] == theta.shape[-1] - 1")
+    if tb.dim() != 1:
+        raise AssertionError("target_theta_bins must be 1-D")
+    if th.dim() < p.dim():
+        th = th.reshape((1,) * (p.dim() - th.dim()) + tuple(th.shape))
+    return result_like(ops.vinterp_conservative(p, th, tb, -1), host)
+
+
+def conservative_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, target_dim,
+                               suffix="", grid=None):
+    """Labelled wrapper (transform.py:252-276): bins along ``target_dim`` (one fewer than the
+    levels), coordinate = bin centres."""
+    from . import ops
+    from .device import as_device_tensor, result_like
+
+    if theta_dim not in theta.dims:
+        raise ValueError(f"`target_data` must have the cell-bounds dimension {theta_dim!r}")
+    if target_theta_levels.ndim != 1:
+        raise NotImplementedError(
+            "Conservative transformation is not yet supported for multi-dimensional targets."
+        )
+    device = grid._device_for(phi) if grid is not None else None
+    x, host = as_device_tensor(phi.data, device)
+    extra = [d for d in theta.dims if d not in phi.dims and d != theta_dim]
+    if extra:
+        raise ValueError(f"target data has dimensions {extra} that the data does not have")
+    axis_num = phi.get_axis_num(phi_dim)
     th_dims = [d if d != theta_dim else phi_dim for d in theta.dims]
     th_t, _ = as_device_tensor(theta.data, x.device)
     present = [d for d in phi.dims if d in th_dims]
@@ -61,21 +152,18 @@ def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, ta
     if perm != list(range(len(perm))):
         th_t = th_t.permute(*perm)
     sizes = dict(zip(th_dims, theta.shape))
-    th_t = th_t.reshape([sizes[d] if d in th_dims else 1 for d in phi.dims])
-    if sizes[phi_dim] != phi.sizes[phi_dim]:
+    if sizes[phi_dim] != phi.sizes[phi_dim] + 1:
         raise ValueError(
-            f"conflicting sizes for dimension {phi_dim!r}: {phi.sizes[phi_dim]} on the data, "
-            f"{sizes[phi_dim]} on the target data"
+            f"`target_data` needs {phi.sizes[phi_dim] + 1} cell bounds along {theta_dim!r}, got {sizes[phi_dim]}"
         )
+    th_t = th_t.reshape([sizes[d] if d in th_dims else 1 for d in phi.dims])
     tg_t, _ = as_device_tensor(target_theta_levels.data, x.device)
-    out = ops.vinterp_linear(x, th_t, tg_t, axis_num, mask_edges, bypass_checks, logarithmic)
+    out = ops.vinterp_conservative(x, th_t, tg_t, axis_num)
     out_dims = tuple(d for d in phi.dims if d != phi_dim) + (target_dim,)
-    # like xr.apply_ufunc with exclude_dims: nothing that lives on the consumed core dim survives
     coords = {k: c for k, c in phi.coords.items()
               if phi_dim not in c.dims and k != target_dim and all(d in out_dims for d in c.dims)}
-    for k, c in target_theta_levels.coords.items():
-        if all(d in out_dims for d in c.dims):
-            coords[k] = c
+    levels = target_theta_levels.values
+    coords[target_dim] = ((target_dim,), (levels[1:] + levels[:-1]) / 2)  # transform.py:270-272
     res = DataArray(result_like(out, host), dims=out_dims, coords=coords)
     if phi.name:
         res.name = phi.name + suffix
@@ -132,10 +220,13 @@ def transform(grid, axis_name, da, target, target_data=None, target_dim=None, me
                 target_dim = target_data.name
         if not isinstance(target, DataArray):
             target = DataArray(target, dims=[target_dim], coords={target_dim: target})
-        if target_dim is None or target.ndim != 1:
-            raise NotImplementedError(
-                "multi-dimensional `target` arrays are not supported by xgcm_b200 "
-                "(the kernel takes one shared 1-D level vector)"
+        if target_dim is None:
+            raise ValueError(
+                "`target` has more than one dimension: `target_dim` must be given explicitly"
+            )
+        if target_dim not in target.dims:
+            raise ValueError(
+                f"The specified `target_dim` {target_dim} is not within the dimensions of the target: [{target.dims}]."
             )
         _check_other_dims(target_data)
         return target, target_dim, target_data
@@ -156,8 +247,22 @@ def transform(grid, axis_name, da, target, target_data=None, target_dim=None, me
             # the output keeps the input's name; only the mid-level wrapper honours `suffix`.
         )
     if method == "conservative":
-        raise NotImplementedError(
-            "method='conservative' (reference transform.py:88-191) is not part of the xgcm_b200 "
-            "hot-path scope yet"
-        )
+        if isinstance(target, DataArray) and len(target.dims) > 1:
+            raise NotImplementedError(
+                "Conservative transformation is not yet supported for multi-dimensional targets."
+            )
+        try:
+            target_data_dim = axis.coords["outer"]
+        except KeyError:
+            raise RuntimeError(
+                "In order to use the method `conservative` the grid object needs to have `outer` coordinates."
+            )
+        target, target_dim, target_data = _parse_target(target, target_dim, target_data_dim, target_data)
+        if target_data_dim not in target_data.dims:
+            warnings.warn(
+                "The `target data` input is not located on the cell bounds. This method will continue with linear interpolation with repeated boundary values. For most accurate results provide values on cell bounds.",
+                UserWarning,
+            )
+            target_data = grid.interp(target_data, axis_name, padding="extend")
+        return conservative_interpolation(da, target_data, target, dim, target_data_dim, target_dim, grid=grid)
     raise ValueError(f"unknown transform method {method!r}")
