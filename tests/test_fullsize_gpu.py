@@ -1,0 +1,107 @@
+"""BASELINE.json's full sizes (config 3: 75 x 2400 x 3600 fp32, 648 M cells) and a > 2^31-element
+field: the oracle cannot hold these in seconds, so parity is checked through size-independent
+properties — any sub-block of the full-size result must equal the oracle applied to the matching
+input sub-block (plus its halo), bit for bit."""
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import stencil as oracle
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _field(shape, seed):
+    from xgcm_b200 import ops
+
+    x = torch.empty(shape, dtype=torch.float32, device=DEV)
+    return ops.fill_uniform(x, seed)
+
+
+def _check_axis_blocks(x, out, axis, op, lo, hi, bc, fill, rng, nblocks=12):
+    """Compare random full lines along `axis` (all cells of the operated axis, a small window of the
+    other dims) against the oracle."""
+    shape = x.shape
+    for _ in range(nblocks):
+        sl = []
+        for d, n in enumerate(shape):
+            if d == axis:
+                sl.append(slice(None))
+            else:
+                w = min(n, 5)
+                s0 = int(rng.integers(0, n - w + 1))
+                sl.append(slice(s0, s0 + w))
+        a = x[tuple(sl)].cpu().numpy()
+        want = oracle.stencil2(op, a, axis, lo, hi, bc if (lo or hi) else None, fill)
+        np.testing.assert_array_equal(out[tuple(sl)].cpu().numpy(), want)
+
+
+def test_config3_full_size_stencils():
+    from xgcm_b200 import ops
+
+    shape = (75, 2400, 3600)
+    x = _field(shape, 0xC0FFEE)
+    rng = np.random.default_rng(0)
+    for axis, (lo, hi), bc, fill in [(2, (1, 0), "periodic", 0.0), (1, (0, 1), "fill", 1.5), (0, (1, 0), "extend", 0.0),
+                                     (0, (1, 1), "fill", 0.0), (2, (0, 0), None, 0.0), (1, (1, 1), "periodic", 0.0)]:
+        for op in ("diff", "interp"):
+            out = ops.stencil2(x, axis, op, lo, hi, bc, fill)
+            _check_axis_blocks(x, out, axis, op, lo, hi, bc, fill, rng)
+            del out
+
+
+def test_config3_full_size_integrate_cumsum_transform():
+    from xgcm_b200 import ops
+
+    shape = (75, 2400, 3600)
+    x = _field(shape, 7)
+    rng = np.random.default_rng(1)
+    dz = torch.from_numpy((10 * 1.05 ** np.arange(75)).astype(np.float32)).to(DEV).reshape(75, 1, 1)
+    got = ops.wreduce(x, 0, dz, "sum")
+    for _ in range(8):
+        j, i = int(rng.integers(0, 2396)), int(rng.integers(0, 3596))
+        a = x[:, j:j + 4, i:i + 4].cpu().numpy()
+        np.testing.assert_array_equal(got[j:j + 4, i:i + 4].cpu().numpy(), oracle.wreduce(a, dz.cpu().numpy(), 0))
+    for axis in (0, 1, 2):
+        c = ops.cumscan(x, axis, False, "drop_last", 1, 0, "fill", 0.0)
+        for _ in range(6):
+            sl = [slice(int(s0), int(s0) + 3) for s0 in (rng.integers(0, n - 3) for n in shape)]
+            sl[axis] = slice(None)
+            a = x[tuple(sl)].cpu().numpy()
+            np.testing.assert_array_equal(c[tuple(sl)].cpu().numpy(), oracle.cumscan(a, axis, False, "drop_last", 1, 0, "fill", 0.0))
+        del c
+    depth = torch.cumsum(dz.reshape(-1), 0)
+    levels = torch.linspace(float(depth[0]) - 5, float(depth[-1]) + 5, 100, device=DEV)
+    t = ops.vinterp_linear(x, depth.reshape(-1, 1, 1), levels, 0, True)
+    assert t.shape == (2400, 3600, 100)
+    for _ in range(6):
+        j, i = int(rng.integers(0, 2396)), int(rng.integers(0, 3596))
+        a = x[:, j:j + 4, i:i + 4].cpu().numpy()
+        want = oracle.vinterp_linear(a, depth.cpu().numpy().reshape(-1, 1, 1) * np.ones((1, 4, 4), np.float32), levels.cpu().numpy(), 0, True)
+        np.testing.assert_array_equal(t[j:j + 4, i:i + 4].cpu().numpy(), want)
+
+
+def test_more_than_2_31_elements():
+    """64-bit indexing: 2.42 G cells (9.7 GB) per field."""
+    from xgcm_b200 import ops
+
+    shape = (9, 16384, 16400)
+    assert np.prod(shape) > 2**31
+    x = _field(shape, 3)
+    rng = np.random.default_rng(2)
+    for axis, (lo, hi), bc in [(2, (1, 0), "periodic"), (1, (0, 1), "extend"), (0, (1, 0), "fill")]:
+        out = ops.stencil2(x, axis, "diff", lo, hi, bc, 2.0)
+        _check_axis_blocks(x, out, axis, "diff", lo, hi, bc, 2.0, rng, nblocks=6)
+        # the far corner of the array (flat offsets beyond 2^31)
+        sl = [slice(n - 3, n) for n in shape]
+        sl[axis] = slice(None)
+        a = x[tuple(sl)].cpu().numpy()
+        np.testing.assert_array_equal(out[tuple(sl)].cpu().numpy(), oracle.stencil2("diff", a, axis, lo, hi, bc, 2.0))
+        del out
+    s = ops.wreduce(x, 0, None, "sum")
+    np.testing.assert_array_equal(s[-2:, -5:].cpu().numpy(), x[:, -2:, -5:].cpu().numpy().sum(axis=0))
+    del s
+    c = ops.cumscan(x, 2)
+    np.testing.assert_array_equal(c[-1, -1, :].cpu().numpy(), np.cumsum(x[-1, -1, :].cpu().numpy()))
