@@ -118,6 +118,17 @@ XG_API int xg_stencil2(int op, int dtype, const void* in, void* out, int ndim,
                 const void* halo_hi, void* stream);
 
 /*
+ * 2 or 3 single-axis stencils fused into one pass: the result equals applying xg_stencil2 along
+ * axes[0], then axes[1] (, then axes[2]) — each with its own op / halo / boundary acting on the
+ * previous intermediate, every intermediate rounded to the field dtype — but the field is read
+ * and written once (xgcm/grid.py:798-832 makes one full pass per axis).  Boundaries: periodic,
+ * fill, extend.  Output extent along axes[k] = n + lo[k] + hi[k] - 1.
+ */
+XG_API int xg_stencil_multi(int dtype, const void* in, void* out, int ndim, const int64_t* shape,
+                     int naxes, const int* axes, const int* ops, const int* lo, const int* hi,
+                     const int* bc, const double* fill_value, void* stream);
+
+/*
  * Cumulative sum along one axis with xgcm's position-shift bookkeeping:
  * c = cumsum(in * pre) (from the high end when reverse), then trim, then pad
  * (pad_lo, pad_hi in {0,1}) with `bc` applied to the cumsum'd data, then / post.

@@ -88,6 +88,14 @@ def install(monkeypatch):
                                      0, mask_edges, bypass_checks, logarithmic) for c in range(cols.shape[0])]
         return _t(np.stack(out).reshape(pm.shape[:-1] + (tg.shape[-1],)))
 
+    def stencil_multi(x, specs):
+        r = _np(x)
+        for axis, op, lo, hi, padding, fill in specs:
+            r = oracle.stencil2(op, r, axis, lo, hi, padding if (lo or hi) else None, fill)
+        return _t(r.astype(_np(x).dtype))
+
+    monkeypatch.setattr(ops, "stencil_multi", stencil_multi)
+
     def vinterp_conservative(phi, theta, target_bins, axis):
         p = _np(phi)
         tshape = list(p.shape)

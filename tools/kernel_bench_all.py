@@ -59,6 +59,9 @@ def main():
         out = torch.empty_like(x)
         report(f"stencil2 diff {names[ax]} c->l periodic", timeit(lambda: ops.stencil2(x, ax, "diff", 1, 0, "periodic", out=out)), 2 * cells * es)
         del out
+    report("stencil_multi interp X then Y (fused, 1 pass)", timeit(lambda: ops.stencil_multi(x, [(2, "interp", 1, 0, "periodic", 0.0), (1, "interp", 1, 0, "fill", 0.0)])), 2 * cells * es)
+    report("stencil_multi interp Y then Z (fused, 1 pass)", timeit(lambda: ops.stencil_multi(x, [(1, "interp", 1, 0, "fill", 0.0), (0, "interp", 1, 0, "extend", 0.0)])), 2 * cells * es)
+    report("stencil_multi interp X,Y,Z (fused, 1 pass)", timeit(lambda: ops.stencil_multi(x, [(2, "interp", 1, 0, "periodic", 0.0), (1, "interp", 1, 0, "fill", 0.0), (0, "interp", 1, 0, "extend", 0.0)])), 2 * cells * es)
     # metric-weighted derivative along X with 2-D dx (Y, X) and along Z with 1-D dz
     dx = (1 + torch.rand((1, shape[1], shape[2]), device="cuda", dtype=dt))
     dz = (1 + torch.rand((shape[0], 1, 1), device="cuda", dtype=dt))

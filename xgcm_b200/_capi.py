@@ -38,6 +38,11 @@ SIGNATURES = {
         [C.c_int, C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int,
          C.c_double, _vp, _i64p, _vp, _i64p, _vp, _vp, _vp],
     ),
+    "xg_stencil_multi": (
+        C.c_int,
+        [C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+         C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_double), _vp],
+    ),
     "xg_cumscan": (
         C.c_int,
         [C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -1,0 +1,324 @@
+// xg_stencil_multi — 2 or 3 single-axis stencils fused into ONE pass over HBM.
+//
+// `Grid.interp(da, ['X', 'Y'])` (and diff / min / max over several axes) is, in the reference,
+// one full pad + ufunc pass per axis (xgcm/grid.py:798-832; its own TODO notes the waste).  Here
+// the chain  op_K(pad_K( ... op_1(pad_1(a)) ... ))  is evaluated per output cell straight from the
+// input: 2^K neighbour loads (absorbed by L1 / L2: DRAM sees one read and one write per cell),
+// every intermediate rounded to the field dtype exactly where the sequential passes would round,
+// each axis with its own halo rule applied to ITS intermediate (fill is a constant of that level,
+// periodic / extend re-index the source).  Bit-identical to K consecutive xg_stencil2 calls at
+// 1/K of their traffic.
+//
+// Work split: a block owns one output row along the innermost dim; threads take 16-byte vectors
+// of it.  The recursion is resolved at compile time (K ops, position LAST of the op acting on the
+// innermost dim, or -1): row ops combine two windows of W values; the innermost op consumes a
+// window of W + 1 consecutive source positions (one aligned vector + one neighbour element).
+//
+// Roofline: HBM, 2 * sizeof(T) bytes per output cell.
+#include "xg_common.cuh"
+
+namespace {
+
+constexpr int kMaxAx = 3;
+constexpr int kMaxGroups = 2 * kMaxAx;  // row groups (everything but the innermost group)
+
+template <typename T>
+struct AxisOp {
+  int op, lo, hi, bc;
+  T fill;
+  int64_t n;          // input (and intermediate) length along this axis
+  int64_t in_stride;  // element stride of this axis in the INPUT (1 for the innermost dim)
+};
+
+template <typename T>
+struct MultiArgs {
+  const T* in;
+  T* out;
+  AxisOp<T> ax[kMaxAx];  // in application order
+  int nrow_groups;
+  int64_t row_size[kMaxGroups];        // extent in the OUTPUT, outermost first
+  int64_t row_in_stride[kMaxGroups];   // input element stride (non-operated groups)
+  int64_t row_out_stride[kMaxGroups];  // output element stride
+  int row_axis[kMaxGroups];            // application index of the operated axis, or -1
+  int64_t last_n_out;                  // output extent of the innermost group
+};
+
+template <typename T>
+__device__ __forceinline__ T apply_rt(int op, T a, T b) {
+  switch (op) {
+    case XG_OP_DIFF: return xg_apply_op<T, XG_OP_DIFF>(a, b);
+    case XG_OP_INTERP: return xg_apply_op<T, XG_OP_INTERP>(a, b);
+    case XG_OP_MIN: return xg_apply_op<T, XG_OP_MIN>(a, b);
+    default: return xg_apply_op<T, XG_OP_MAX>(a, b);
+  }
+}
+
+// source index of padded position idx along an axis; false when the halo is the fill constant
+template <typename T>
+__device__ __forceinline__ bool resolve(const AxisOp<T>& a, int64_t idx, int64_t& s) {
+  s = idx - a.lo;
+  if (s < 0) {
+    if (a.bc == XG_BC_FILL) { s = 0; return false; }
+    s = (a.bc == XG_BC_PERIODIC) ? s + a.n : 0;
+  } else if (s >= a.n) {
+    if (a.bc == XG_BC_FILL) { s = a.n - 1; return false; }
+    s = (a.bc == XG_BC_PERIODIC) ? s - a.n : a.n - 1;
+  }
+  return true;
+}
+
+template <typename T, int W>
+struct Win {
+  T v[W];
+};
+
+// W consecutive input elements along the innermost dim starting at source position xs (which may
+// be -1, and xs + W - 1 may be n, only when the innermost dim is operated: those ends follow the
+// halo rule of that op; a fill halo is patched by the caller, here it just reads a valid cell).
+template <typename T, int VEC, int W, int LAST>
+__device__ __forceinline__ Win<T, W> load_window(const MultiArgs<T>& a, int64_t off, int64_t xs) {
+  Win<T, W> r;
+  const T* p = a.in + off;
+  if constexpr (LAST < 0) {
+    static_assert(W == VEC, "window == vector when the innermost dim is not operated");
+    XgPack<T, VEC> pk = xg_ld_cached<T, VEC>(p + xs);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) r.v[q] = pk.v[q];
+  } else {
+    const AxisOp<T>& ax = a.ax[LAST];
+    auto scalar_at = [&](int64_t pos) -> T {
+      if (pos < 0) pos = (ax.bc == XG_BC_PERIODIC) ? pos + ax.n : 0;
+      else if (pos >= ax.n) pos = (ax.bc == XG_BC_PERIODIC) ? pos - ax.n : ax.n - 1;
+      return __ldg(p + pos);
+    };
+    if constexpr (VEC > 1 && W == VEC + 1) {
+      // exactly one aligned vector plus one neighbour: xs = x0 - lo with x0 a multiple of VEC
+      const bool lead = (xs & (VEC - 1)) != 0;  // lo == 1: the neighbour comes first
+      const int64_t xv = lead ? xs + 1 : xs;
+      XgPack<T, VEC> pk = xg_ld_cached<T, VEC>(p + xv);
+      const T extra = scalar_at(lead ? xs : xs + VEC);
+#pragma unroll
+      for (int q = 0; q < VEC; ++q) r.v[lead ? q + 1 : q] = pk.v[q];
+      r.v[lead ? 0 : VEC] = extra;
+    } else {
+#pragma unroll
+      for (int q = 0; q < W; ++q) r.v[q] = scalar_at(xs + q);
+    }
+  }
+  return r;
+}
+
+// Window of W values of the intermediate after the first k ops, at row coordinates j (axes < k
+// in their output space; axes >= k already folded into `off`), innermost coordinate x.
+template <typename T, int VEC, int K, int LAST>
+struct Eval {
+  template <int k, int W>
+  static __device__ __forceinline__ Win<T, W> run(const MultiArgs<T>& a, const int64_t* j, int64_t off,
+                                                   int64_t x) {
+    if constexpr (k == 0) {
+      return load_window<T, VEC, W, LAST>(a, off, x);
+    } else {
+      constexpr int m = k - 1;  // the op applied at this level
+      const AxisOp<T>& ax = a.ax[m];
+      Win<T, W> r;
+      if constexpr (m == LAST) {
+        // innermost op: padded positions x .. x+W  <-  sources x-lo .. x-lo+W
+        const int64_t xs = x - ax.lo;
+        Win<T, W + 1> w = run<k - 1, W + 1>(a, j, off, xs);
+        if (ax.bc == XG_BC_FILL) {  // the ends of the window may be halo cells of THIS level
+          if (xs < 0) w.v[0] = ax.fill;
+          if (xs + W >= ax.n) w.v[W] = ax.fill;
+        }
+#pragma unroll
+        for (int q = 0; q < W; ++q) r.v[q] = apply_rt<T>(ax.op, w.v[q], w.v[q + 1]);
+      } else {
+        int64_t s0, s1;
+        const bool ok0 = resolve(ax, j[m], s0);  // block-uniform: j is this block's row
+        const bool ok1 = resolve(ax, j[m] + 1, s1);
+        Win<T, W> lo_v, hi_v;
+        if (ok0) lo_v = run<k - 1, W>(a, j, off + s0 * ax.in_stride, x);
+        else {
+#pragma unroll
+          for (int q = 0; q < W; ++q) lo_v.v[q] = ax.fill;
+        }
+        if (ok1) hi_v = run<k - 1, W>(a, j, off + s1 * ax.in_stride, x);
+        else {
+#pragma unroll
+          for (int q = 0; q < W; ++q) hi_v.v[q] = ax.fill;
+        }
+#pragma unroll
+        for (int q = 0; q < W; ++q) r.v[q] = apply_rt<T>(ax.op, lo_v.v[q], hi_v.v[q]);
+      }
+      return r;
+    }
+  }
+};
+
+template <typename T, int VEC, int K, int LAST>
+__global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
+  // this block's output row: coordinates of the operated row axes, source offset of the
+  // non-operated groups, output offset
+  int64_t row = blockIdx.x;
+  int64_t j[kMaxAx] = {0, 0, 0};
+  int64_t off_in = 0, off_out = 0;
+#pragma unroll
+  for (int g = kMaxGroups - 1; g >= 0; --g) {
+    if (g < a.nrow_groups) {
+      const int64_t q = row / a.row_size[g];
+      const int64_t c = row - q * a.row_size[g];
+      row = q;
+      off_out += c * a.row_out_stride[g];
+      if (a.row_axis[g] >= 0) j[a.row_axis[g]] = c;
+      else off_in += c * a.row_in_stride[g];
+    }
+  }
+  const int64_t nvec = (a.last_n_out + VEC - 1) / VEC;  // exact when VEC > 1 (host guarantees it)
+  T* orow = a.out + off_out;
+  for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
+    const int64_t x0 = v * VEC;
+    Win<T, VEC> r = Eval<T, VEC, K, LAST>::template run<K, VEC>(a, j, off_in, x0);
+    XgPack<T, VEC> res;
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) res.v[q] = r.v[q];
+    xg_st_stream<T, VEC>(orow + x0, res);
+  }
+}
+
+template <typename T, int VEC, int K>
+int launch_last(int last, const MultiArgs<T>& a, int64_t nrows, int threads, cudaStream_t st) {
+  const unsigned grid = (unsigned)nrows;
+  switch (last) {
+    case -1: k_stencil_multi<T, VEC, K, -1><<<grid, threads, 0, st>>>(a); break;
+    case 0: k_stencil_multi<T, VEC, K, 0><<<grid, threads, 0, st>>>(a); break;
+    case 1: k_stencil_multi<T, VEC, K, 1><<<grid, threads, 0, st>>>(a); break;
+    case 2:
+      if constexpr (K == 3) { k_stencil_multi<T, VEC, K, 2><<<grid, threads, 0, st>>>(a); break; }
+    default: return xg_fail(XG_EINVAL, "xg_stencil_multi: bad innermost op index");
+  }
+  return xg_check_launch("xg_stencil_multi");
+}
+
+template <typename T>
+int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int naxes, const int* axes,
+                const int* ops, const int* lo, const int* hi, const int* bc, const double* fill,
+                cudaStream_t st) {
+  constexpr int VEC = XgVecWidth<T>::value;
+  MultiArgs<T> a;
+  a.in = static_cast<const T*>(in);
+  a.out = static_cast<T*>(out);
+  int64_t out_shape[XG_MAX_NDIM], in_stride[XG_MAX_NDIM], out_stride[XG_MAX_NDIM];
+  int app_index[XG_MAX_NDIM];
+  for (int d = 0; d < ndim; ++d) {
+    out_shape[d] = shape[d];
+    app_index[d] = -1;
+  }
+  for (int k = 0; k < naxes; ++k) {
+    const int d = axes[k];
+    if (d < 0 || d >= ndim) return xg_fail(XG_EINVAL, "xg_stencil_multi: axis out of range");
+    if (app_index[d] >= 0) return xg_fail(XG_EINVAL, "xg_stencil_multi: an axis may appear only once");
+    if (lo[k] < 0 || lo[k] > 1 || hi[k] < 0 || hi[k] > 1)
+      return xg_fail(XG_EINVAL, "xg_stencil_multi: halo widths must be 0 or 1");
+    if ((lo[k] || hi[k]) && (bc[k] < XG_BC_PERIODIC || bc[k] > XG_BC_EXTEND))
+      return xg_fail(XG_EINVAL,
+                     "xg_stencil_multi: each padded axis needs a periodic / fill / extend boundary");
+    if (shape[d] == 0) return xg_fail(XG_EINVAL, "xg_stencil_multi: empty operated axis");
+    app_index[d] = k;
+    out_shape[d] = shape[d] + lo[k] + hi[k] - 1;
+  }
+  int64_t total_out = 1;
+  {
+    int64_t si = 1, so = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+      in_stride[d] = si;
+      out_stride[d] = so;
+      si *= shape[d];
+      so *= out_shape[d];
+      total_out *= out_shape[d];
+    }
+  }
+  if (total_out == 0) return XG_OK;
+  for (int k = 0; k < naxes; ++k) {
+    const int d = axes[k];
+    a.ax[k].op = ops[k];
+    a.ax[k].lo = lo[k];
+    a.ax[k].hi = hi[k];
+    a.ax[k].bc = bc[k];
+    a.ax[k].fill = static_cast<T>(fill[k]);
+    a.ax[k].n = shape[d];
+    a.ax[k].in_stride = in_stride[d];
+  }
+  // innermost group: the last dim if it is operated, else the run of trailing non-operated dims
+  int last = app_index[ndim - 1];
+  int d_end = ndim - 1;  // dims [0, d_end) form the row space
+  int64_t last_n_out = out_shape[ndim - 1];
+  if (last < 0) {
+    while (d_end > 0 && app_index[d_end - 1] < 0) {
+      --d_end;
+      last_n_out *= out_shape[d_end];
+    }
+  }
+  a.last_n_out = last_n_out;
+  // row groups: operated dims alone, runs of non-operated dims merged
+  a.nrow_groups = 0;
+  int64_t nrows = 1;
+  for (int d = 0; d < d_end; ++d) {
+    if (out_shape[d] == 1 && app_index[d] < 0) continue;
+    const bool merge = a.nrow_groups > 0 && app_index[d] < 0 && a.row_axis[a.nrow_groups - 1] < 0 &&
+                       a.row_in_stride[a.nrow_groups - 1] == in_stride[d] * shape[d] &&
+                       a.row_out_stride[a.nrow_groups - 1] == out_stride[d] * out_shape[d];
+    if (merge) {
+      const int g = a.nrow_groups - 1;
+      a.row_size[g] *= out_shape[d];
+      a.row_in_stride[g] = in_stride[d];
+      a.row_out_stride[g] = out_stride[d];
+    } else {
+      if (a.nrow_groups == kMaxGroups)
+        return xg_fail(XG_ENOTIMPL, "xg_stencil_multi: too many interleaved dimensions");
+      const int g = a.nrow_groups++;
+      a.row_size[g] = out_shape[d];
+      a.row_in_stride[g] = in_stride[d];
+      a.row_out_stride[g] = out_stride[d];
+      a.row_axis[g] = app_index[d];
+    }
+    nrows *= out_shape[d];
+  }
+  if (nrows > 0x7fffffffLL) return xg_fail(XG_ENOTIMPL, "xg_stencil_multi: more than 2^31 rows");
+  // vector path: aligned rows whose length the vector width divides; an operated innermost dim must
+  // keep its length (lo + hi == 1) so input and output rows stay aligned with each other
+  bool vec_ok = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && (last_n_out % VEC == 0);
+  if (last >= 0) vec_ok = vec_ok && (lo[last] + hi[last] == 1) && (shape[ndim - 1] % VEC == 0) && shape[ndim - 1] >= 2 * VEC;
+  for (int d = 0; d < ndim - 1 && vec_ok; ++d)
+    if (shape[d] > 1 && in_stride[d] % VEC != 0) vec_ok = false;
+  for (int d = 0; d < ndim - 1 && vec_ok; ++d)
+    if (out_shape[d] > 1 && out_stride[d] % VEC != 0) vec_ok = false;
+  const int64_t nvec = vec_ok ? last_n_out / VEC : last_n_out;
+  int threads = 256;
+  while (threads > 32 && threads / 2 >= nvec) threads /= 2;
+  if (naxes == 2) {
+    if (vec_ok) return launch_last<T, VEC, 2>(last, a, nrows, threads, st);
+    return launch_last<T, 1, 2>(last, a, nrows, threads, st);
+  }
+  if (vec_ok) return launch_last<T, VEC, 3>(last, a, nrows, threads, st);
+  return launch_last<T, 1, 3>(last, a, nrows, threads, st);
+}
+
+}  // namespace
+
+extern "C" int xg_stencil_multi(int dtype, const void* in, void* out, int ndim, const int64_t* shape,
+                                int naxes, const int* axes, const int* ops, const int* lo, const int* hi,
+                                const int* bc, const double* fill_value, void* stream) {
+  if (!in || !out || !shape || !axes || !ops || !lo || !hi || !bc || !fill_value)
+    return xg_fail(XG_EINVAL, "xg_stencil_multi: null pointer");
+  if (ndim < 1 || ndim > XG_MAX_NDIM) return xg_fail(XG_EINVAL, "xg_stencil_multi: bad ndim");
+  if (naxes < 2 || naxes > kMaxAx)
+    return xg_fail(XG_EINVAL, "xg_stencil_multi: 2 or 3 axes (use xg_stencil2 for one)");
+  for (int k = 0; k < naxes; ++k)
+    if (ops[k] < XG_OP_DIFF || ops[k] > XG_OP_MAX) return xg_fail(XG_EINVAL, "xg_stencil_multi: unknown op");
+  if (in == out) return xg_fail(XG_EINVAL, "xg_stencil_multi: in-place operation is not supported");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == XG_F32)
+    return multi_typed<float>(in, out, ndim, shape, naxes, axes, ops, lo, hi, bc, fill_value, st);
+  if (dtype == XG_F64)
+    return multi_typed<double>(in, out, ndim, shape, naxes, axes, ops, lo, hi, bc, fill_value, st);
+  return xg_fail(XG_EINVAL, "xg_stencil_multi: dtype must be XG_F32 or XG_F64");
+}

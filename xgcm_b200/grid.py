@@ -414,6 +414,17 @@ class Grid:
         host_input = not unpacked.is_device
         array = unpacked.copy(deep=False)
         n_axes = len(axis)
+        if (
+            n_axes in (2, 3)
+            and len(set(axis)) == n_axes
+            and not any(metric_weighted.get(ax) for ax in axis)
+            and _divide_by_metric_of is None
+            and not isinstance(data, dict)
+            and set(kwargs) <= {"padding", "fill_value"}
+        ):
+            fused = self._fused_multi_axis(funcname, array, axis, signatures, kwargs)
+            if fused is not None:
+                return self._wrap_out(fused, as_xarray)
         if host_input and n_axes > 1:
             # several passes: upload once, keep the intermediates resident, download once
             array = array.to_device(self._device_for(None))
@@ -442,6 +453,49 @@ class Grid:
 
             array = array._replace(data=result_like(array.data, True))
         return self._wrap_out(array, as_xarray)
+
+    def _fused_multi_axis(self, funcname, array, axis, signatures, kwargs):
+        """All axes of a multi-axis diff / interp / min / max in ONE kernel launch
+        (``xg_stencil_multi``): same values as the per-axis loop of grid.py:800-832, one read and
+        one write of the field instead of one pass per axis.  Returns None when the fused kernel
+        does not cover the case (then the caller runs the per-axis launches)."""
+        from . import ops
+        from .device import as_device_tensor, result_like
+
+        paddings = self._complete_user_kwargs_using_axis_defaults(kwargs.get("padding"), "padding")
+        fills = self._complete_user_kwargs_using_axis_defaults(kwargs.get("fill_value"), "fill_value")
+        specs, rename = [], {}
+        for sig, ax_name in zip(signatures, axis):
+            grid_ufunc, _ = _select_grid_ufunc(funcname, sig, module=gridops)
+            lo, hi = (grid_ufunc.padding_width or {}).get(sig.in_ax_names[0][0], (0, 0))
+            from_pos = sig.in_ax_positions[0][0]
+            to_pos = sig.out_ax_positions[0][0]
+            in_dim = self.axes[ax_name].coords[from_pos]
+            try:
+                out_dim = self.axes[ax_name].coords[to_pos]
+            except KeyError:
+                raise ValueError(f"Axis position ({ax_name}:{to_pos}) does not exist in grid")
+            pad_mode = paddings[ax_name]
+            if (lo or hi) and pad_mode is None:
+                raise ValueError(
+                    f"No boundary condition was specified for axis {ax_name!r}, but the "
+                    f"requested operation needs to pad it. Set a boundary condition, "
+                    f"e.g. ``padding='fill'`` (or 'extend'/'periodic'), on the Grid "
+                    f"(``Grid(..., padding=...)``) or pass ``padding=`` to the "
+                    f"grid method."
+                )
+            if pad_mode not in ("periodic", "fill", "extend", None):
+                return None  # e.g. the opt-in extrapolate extension: per-axis path
+            fv = fills[ax_name] if fills[ax_name] is not None else 0.0
+            specs.append((array.get_axis_num(in_dim), funcname, lo, hi, pad_mode if (lo or hi) else None, fv))
+            rename[in_dim] = out_dim
+        if array.shape[-1] < 32:
+            return None  # tiny rows: the one-block-per-row kernel has nothing to chew on
+        x, was_host = as_device_tensor(array.data, self._device_for(array))
+        out = ops.stencil_multi(x, specs)
+        out_dims = tuple(rename.get(d, d) for d in array.dims)
+        res = DataArray(result_like(out, was_host), dims=out_dims, name=array.name, attrs=array.attrs)
+        return _reattach_coords([res], self, None, set(rename.values()), [array])[0]
 
     def apply_as_grid_ufunc(self, func: Callable, *args, axis=None, signature="", padding_width=None,
                             padding=None, fill_value=None, dask="forbidden", map_overlap=False,

@@ -130,6 +130,51 @@ def stencil2(
     return out
 
 
+def stencil_multi(x: torch.Tensor, specs: Sequence[Tuple[int, str, int, int, Optional[str], float]]) -> torch.Tensor:
+    """Fused chain of 2 or 3 single-axis stencils: ``specs`` = [(axis, op, lo, hi, padding, fill), ...]
+    in application order.  Bit-identical to the corresponding sequence of :func:`stencil2` calls,
+    with one read and one write of the field (reference: one full pass per axis, grid.py:798-832)."""
+    import ctypes as C
+
+    lib = _capi.load()
+    _require_cuda(x, "field")
+    if not 2 <= len(specs) <= 3:
+        raise ValueError("stencil_multi fuses 2 or 3 axes")
+    x = x.contiguous()
+    shape = list(x.shape)
+    out_shape = list(shape)
+    axes, opc, los, his, bcs, fills = [], [], [], [], [], []
+    for axis, op, lo, hi, padding, fill in specs:
+        axis = _norm_axis(axis, x.dim())
+        if op not in _capi.OPS:
+            raise ValueError(f"unknown op {op!r}")
+        if padding not in ("periodic", "fill", "extend", None):
+            raise NotImplementedError(f"fused multi-axis stencils support periodic / fill / extend, not {padding!r}")
+        if (lo or hi) and padding is None:
+            raise ValueError("no boundary condition was specified but the operation needs to pad the axis")
+        axes.append(axis)
+        opc.append(_capi.OPS[op])
+        los.append(int(lo))
+        his.append(int(hi))
+        bcs.append(_capi.BCS[padding] if (lo or hi) else 0)
+        fills.append(float(fill))
+        out_shape[axis] = shape[axis] + lo + hi - 1
+    if len(set(axes)) != len(axes):
+        raise ValueError("each axis may appear only once")
+    out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
+    n = len(specs)
+    IntArr, DblArr = C.c_int * n, C.c_double * n
+    if out.numel():
+        with torch.cuda.device(x.device):
+            rc = lib.xg_stencil_multi(
+                _dtype_code(x), x.data_ptr(), out.data_ptr(), x.dim(), _capi.i64_array(shape), n,
+                IntArr(*axes), IntArr(*opc), IntArr(*los), IntArr(*his), IntArr(*bcs), DblArr(*fills),
+                _stream_ptr(x),
+            )
+        _capi.check(rc)
+    return out
+
+
 def pad(x: torch.Tensor, axis: int, lo: int, hi: int, padding: Optional[str],
         fill_value: float = 0.0) -> torch.Tensor:
     """The padded array itself (padding.py:575-616), one axis."""
