@@ -41,6 +41,10 @@ struct MultiArgs {
   int64_t row_out_stride[kMaxGroups];  // output element stride
   int row_axis[kMaxGroups];            // application index of the operated axis, or -1
   int64_t last_n_out;                  // output extent of the innermost group
+  // the march axis (last applied row-axis op): not part of the row groups
+  int64_t march_n_out, march_out_stride;
+  int J;
+  int64_t nseg;
 };
 
 template <typename T>
@@ -154,48 +158,117 @@ struct Eval {
   }
 };
 
-template <typename T, int VEC, int K, int LAST>
+// MARCH = application index of the LAST applied row-axis op.  A thread owns one vector position of
+// the innermost dim and walks J consecutive output coordinates of that axis: the lower operand of
+// step j+1 is the upper operand of step j (consecutive padded positions), so it stays in
+// registers and only ONE evaluation of the levels below is needed per output — for
+// interp(['X','Y']) that is one 16-byte load plus one neighbour element per 16-byte store.  The
+// only level that can sit above MARCH is the op on the innermost dim (elementwise on the window).
+template <typename T, int VEC, int K, int LAST, int MARCH>
 __global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
-  // this block's output row: coordinates of the operated row axes, source offset of the
-  // non-operated groups, output offset
-  int64_t row = blockIdx.x;
+  constexpr bool kInnerAbove = (LAST > MARCH);
+  constexpr int WM = kInnerAbove ? VEC + 1 : VEC;  // window width at the march level
+  constexpr int U = 4;
+  // this block: a segment of the march axis at fixed coordinates of every other row group
+  int64_t unit = blockIdx.x;
+  const int64_t seg = unit % a.nseg;
+  unit /= a.nseg;
   int64_t j[kMaxAx] = {0, 0, 0};
   int64_t off_in = 0, off_out = 0;
 #pragma unroll
   for (int g = kMaxGroups - 1; g >= 0; --g) {
     if (g < a.nrow_groups) {
-      const int64_t q = row / a.row_size[g];
-      const int64_t c = row - q * a.row_size[g];
-      row = q;
+      const int64_t q = unit / a.row_size[g];
+      const int64_t c = unit - q * a.row_size[g];
+      unit = q;
       off_out += c * a.row_out_stride[g];
       if (a.row_axis[g] >= 0) j[a.row_axis[g]] = c;
       else off_in += c * a.row_in_stride[g];
     }
   }
+  const AxisOp<T>& mx = a.ax[MARCH];
+  const int64_t jm0 = seg * a.J;
+  const int64_t jm1 = (jm0 + a.J < a.march_n_out) ? jm0 + a.J : a.march_n_out;
   const int64_t nvec = (a.last_n_out + VEC - 1) / VEC;  // exact when VEC > 1 (host guarantees it)
-  T* orow = a.out + off_out;
+
   for (int64_t v = threadIdx.x; v < nvec; v += blockDim.x) {
     const int64_t x0 = v * VEC;
-    Win<T, VEC> r = Eval<T, VEC, K, LAST>::template run<K, VEC>(a, j, off_in, x0);
-    XgPack<T, VEC> res;
+    int64_t xw = x0;  // innermost coordinate of the window at the march level
+    if constexpr (kInnerAbove) xw = x0 - a.ax[LAST].lo;
+    // padded intermediate below the march op at padded position p of the march axis
+    auto below = [&](int64_t p) -> Win<T, WM> {
+      int64_t sidx;
+      if (!resolve(mx, p, sidx)) {
+        Win<T, WM> f;
 #pragma unroll
-    for (int q = 0; q < VEC; ++q) res.v[q] = r.v[q];
-    xg_st_stream<T, VEC>(orow + x0, res);
+        for (int q = 0; q < WM; ++q) f.v[q] = mx.fill;
+        return f;
+      }
+      return Eval<T, VEC, K, LAST>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
+    };
+    auto finish = [&](int64_t jm, const Win<T, WM>& lo_w, const Win<T, WM>& hi_w) {
+      Win<T, WM> r;
+#pragma unroll
+      for (int q = 0; q < WM; ++q) r.v[q] = apply_rt<T>(mx.op, lo_w.v[q], hi_w.v[q]);
+      XgPack<T, VEC> res;
+      if constexpr (kInnerAbove) {
+        const AxisOp<T>& ix = a.ax[LAST];
+        if (ix.bc == XG_BC_FILL) {  // halo cells of the innermost op's own level
+          if (xw < 0) r.v[0] = ix.fill;
+          if (xw + VEC >= ix.n) r.v[VEC] = ix.fill;
+        }
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) res.v[q] = apply_rt<T>(ix.op, r.v[q], r.v[q + 1]);
+      } else {
+#pragma unroll
+        for (int q = 0; q < VEC; ++q) res.v[q] = r.v[q];
+      }
+      xg_st_stream<T, VEC>(a.out + off_out + jm * a.march_out_stride + x0, res);
+    };
+    Win<T, WM> prev = below(jm0);
+    int64_t jm = jm0;
+    for (; jm + U <= jm1; jm += U) {
+      Win<T, WM> cur[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) cur[u] = below(jm + u + 1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        finish(jm + u, prev, cur[u]);
+        prev = cur[u];
+      }
+    }
+    for (; jm < jm1; ++jm) {
+      Win<T, WM> cur = below(jm + 1);
+      finish(jm, prev, cur);
+      prev = cur;
+    }
   }
 }
 
+template <typename T, int VEC, int K, int LAST>
+int launch_march(int march, const MultiArgs<T>& a, int64_t nblocks, int threads, cudaStream_t st) {
+  const unsigned grid = (unsigned)nblocks;
+  // MARCH is a row-axis op, so MARCH != LAST
+  if (march == 0) {
+    if constexpr (LAST != 0) { k_stencil_multi<T, VEC, K, LAST, 0><<<grid, threads, 0, st>>>(a); return xg_check_launch("xg_stencil_multi"); }
+  } else if (march == 1) {
+    if constexpr (LAST != 1) { k_stencil_multi<T, VEC, K, LAST, 1><<<grid, threads, 0, st>>>(a); return xg_check_launch("xg_stencil_multi"); }
+  } else if (march == 2) {
+    if constexpr (K == 3 && LAST != 2) { k_stencil_multi<T, VEC, K, LAST, 2><<<grid, threads, 0, st>>>(a); return xg_check_launch("xg_stencil_multi"); }
+  }
+  return xg_fail(XG_EINVAL, "xg_stencil_multi: bad march axis");
+}
+
 template <typename T, int VEC, int K>
-int launch_last(int last, const MultiArgs<T>& a, int64_t nrows, int threads, cudaStream_t st) {
-  const unsigned grid = (unsigned)nrows;
+int launch_last(int last, int march, const MultiArgs<T>& a, int64_t nblocks, int threads, cudaStream_t st) {
   switch (last) {
-    case -1: k_stencil_multi<T, VEC, K, -1><<<grid, threads, 0, st>>>(a); break;
-    case 0: k_stencil_multi<T, VEC, K, 0><<<grid, threads, 0, st>>>(a); break;
-    case 1: k_stencil_multi<T, VEC, K, 1><<<grid, threads, 0, st>>>(a); break;
+    case -1: return launch_march<T, VEC, K, -1>(march, a, nblocks, threads, st);
+    case 0: return launch_march<T, VEC, K, 0>(march, a, nblocks, threads, st);
+    case 1: return launch_march<T, VEC, K, 1>(march, a, nblocks, threads, st);
     case 2:
-      if constexpr (K == 3) { k_stencil_multi<T, VEC, K, 2><<<grid, threads, 0, st>>>(a); break; }
+      if constexpr (K == 3) return launch_march<T, VEC, K, 2>(march, a, nblocks, threads, st);
     default: return xg_fail(XG_EINVAL, "xg_stencil_multi: bad innermost op index");
   }
-  return xg_check_launch("xg_stencil_multi");
 }
 
 template <typename T>
@@ -258,10 +331,20 @@ int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int n
     }
   }
   a.last_n_out = last_n_out;
+  // the march axis: the last applied op that is not on the innermost dim
+  int march = -1;
+  for (int k = naxes - 1; k >= 0; --k)
+    if (k != last) { march = k; break; }
+  const int march_dim = axes[march];
+  a.march_n_out = out_shape[march_dim];
+  a.march_out_stride = out_stride[march_dim];
+  a.J = a.march_n_out <= 96 ? (int)a.march_n_out : 32;
+  a.nseg = xg_ceil_div(a.march_n_out, a.J);
   // row groups: operated dims alone, runs of non-operated dims merged
   a.nrow_groups = 0;
   int64_t nrows = 1;
   for (int d = 0; d < d_end; ++d) {
+    if (d == march_dim) continue;
     if (out_shape[d] == 1 && app_index[d] < 0) continue;
     const bool merge = a.nrow_groups > 0 && app_index[d] < 0 && a.row_axis[a.nrow_groups - 1] < 0 &&
                        a.row_in_stride[a.nrow_groups - 1] == in_stride[d] * shape[d] &&
@@ -282,7 +365,8 @@ int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int n
     }
     nrows *= out_shape[d];
   }
-  if (nrows > 0x7fffffffLL) return xg_fail(XG_ENOTIMPL, "xg_stencil_multi: more than 2^31 rows");
+  const int64_t nblocks = nrows * a.nseg;
+  if (nblocks > 0x7fffffffLL) return xg_fail(XG_ENOTIMPL, "xg_stencil_multi: more than 2^31 blocks");
   // vector path: aligned rows whose length the vector width divides; an operated innermost dim must
   // keep its length (lo + hi == 1) so input and output rows stay aligned with each other
   bool vec_ok = ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0) && (last_n_out % VEC == 0);
@@ -295,11 +379,11 @@ int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int n
   int threads = 256;
   while (threads > 32 && threads / 2 >= nvec) threads /= 2;
   if (naxes == 2) {
-    if (vec_ok) return launch_last<T, VEC, 2>(last, a, nrows, threads, st);
-    return launch_last<T, 1, 2>(last, a, nrows, threads, st);
+    if (vec_ok) return launch_last<T, VEC, 2>(last, march, a, nblocks, threads, st);
+    return launch_last<T, 1, 2>(last, march, a, nblocks, threads, st);
   }
-  if (vec_ok) return launch_last<T, VEC, 3>(last, a, nrows, threads, st);
-  return launch_last<T, 1, 3>(last, a, nrows, threads, st);
+  if (vec_ok) return launch_last<T, VEC, 3>(last, march, a, nblocks, threads, st);
+  return launch_last<T, 1, 3>(last, march, a, nblocks, threads, st);
 }
 
 }  // namespace
