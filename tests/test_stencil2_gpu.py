@@ -154,12 +154,13 @@ def test_stencil_multi_equals_sequential(dtype, shape):
         for trial in range(6):
             specs = []
             ok = True
-            for ax in axes:
+            same_op = OPS[rng.integers(0, 4)]  # Grid methods apply one operator along all axes;
+            for ax in axes:                    # every 6th trial mixes them (chained per-axis path)
                 lo, hi = SHIFTS[rng.integers(0, 4)]
                 if shape[ax] + lo + hi - 1 <= 0:
                     ok = False
                 bc, fill = bcs[rng.integers(0, 4)]
-                specs.append((ax, OPS[rng.integers(0, 4)], lo, hi, bc, fill))
+                specs.append((ax, same_op if trial < 5 else OPS[rng.integers(0, 4)], lo, hi, bc, fill))
             if not ok:
                 continue
             want = a
@@ -179,8 +180,8 @@ def test_stencil_multi_c_grid_interp_to_corner():
     got = ops.stencil_multi(x, [(2, "interp", 1, 0, "periodic", 0.0), (1, "interp", 1, 0, "fill", 0.0)]).cpu().numpy()
     want = oracle.stencil2("interp", oracle.stencil2("interp", a, 2, 1, 0, "periodic"), 1, 1, 0, "fill", 0.0)
     np.testing.assert_array_equal(got, want)
-    got = ops.stencil_multi(x, [(1, "diff", 0, 1, "extend", 0.0), (2, "diff", 1, 0, "periodic", 0.0), (0, "interp", 1, 1, "fill", 2.0)]).cpu().numpy()
-    want = oracle.stencil2("interp", oracle.stencil2("diff", oracle.stencil2("diff", a, 1, 0, 1, "extend"), 2, 1, 0, "periodic"), 0, 1, 1, "fill", 2.0)
+    got = ops.stencil_multi(x, [(1, "diff", 0, 1, "extend", 0.0), (2, "diff", 1, 0, "periodic", 0.0), (0, "diff", 1, 1, "fill", 2.0)]).cpu().numpy()
+    want = oracle.stencil2("diff", oracle.stencil2("diff", oracle.stencil2("diff", a, 1, 0, 1, "extend"), 2, 1, 0, "periodic"), 0, 1, 1, "fill", 2.0)
     np.testing.assert_array_equal(got, want)
     with pytest.raises(ValueError):
         ops.stencil_multi(x, [(2, "interp", 1, 0, None, 0.0), (1, "interp", 1, 0, "fill", 0.0)])

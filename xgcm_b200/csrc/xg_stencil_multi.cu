@@ -114,7 +114,7 @@ __device__ __forceinline__ Win<T, W> load_window(const MultiArgs<T>& a, int64_t 
 
 // Window of W values of the intermediate after the first k ops, at row coordinates j (axes < k
 // in their output space; axes >= k already folded into `off`), innermost coordinate x.
-template <typename T, int VEC, int K, int LAST>
+template <typename T, int VEC, int K, int LAST, int OP>
 struct Eval {
   template <int k, int W>
   static __device__ __forceinline__ Win<T, W> run(const MultiArgs<T>& a, const int64_t* j, int64_t off,
@@ -134,7 +134,7 @@ struct Eval {
           if (xs + W >= ax.n) w.v[W] = ax.fill;
         }
 #pragma unroll
-        for (int q = 0; q < W; ++q) r.v[q] = apply_rt<T>(ax.op, w.v[q], w.v[q + 1]);
+        for (int q = 0; q < W; ++q) r.v[q] = xg_apply_op<T, OP>(w.v[q], w.v[q + 1]);
       } else {
         int64_t s0, s1;
         const bool ok0 = resolve(ax, j[m], s0);  // block-uniform: j is this block's row
@@ -151,7 +151,7 @@ struct Eval {
           for (int q = 0; q < W; ++q) hi_v.v[q] = ax.fill;
         }
 #pragma unroll
-        for (int q = 0; q < W; ++q) r.v[q] = apply_rt<T>(ax.op, lo_v.v[q], hi_v.v[q]);
+        for (int q = 0; q < W; ++q) r.v[q] = xg_apply_op<T, OP>(lo_v.v[q], hi_v.v[q]);
       }
       return r;
     }
@@ -164,7 +164,7 @@ struct Eval {
 // registers and only ONE evaluation of the levels below is needed per output — for
 // interp(['X','Y']) that is one 16-byte load plus one neighbour element per 16-byte store.  The
 // only level that can sit above MARCH is the op on the innermost dim (elementwise on the window).
-template <typename T, int VEC, int K, int LAST, int MARCH>
+template <typename T, int VEC, int K, int LAST, int MARCH, int OP>
 __global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
   constexpr bool kInnerAbove = (LAST > MARCH);
   constexpr int WM = kInnerAbove ? VEC + 1 : VEC;  // window width at the march level
@@ -204,12 +204,12 @@ __global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
         for (int q = 0; q < WM; ++q) f.v[q] = mx.fill;
         return f;
       }
-      return Eval<T, VEC, K, LAST>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
+      return Eval<T, VEC, K, LAST, OP>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
     };
     auto finish = [&](int64_t jm, const Win<T, WM>& lo_w, const Win<T, WM>& hi_w) {
       Win<T, WM> r;
 #pragma unroll
-      for (int q = 0; q < WM; ++q) r.v[q] = apply_rt<T>(mx.op, lo_w.v[q], hi_w.v[q]);
+      for (int q = 0; q < WM; ++q) r.v[q] = xg_apply_op<T, OP>(lo_w.v[q], hi_w.v[q]);
       XgPack<T, VEC> res;
       if constexpr (kInnerAbove) {
         const AxisOp<T>& ix = a.ax[LAST];
@@ -218,7 +218,7 @@ __global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
           if (xw + VEC >= ix.n) r.v[VEC] = ix.fill;
         }
 #pragma unroll
-        for (int q = 0; q < VEC; ++q) res.v[q] = apply_rt<T>(ix.op, r.v[q], r.v[q + 1]);
+        for (int q = 0; q < VEC; ++q) res.v[q] = xg_apply_op<T, OP>(r.v[q], r.v[q + 1]);
       } else {
 #pragma unroll
         for (int q = 0; q < VEC; ++q) res.v[q] = r.v[q];
@@ -245,16 +245,28 @@ __global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
   }
 }
 
+template <typename T, int VEC, int K, int LAST, int MARCH>
+int launch_op(int op, const MultiArgs<T>& a, int64_t nblocks, int threads, cudaStream_t st) {
+  const unsigned grid = (unsigned)nblocks;
+  switch (op) {
+    case XG_OP_DIFF: k_stencil_multi<T, VEC, K, LAST, MARCH, XG_OP_DIFF><<<grid, threads, 0, st>>>(a); break;
+    case XG_OP_INTERP: k_stencil_multi<T, VEC, K, LAST, MARCH, XG_OP_INTERP><<<grid, threads, 0, st>>>(a); break;
+    case XG_OP_MIN: k_stencil_multi<T, VEC, K, LAST, MARCH, XG_OP_MIN><<<grid, threads, 0, st>>>(a); break;
+    default: k_stencil_multi<T, VEC, K, LAST, MARCH, XG_OP_MAX><<<grid, threads, 0, st>>>(a); break;
+  }
+  return xg_check_launch("xg_stencil_multi");
+}
+
 template <typename T, int VEC, int K, int LAST>
 int launch_march(int march, const MultiArgs<T>& a, int64_t nblocks, int threads, cudaStream_t st) {
-  const unsigned grid = (unsigned)nblocks;
+  const int op = a.ax[0].op;  // the fused kernel applies one operator along all axes
   // MARCH is a row-axis op, so MARCH != LAST
   if (march == 0) {
-    if constexpr (LAST != 0) { k_stencil_multi<T, VEC, K, LAST, 0><<<grid, threads, 0, st>>>(a); return xg_check_launch("xg_stencil_multi"); }
+    if constexpr (LAST != 0) return launch_op<T, VEC, K, LAST, 0>(op, a, nblocks, threads, st);
   } else if (march == 1) {
-    if constexpr (LAST != 1) { k_stencil_multi<T, VEC, K, LAST, 1><<<grid, threads, 0, st>>>(a); return xg_check_launch("xg_stencil_multi"); }
+    if constexpr (LAST != 1) return launch_op<T, VEC, K, LAST, 1>(op, a, nblocks, threads, st);
   } else if (march == 2) {
-    if constexpr (K == 3 && LAST != 2) { k_stencil_multi<T, VEC, K, LAST, 2><<<grid, threads, 0, st>>>(a); return xg_check_launch("xg_stencil_multi"); }
+    if constexpr (K == 3 && LAST != 2) return launch_op<T, VEC, K, LAST, 2>(op, a, nblocks, threads, st);
   }
   return xg_fail(XG_EINVAL, "xg_stencil_multi: bad march axis");
 }
@@ -396,8 +408,12 @@ extern "C" int xg_stencil_multi(int dtype, const void* in, void* out, int ndim, 
   if (ndim < 1 || ndim > XG_MAX_NDIM) return xg_fail(XG_EINVAL, "xg_stencil_multi: bad ndim");
   if (naxes < 2 || naxes > kMaxAx)
     return xg_fail(XG_EINVAL, "xg_stencil_multi: 2 or 3 axes (use xg_stencil2 for one)");
-  for (int k = 0; k < naxes; ++k)
+  for (int k = 0; k < naxes; ++k) {
     if (ops[k] < XG_OP_DIFF || ops[k] > XG_OP_MAX) return xg_fail(XG_EINVAL, "xg_stencil_multi: unknown op");
+    if (ops[k] != ops[0])
+      return xg_fail(XG_ENOTIMPL, "xg_stencil_multi: the fused kernel applies ONE operator along all axes "
+                                  "(what Grid.diff / interp / min / max do); chain xg_stencil2 for mixed ones");
+  }
   if (in == out) return xg_fail(XG_EINVAL, "xg_stencil_multi: in-place operation is not supported");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == XG_F32)

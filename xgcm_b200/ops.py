@@ -161,6 +161,12 @@ def stencil_multi(x: torch.Tensor, specs: Sequence[Tuple[int, str, int, int, Opt
         out_shape[axis] = shape[axis] + lo + hi - 1
     if len(set(axes)) != len(axes):
         raise ValueError("each axis may appear only once")
+    if len(set(opc)) != 1:
+        # mixed operators: not a Grid-level case; same result through the per-axis kernel
+        out = x
+        for axis, op, lo, hi, padding, fill in specs:
+            out = stencil2(out, axis, op, lo, hi, padding if (lo or hi) else None, fill)
+        return out
     out = torch.empty(out_shape, dtype=x.dtype, device=x.device)
     n = len(specs)
     IntArr, DblArr = C.c_int * n, C.c_double * n
