@@ -165,7 +165,7 @@ struct Eval {
 // interp(['X','Y']) that is one 16-byte load plus one neighbour element per 16-byte store.  The
 // only level that can sit above MARCH is the op on the innermost dim (elementwise on the window).
 template <typename T, int VEC, int K, int LAST, int MARCH, int OP>
-__global__ void __launch_bounds__(256) k_stencil_multi(const MultiArgs<T> a) {
+__global__ void __launch_bounds__(256, 4) k_stencil_multi(const MultiArgs<T> a) {
   constexpr bool kInnerAbove = (LAST > MARCH);
   constexpr int WM = kInnerAbove ? VEC + 1 : VEC;  // window width at the march level
   constexpr int U = 4;
