@@ -101,9 +101,13 @@ __device__ __forceinline__ Win<T, W> load_window(const MultiArgs<T>& a, int64_t 
       const int64_t xv = lead ? xs + 1 : xs;
       XgPack<T, VEC> pk = xg_ld_cached<T, VEC>(p + xv);
       const T extra = scalar_at(lead ? xs : xs + VEC);
+      // static indices only (a runtime-indexed window would live in local memory)
 #pragma unroll
-      for (int q = 0; q < VEC; ++q) r.v[lead ? q + 1 : q] = pk.v[q];
-      r.v[lead ? 0 : VEC] = extra;
+      for (int q = 0; q <= VEC; ++q) {
+        const T from_lead = (q == 0) ? extra : pk.v[q > 0 ? q - 1 : 0];
+        const T from_tail = (q < VEC) ? pk.v[q < VEC ? q : 0] : extra;
+        r.v[q] = lead ? from_lead : from_tail;
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < W; ++q) r.v[q] = scalar_at(xs + q);
