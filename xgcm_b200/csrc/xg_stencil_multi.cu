@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(256, 4) k_stencil_multi(const MultiArgs<T> a) 
   int64_t unit = blockIdx.x;
   const int64_t seg = unit % a.nseg;
   unit /= a.nseg;
-  int64_t j[kMaxAx] = {0, 0, 0};
+  int64_t j0 = 0, j1 = 0, j2 = 0;  // separate scalars: a runtime-indexed array would live in local memory
   int64_t off_in = 0, off_out = 0;
 #pragma unroll
   for (int g = kMaxGroups - 1; g >= 0; --g) {
@@ -186,10 +186,14 @@ __global__ void __launch_bounds__(256, 4) k_stencil_multi(const MultiArgs<T> a) 
       const int64_t c = unit - q * a.row_size[g];
       unit = q;
       off_out += c * a.row_out_stride[g];
-      if (a.row_axis[g] >= 0) j[a.row_axis[g]] = c;
+      const int ra = a.row_axis[g];
+      if (ra == 0) j0 = c;
+      else if (ra == 1) j1 = c;
+      else if (ra == 2) j2 = c;
       else off_in += c * a.row_in_stride[g];
     }
   }
+  const int64_t j[kMaxAx] = {j0, j1, j2};
   const AxisOp<T>& mx = a.ax[MARCH];
   const int64_t jm0 = seg * a.J;
   const int64_t jm1 = (jm0 + a.J < a.march_n_out) ? jm0 + a.J : a.march_n_out;
