@@ -35,7 +35,9 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kTile = 32;
 constexpr int LIKELY_IN_CACHE_SIZE = 8;
-constexpr int kPrefetchRows = 6;  // phi rows pulled into L1 ahead of the interval in use
+constexpr int kPrefetchRows = 6;
+template <typename T>
+constexpr int kCPLv = sizeof(T) == 4 ? 2 : 1;  // columns per lane in the shared-theta kernel  // phi rows pulled into L1 ahead of the interval in use
 
 template <typename T>
 struct InterpArgs {
@@ -151,14 +153,14 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int n = (int)a.n, m = (int)a.m;
   const int nchunk = (m + kTile - 1) / kTile;
-  // layout: runs[m + nchunk] | xt[m] | X[n] | rdx[n] | tile[kWarps][32][33] | tj[m] tk[m] chunk_run[nchunk+1] flags[4]
+  // layout: runs[m + nchunk] | xt[m] | X[n] | rdx[n] | tile[kWarps][kCPLv<T>][32][33] | tj[m] tk[m] chunk_run[nchunk+1] flags[4]
   Run* runs = reinterpret_cast<Run*>(smem_raw);
   double* xt = reinterpret_cast<double*>(runs + (m + nchunk));
   double* Xs = xt + m;
   double* rdx = Xs + n;  // RN(1 / (X[j+1] - X[j])) or 0 when the fast division must not be used
-  T(*tiles)[kTile][kTile + 1] = reinterpret_cast<T(*)[kTile][kTile + 1]>(rdx + n);
+  T(*tiles)[kCPLv<T>][kTile][kTile + 1] = reinterpret_cast<T(*)[kCPLv<T>][kTile][kTile + 1]>(rdx + n);
   int* tj = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(tiles) +
-                                   sizeof(T) * kWarps * kTile * (kTile + 1));
+                                   sizeof(T) * kWarps * kCPLv<T> * kTile * (kTile + 1));
   int* tk = tj + m;
   int* chunk_run = tk + m;
   int* flags = chunk_run + nchunk + 1;
@@ -292,75 +294,111 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
   __syncthreads();
 
   // ---- columns ----------------------------------------------------------------
+  // Every column runs the SAME sequence of runs (theta is shared), so a lane carries kCPLv<T> columns in
+  // lock-step: twice the independent load -> divide -> interpolate chains per warp, and the plan
+  // reads / loop control are paid once for both.
   const int w = tid >> 5, lane = tid & 31;
-  T(*tile)[kTile + 1] = tiles[w];
   const int64_t ncols = a.outer * a.inner;
-  const int64_t tile_stride = (int64_t)gridDim.x * kWarps;
+  const int64_t group_stride = (int64_t)gridDim.x * kWarps;
+  const int64_t ngroups = (a.ntiles + kCPLv<T> - 1) / kCPLv<T>;
   const int64_t step = flip ? -a.inner : a.inner;  // phi pointer step for j -> j + 1
-  for (int64_t ct = (int64_t)blockIdx.x * kWarps + w; ct < a.ntiles; ct += tile_stride) {
-    const int64_t col0 = ct * kTile;
-    const int64_t col = col0 + lane;
-    const bool col_ok = col < ncols;
-    const int ncol_here = (int)((ncols - col0 < kTile) ? (ncols - col0) : kTile);
-    const T* phi0 = a.phi;  // -> Y(0) of this column
-    if (col_ok) {
-      int64_t o, i;
-      xg_divmod(col, a.inner, a.small_cols, o, i);
-      phi0 = a.phi + o * a.n * a.inner + i + (flip ? (int64_t)(n - 1) * a.inner : 0);
+  for (int64_t cg = (int64_t)blockIdx.x * kWarps + w; cg < ngroups; cg += group_stride) {
+    const T* phi0[kCPLv<T>];
+    const T* pj1[kCPLv<T>];
+    bool ok[kCPLv<T>];
+    double yj[kCPLv<T>], yj1[kCPLv<T>], slope[kCPLv<T>], y_first[kCPLv<T>], y_last[kCPLv<T>];
 #pragma unroll
-      for (int k = 1; k <= kPrefetchRows; ++k)  // warm L1 with the first rows of this column
-        if (k < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(phi0 + k * step));
+    for (int c = 0; c < kCPLv<T>; ++c) {
+      const int64_t col = (cg * kCPLv<T> + c) * kTile + lane;
+      ok[c] = col < ncols;
+      phi0[c] = a.phi;
+      if (ok[c]) {
+        int64_t o, i;
+        xg_divmod(col, a.inner, a.small_cols, o, i);
+        phi0[c] = a.phi + o * a.n * a.inner + i + (flip ? (int64_t)(n - 1) * a.inner : 0);
+#pragma unroll
+        for (int k = 1; k <= kPrefetchRows; ++k)  // warm L1 with the first rows of this column
+          if (k < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(phi0[c] + k * step));
+      }
+      pj1[c] = phi0[c];
+      yj[c] = yj1[c] = slope[c] = 0.0;
     }
-    int cj = -2;  // memoised interval
-    const T* pj1 = phi0;  // -> Y(cj + 1)
-    double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
-    const double y_first = col_ok ? (double)__ldg(phi0) : 0.0;
-    const double y_last = col_ok ? (double)__ldg(phi0 + (int64_t)(n - 1) * step) : 0.0;
-    for (int c = 0; c < nchunk; ++c) {
-      const int t0 = c * kTile;
+#pragma unroll
+    for (int c = 0; c < kCPLv<T>; ++c) {
+      y_first[c] = ok[c] ? (double)__ldg(phi0[c]) : 0.0;
+      y_last[c] = ok[c] ? (double)__ldg(phi0[c] + (int64_t)(n - 1) * step) : 0.0;
+    }
+    int cj = -2;  // memoised interval (common to the kCPLv<T> columns)
+    double xj = 0.0, xj1 = 0.0;
+    for (int cc = 0; cc < nchunk; ++cc) {
+      const int t0 = cc * kTile;
       const int nt = (m - t0 < kTile) ? (m - t0) : kTile;
-      if (col_ok) {
-        const int r_end = chunk_run[c + 1];
-        for (int r = chunk_run[c]; r < r_end; ++r) {
-          const Run run = runs[r];  // one 16-byte broadcast read
-          T* dst = &tile[lane][run.t_begin - t0];
-          const int len = run.t_end - run.t_begin;
-          if (run.kind <= PK_EXACT) {
-            if (run.j != cj) {
-              if (run.j != cj + 1 || cj < 0) {  // rare: a jump — re-seat on node j first
-                pj1 = phi0 + (int64_t)run.j * step;
-                yj1 = (double)__ldg(pj1);
-                xj1 = Xs[run.j];
+      const int r_end = chunk_run[cc + 1];
+      for (int r = chunk_run[cc]; r < r_end; ++r) {
+        const Run run = runs[r];  // one 16-byte broadcast read
+        const int len = run.t_end - run.t_begin;
+        const int d0 = run.t_begin - t0;
+        if (run.kind <= PK_EXACT) {
+          if (run.j != cj) {
+            const bool jump = (run.j != cj + 1 || cj < 0);  // rare: re-seat on node j first
+            cj = run.j;
+            const double xj_new = jump ? Xs[cj] : xj1;
+            xj = xj_new;
+            xj1 = Xs[cj + 1];
+            const double dxj = xj1 - xj, rr = rdx[cj];
+            const bool pf = cj + 1 + kPrefetchRows < n;
+#pragma unroll
+            for (int c = 0; c < kCPLv<T>; ++c) {
+              if (ok[c]) {
+                if (jump) {
+                  pj1[c] = phi0[c] + (int64_t)cj * step;
+                  yj1[c] = (double)__ldg(pj1[c]);
+                }
+                // the usual case: walk one interval up; (xj1, yj1) held node j already
+                yj[c] = yj1[c];
+                pj1[c] += step;
+                yj1[c] = (double)__ldg(pj1[c]);
+                // targets normally ascend: pull a row a few intervals ahead into L1 now
+                if (pf) asm volatile("prefetch.global.L1 [%0];" ::"l"(pj1[c] + kPrefetchRows * step));
               }
-              // the usual case: walk one interval up; (xj1, yj1) hold node j already
-              cj = run.j;
-              yj = yj1;
-              xj = xj1;
-              pj1 += step;
-              yj1 = (double)__ldg(pj1);
-              xj1 = Xs[cj + 1];
-              // targets normally ascend: pull a row a few intervals ahead into L1 now so the next
-              // interval switches do not wait on DRAM
-              if (cj + 1 + kPrefetchRows < n)
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(pj1 + kPrefetchRows * step));
-              const double dyj = yj1 - yj, rr = rdx[cj];
-              if (rr != 0.0 && exponent_safe(dyj)) slope = div_with_recip(dyj, xj1 - xj, rr);
-              else slope = dyj / (xj1 - xj);
             }
-            if (run.kind == PK_INTERP) {
-              const double* xp = xt + run.t_begin;
-              for (int q = 0; q < len; ++q) dst[q] = (T)interp_value(xp[q], xj, xj1, yj, yj1, slope);
-            } else {
-              const T v = (T)yj;
-              for (int q = 0; q < len; ++q) dst[q] = v;
+#pragma unroll
+            for (int c = 0; c < kCPLv<T>; ++c) {
+              const double dyj = yj1[c] - yj[c];
+              slope[c] = (rr != 0.0 && exponent_safe(dyj)) ? div_with_recip(dyj, dxj, rr) : dyj / dxj;
+            }
+          }
+          if (run.kind == PK_INTERP) {
+            const double* xp = xt + run.t_begin;
+            for (int q = 0; q < len; ++q) {
+              const double x = xp[q];
+#pragma unroll
+              for (int c = 0; c < kCPLv<T>; ++c)
+                tiles[w][c][lane][d0 + q] = (T)interp_value(x, xj, xj1, yj[c], yj1[c], slope[c]);
             }
           } else {
-            const T v = (run.kind == PK_FIRST) ? (T)y_first : (run.kind == PK_LAST) ? (T)y_last : T(NAN);
-            for (int q = 0; q < len; ++q) dst[q] = v;
+#pragma unroll
+            for (int c = 0; c < kCPLv<T>; ++c) {
+              const T v = (T)yj[c];
+              for (int q = 0; q < len; ++q) tiles[w][c][lane][d0 + q] = v;
+            }
+          }
+        } else {
+#pragma unroll
+          for (int c = 0; c < kCPLv<T>; ++c) {
+            const T v = (run.kind == PK_FIRST) ? (T)y_first[c] : (run.kind == PK_LAST) ? (T)y_last[c] : T(NAN);
+            for (int q = 0; q < len; ++q) tiles[w][c][lane][d0 + q] = v;
           }
         }
       }
-      store_tile<T>(tile, a.out, col0, ncol_here, a.m, t0, nt, lane);
+#pragma unroll
+      for (int c = 0; c < kCPLv<T>; ++c) {
+        const int64_t col0 = (cg * kCPLv<T> + c) * kTile;
+        if (col0 < ncols) {  // warp-uniform
+          const int ncol_here = (int)((ncols - col0 < kTile) ? (ncols - col0) : kTile);
+          store_tile<T>(tiles[w][c], a.out, col0, ncol_here, a.m, t0, nt, lane);
+        }
+      }
     }
   }
 }
@@ -556,15 +594,15 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
   };
   const int64_t nchunk = xg_ceil_div(m, kTile);
   const size_t plan_bytes = (size_t)(m + nchunk) * sizeof(Run) + (size_t)(m + 2 * v.n) * sizeof(double) +
-                            sizeof(T) * kWarps * kTile * (kTile + 1) +
+                            sizeof(T) * kWarps * kCPLv<T> * kTile * (kTile + 1) +
                             (size_t)(2 * m + nchunk + 1 + 4) * sizeof(int);
   if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan_bytes);
     if (e != cudaSuccess)
       return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
-    int64_t blocks = xg_ceil_div(a.ntiles, kWarps);
-    if (blocks > 148 * 8) blocks = 148 * 8;  // persistent-ish: the plan is amortised over many tiles
+    int64_t blocks = xg_ceil_div(xg_ceil_div(a.ntiles, kCPLv<T>), kWarps);
+    if (blocks > 148 * 6) blocks = 148 * 6;  // persistent-ish: the plan is amortised over many tiles
     k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
     return xg_check_launch("xg_vinterp_linear(shared)");
   }
