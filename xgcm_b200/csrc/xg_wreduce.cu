@@ -85,8 +85,8 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
   xg_st_stream<T, VEC>(a.out + o * a.inner + i, r);
 }
 
-// one warp per row (innermost axis); fp64 accumulation
-template <typename T, bool HASW>
+// one warp per row (innermost axis); fp64 accumulation; 16-byte loads when the rows allow it
+template <typename T, bool HASW, int VEC>
 __global__ void __launch_bounds__(kThreads) k_reduce_rows(const ReduceArgs<T> a) {
   const int64_t r = (int64_t)blockIdx.x * (kThreads / 32) + (threadIdx.x >> 5);
   if (r >= a.outer) return;
@@ -97,17 +97,20 @@ __global__ void __launch_bounds__(kThreads) k_reduce_rows(const ReduceArgs<T> a)
   if (HASW) w_base = xg_groups_offset(a.w.outer, r);
   const bool mean = a.mode == XG_REDUCE_MEAN;
   double num = 0.0, den = 0.0;
-  for (int64_t x = lane; x < a.n; x += 32) {
-    T v = __ldcs(row + x);
-    T w = HASW ? __ldg(wp + w_base + x * a.w.axis_stride) : T(1);
-    if (!mean) {
-      T p = HASW ? v * w : v;
-      if (a.skipna && xg_isnan(p)) p = T(0);
-      num += (double)p;
-    } else {
-      const bool valid = !xg_isnan(v);
-      num += valid ? (double)(v * w) : 0.0;
-      den += valid ? (double)w : 0.0;
+  for (int64_t x = (int64_t)lane * VEC; x < a.n; x += 32 * VEC) {
+    XgPack<T, VEC> v = xg_ld_stream<T, VEC>(row + x);
+#pragma unroll
+    for (int q = 0; q < VEC; ++q) {
+      const T w = HASW ? __ldg(wp + w_base + (x + q) * a.w.axis_stride) : T(1);
+      if (!mean) {
+        T p = HASW ? v.v[q] * w : v.v[q];
+        if (a.skipna && xg_isnan(p)) p = T(0);
+        num += (double)p;
+      } else {
+        const bool valid = !xg_isnan(v.v[q]);
+        num += valid ? (double)(v.v[q] * w) : 0.0;
+        den += valid ? (double)w : 0.0;
+      }
     }
   }
 #pragma unroll
@@ -141,7 +144,10 @@ int reduce_launch(ReduceArgs<T>& a, cudaStream_t st) {
   }
   const int64_t blocks = xg_ceil_div(a.outer, kThreads / 32);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_wreduce: grid too large");
-  k_reduce_rows<T, HASW><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  if (a.n % VEC == 0 && ((uintptr_t)a.in & 15) == 0)
+    k_reduce_rows<T, HASW, VEC><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  else
+    k_reduce_rows<T, HASW, 1><<<(unsigned)blocks, kThreads, 0, st>>>(a);
   return xg_check_launch("xg_wreduce(rows)");
 }
 
