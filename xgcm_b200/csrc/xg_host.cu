@@ -11,6 +11,8 @@
 //
 // Workspace (device slabs + events + streams) is cached per device and reused;
 // xg_host_workspace_release() frees it.
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -148,7 +150,11 @@ extern "C" int xg_stencil2_host(int op, int dtype, const void* in, void* out, in
   const bool ax0 = axis == 0;
 
   // slab height along dim 0: ~128 MiB of input per slab, at least 4 slabs if possible
-  const int64_t target_bytes = 128ll << 20;
+  int64_t target_bytes = 128ll << 20;
+  if (const char* env = getenv("XG_HOST_SLAB_MB")) {  // tuning knob (benchmarks only)
+    const long mb = atol(env);
+    if (mb >= 1 && mb <= 4096) target_bytes = (int64_t)mb << 20;
+  }
   int64_t rows = target_bytes / (int64_t)(row_in * es);
   if (rows < 1) rows = 1;
   if (rows > (n0_out + 3) / 4) rows = (n0_out + 3) / 4;
