@@ -215,6 +215,8 @@ extern "C" int xg_stencil2_host(int op, int dtype, const void* in, void* out, in
   int64_t slab_shape[XG_MAX_NDIM];
   for (int d = 0; d < ndim; ++d) slab_shape[d] = shape[d];
 
+  int64_t prev_last_row = -1;          // global index of the last plane of the previous slab
+  const char* prev_last_ptr = nullptr;  // ... and where it sits on the device
   for (int64_t s = 0; s < nslab; ++s) {
     const int slot = (int)(s % kSlots);
     const int64_t j0 = s * rows;                                  // first output row of the slab
@@ -237,8 +239,20 @@ extern "C" int xg_stencil2_host(int op, int dtype, const void* in, void* out, in
       XG_CUDA(cudaStreamWaitEvent(w->s_h2d, w->e_done[slot], 0));
       XG_CUDA(cudaStreamWaitEvent(w->s_k, w->e_down[slot], 0));
     }
-    XG_CUDA(cudaMemcpyAsync(w->d_in[slot], hin + (size_t)i0 * row_in * es,
-                            (size_t)(i1 - i0) * row_in * es, cudaMemcpyHostToDevice, w->s_h2d));
+    if (ax0 && s > 0 && prev_last_row == i0 && i1 - i0 > 1) {
+      // consecutive slabs of the operated axis overlap by exactly one plane: carry it over on the
+      // device (same in-order stream as the uploads) instead of sending it over PCIe again
+      XG_CUDA(cudaMemcpyAsync(w->d_in[slot], prev_last_ptr, (size_t)row_in * es,
+                              cudaMemcpyDeviceToDevice, w->s_h2d));
+      XG_CUDA(cudaMemcpyAsync((char*)w->d_in[slot] + (size_t)row_in * es,
+                              hin + (size_t)(i0 + 1) * row_in * es,
+                              (size_t)(i1 - i0 - 1) * row_in * es, cudaMemcpyHostToDevice, w->s_h2d));
+    } else {
+      XG_CUDA(cudaMemcpyAsync(w->d_in[slot], hin + (size_t)i0 * row_in * es,
+                              (size_t)(i1 - i0) * row_in * es, cudaMemcpyHostToDevice, w->s_h2d));
+    }
+    prev_last_row = i1 - 1;
+    prev_last_ptr = (const char*)w->d_in[slot] + (size_t)(i1 - 1 - i0) * row_in * es;
     XG_CUDA(cudaEventRecord(w->e_up[slot], w->s_h2d));
     XG_CUDA(cudaStreamWaitEvent(w->s_k, w->e_up[slot], 0));
 
