@@ -19,6 +19,8 @@
 //
 // Roofline: HBM.  Algorithmic bytes = 2 * sizeof(T) per output cell
 // (+ metric bytes), see DESIGN.md.
+#include <stdlib.h>
+
 #include "xg_common.cuh"
 
 namespace {
@@ -315,14 +317,20 @@ k_stencil_row_vec(const StencilArgs<T> a) {
 // ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+
 template <typename T, int VEC, int OP, bool MET>
 int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
-  constexpr int U = 4;
   const int64_t nvec = xg_ceil_div(a.inner, VEC);
   a.nwc = xg_ceil_div(nvec, 32);
   // march length: long enough that the re-read halo row is a few % of traffic,
   // short enough that there are plenty of warps for 148 SMs.
-  int J = 32;
+  static const int tune_j = env_int("XG_STRIDED_J", 0);  // tuning knobs (benchmarks only)
+  static const int tune_u = env_int("XG_STRIDED_U", 0);
+  int J = tune_j > 0 ? tune_j : 32;
   if (a.n_out <= 96) J = (int)a.n_out;  // short axes (e.g. 75 depth levels): one march
   a.J = J;
   a.nseg = xg_ceil_div(a.n_out, J);
@@ -330,7 +338,12 @@ int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
   a.small_units = a.nunits < (1ll << 31);
   const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2: grid too large");
-  k_stencil_strided<T, VEC, OP, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  if (!MET && tune_u == 8)
+    k_stencil_strided<T, VEC, OP, MET, 8><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  else if (!MET && tune_u == 2)
+    k_stencil_strided<T, VEC, OP, MET, 2><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  else
+    k_stencil_strided<T, VEC, OP, MET, 4><<<(unsigned)blocks, kThreads, 0, st>>>(a);
   return xg_check_launch("xg_stencil2(strided)");
 }
 
