@@ -36,6 +36,7 @@ struct StencilArgs {
   int64_t nseg, nwc;   // segments along the axis, warp-columns (or row chunks)
   int64_t nunits;      // total warp-units
   bool small_units;    // nunits < 2^31: 32-bit unit decomposition
+  bool seg_fast;       // unit order: segment index fastest (else warp-column fastest)
   XgOperand pre, post;
   int pre_axis_vec_ok, post_axis_vec_ok;  // row kernels: metric vector loads along x
   const T* halo_lo;
@@ -57,8 +58,13 @@ k_stencil_strided(const StencilArgs<T> a) {
   if (unit >= a.nunits) return;
   const int lane = threadIdx.x & 31;
   int64_t wc, t, seg, o;
-  xg_divmod(unit, a.nwc, a.small_units, t, wc);
-  xg_divmod(t, a.nseg, a.small_units, o, seg);
+  if (a.seg_fast) {  // segments of one column group adjacent in launch order
+    xg_divmod(unit, a.nseg, a.small_units, t, seg);
+    xg_divmod(t, a.nwc, a.small_units, o, wc);
+  } else {
+    xg_divmod(unit, a.nwc, a.small_units, t, wc);
+    xg_divmod(t, a.nseg, a.small_units, o, seg);
+  }
   const int64_t i = (wc * 32 + lane) * VEC;
   if (i >= a.inner) return;
 
@@ -345,6 +351,8 @@ int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
   a.nseg = xg_ceil_div(a.n_out, J);
   a.nunits = a.outer * a.nseg * a.nwc;
   a.small_units = a.nunits < (1ll << 31);
+  static const int tune_sf = env_int("XG_STRIDED_SEGFAST", 0);
+  a.seg_fast = tune_sf != 0;
   const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2: grid too large");
   if (!MET && tune_u == 8)
@@ -447,6 +455,7 @@ int stencil2_typed(int op, const void* in, void* out, int ndim, const int64_t* s
   a.J = 0;
   a.nseg = a.nwc = a.nunits = 0;
   a.small_units = false;
+  a.seg_fast = false;
   if (v.n == 0) return xg_fail(XG_EINVAL, "xg_stencil2: empty operated axis");
   if (v.outer == 0 || v.inner == 0 || a.n_out <= 0) return XG_OK;  // nothing to write
 
