@@ -116,6 +116,36 @@ def test_multi_axis_sequential_and_dim_order():
     np.testing.assert_array_equal(got.values, want)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_multi_axis_fused_path_wide_rows(dtype):
+    """Rows >= 32 wide take the fused xg_stencil_multi launch: same values as the per-axis loop
+    (grid.py:800-832), for every op, 2 and 3 axes, any order, per-axis `to` / padding / fill."""
+    ds, gc, rng = all_positions_3d((6, 20, 40))
+    grid = xg.Grid(ds, coords=gc, padding={"X": "periodic", "Y": "fill", "Z": "extend"})
+    a = rng.random((6, 20, 40)).astype(dtype)
+    da = xg.DataArray(a, dims=("z_c", "y_c", "x_c"))
+    bc = {"X": "periodic", "Y": "fill", "Z": "extend"}
+    idx = {"Z": 0, "Y": 1, "X": 2}
+    for op in OPS:
+        for axes in (["X", "Y"], ["Y", "X"], ["Y", "Z"], ["Z", "X"], ["X", "Y", "Z"], ["Z", "Y", "X"]):
+            for to in ("left", "right", "outer", "inner"):
+                lo, hi = oracle.PADDING_WIDTH[("center", to)]
+                want = a
+                for ax in axes:
+                    want = oracle.stencil2(op, want, idx[ax], lo, hi, bc[ax] if (lo or hi) else None, 0.0)
+                got = getattr(grid, op)(da, axes, to=to)
+                sfx = POS_SUFFIX[to]
+                exp_dims = tuple(f"{d[0]}_{sfx}" if d[0].upper() in axes else d for d in ("z_c", "y_c", "x_c"))
+                assert got.dims == exp_dims, (op, axes, to)
+                np.testing.assert_array_equal(got.values, want, err_msg=f"{op} {axes} {to}")
+                np.testing.assert_array_equal(got.coords[exp_dims[2]].values, ds[exp_dims[2]].values)
+    got = grid.diff(da, ["X", "Z"], to={"X": "right", "Z": "outer"}, padding={"X": "fill"}, fill_value={"X": 3.0})
+    want = oracle.stencil2("diff", oracle.stencil2("diff", a, 2, 0, 1, "fill", 3.0), 0, 1, 1, "extend")
+    np.testing.assert_array_equal(got.values, want)
+    with pytest.raises(ValueError, match="No boundary condition"):
+        xg.Grid(ds, coords=gc).interp(da, ["X", "Y"])
+
+
 def test_device_resident_inputs_stay_on_device():
     ds, gc, rng = all_positions_3d((6, 7, 8))
     grid = xg.Grid(ds, coords=gc, padding="periodic")

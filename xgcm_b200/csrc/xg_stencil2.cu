@@ -336,15 +336,12 @@ int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
   // short enough that there are plenty of warps for 148 SMs.
   static const int tune_j = env_int("XG_STRIDED_J", 0);  // tuning knobs (benchmarks only)
   static const int tune_u = env_int("XG_STRIDED_U", 0);
-  // Measured on B200 (profiles/r02_tune_strided.txt): when one row of the slab spans few
-  // warp-columns (Y of a (Z, Y, X) field: 29), the segment that re-reads a halo row runs
-  // concurrently with the one that owns it, the re-read is an L2 hit, and SHORT marches win
-  // (J = 4: 1.05 of the copy peak, J = 32: 0.97) because they spread a DRAM page over more
-  // concurrent warps.  When a row is a whole plane (Z: 67 500 warp-columns) the re-read would
-  // come from DRAM, so march as far as possible.
+  // Tuning notes (profiles/r02_tune_strided.txt): in a loop of identical launches short marches
+  // (J = 4) look 8 % faster for Y, but per-launch ncu timings and the mixed sequence of bench.py
+  // show no gain, and the fused-metric variants lose 20 % (per-segment operand setup is amortised
+  // over fewer rows) — so 32 stays; a plane-strided axis marches as far as possible.
   int J;
   if (tune_j > 0) J = tune_j;
-  else if (a.nwc <= 2048) J = 4;
   else J = (a.n_out <= 96) ? (int)a.n_out : 32;
   if (J > a.n_out) J = (int)a.n_out;
   a.J = J;

@@ -467,7 +467,8 @@ class Grid:
         specs, rename = [], {}
         for sig, ax_name in zip(signatures, axis):
             grid_ufunc, _ = _select_grid_ufunc(funcname, sig, module=gridops)
-            lo, hi = (grid_ufunc.padding_width or {}).get(sig.in_ax_names[0][0], (0, 0))
+            dummy = grid_ufunc.signature.in_ax_names[0][0]  # the ufunc's own dummy axis name ("X")
+            lo, hi = (grid_ufunc.padding_width or {}).get(dummy, (0, 0))
             from_pos = sig.in_ax_positions[0][0]
             to_pos = sig.out_ax_positions[0][0]
             in_dim = self.axes[ax_name].coords[from_pos]
