@@ -15,6 +15,8 @@
 // window of W + 1 consecutive source positions (one aligned vector + one neighbour element).
 //
 // Roofline: HBM, 2 * sizeof(T) bytes per output cell.
+#include <stdlib.h>
+
 #include "xg_common.cuh"
 
 namespace {
@@ -358,7 +360,11 @@ int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int n
   const int march_dim = axes[march];
   a.march_n_out = out_shape[march_dim];
   a.march_out_stride = out_stride[march_dim];
-  a.J = a.march_n_out <= 96 ? (int)a.march_n_out : 32;
+  a.J = a.march_n_out <= 16 ? (int)a.march_n_out : 16;  // measured flat optimum (profiles/r02_tune_multi.txt)
+  if (const char* e = getenv("XG_MULTI_J")) {  // tuning knob (benchmarks only)
+    const int tj = atoi(e);
+    if (tj > 0) a.J = tj < a.march_n_out ? tj : (int)a.march_n_out;
+  }
   a.nseg = xg_ceil_div(a.march_n_out, a.J);
   // row groups: operated dims alone, runs of non-operated dims merged
   a.nrow_groups = 0;
