@@ -145,19 +145,13 @@ struct Eval {
         int64_t s0, s1;
         const bool ok0 = resolve(ax, j[m], s0);  // block-uniform: j is this block's row
         const bool ok1 = resolve(ax, j[m] + 1, s1);
-        Win<T, W> lo_v, hi_v;
-        if (ok0) lo_v = run<k - 1, W>(a, j, off + s0 * ax.in_stride, x);
-        else {
+        // branch-free: a fill halo still reads a (clamped, valid) row and is replaced afterwards,
+        // so every load of the recursion can be issued before the first value is consumed
+        Win<T, W> lo_v = run<k - 1, W>(a, j, off + s0 * ax.in_stride, x);
+        Win<T, W> hi_v = run<k - 1, W>(a, j, off + s1 * ax.in_stride, x);
 #pragma unroll
-          for (int q = 0; q < W; ++q) lo_v.v[q] = ax.fill;
-        }
-        if (ok1) hi_v = run<k - 1, W>(a, j, off + s1 * ax.in_stride, x);
-        else {
-#pragma unroll
-          for (int q = 0; q < W; ++q) hi_v.v[q] = ax.fill;
-        }
-#pragma unroll
-        for (int q = 0; q < W; ++q) r.v[q] = xg_apply_op<T, OP>(lo_v.v[q], hi_v.v[q]);
+        for (int q = 0; q < W; ++q)
+          r.v[q] = xg_apply_op<T, OP>(ok0 ? lo_v.v[q] : ax.fill, ok1 ? hi_v.v[q] : ax.fill);
       }
       return r;
     }
@@ -208,13 +202,11 @@ __global__ void __launch_bounds__(256, 4) k_stencil_multi(const MultiArgs<T> a) 
     // padded intermediate below the march op at padded position p of the march axis
     auto below = [&](int64_t p) -> Win<T, WM> {
       int64_t sidx;
-      if (!resolve(mx, p, sidx)) {
-        Win<T, WM> f;
+      const bool ok = resolve(mx, p, sidx);  // a fill halo reads the clamped row and is replaced
+      Win<T, WM> r = Eval<T, VEC, K, LAST, OP>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
 #pragma unroll
-        for (int q = 0; q < WM; ++q) f.v[q] = mx.fill;
-        return f;
-      }
-      return Eval<T, VEC, K, LAST, OP>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
+      for (int q = 0; q < WM; ++q) r.v[q] = ok ? r.v[q] : mx.fill;
+      return r;
     };
     auto finish = [&](int64_t jm, const Win<T, WM>& lo_w, const Win<T, WM>& hi_w) {
       Win<T, WM> r;
