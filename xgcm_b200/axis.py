@@ -11,7 +11,7 @@ from __future__ import annotations
 
 from typing import Mapping, Optional, Tuple, Union
 
-from .labeled import DataArray, Dataset
+from .labeled import Dataset
 
 VALID_POSITION_NAMES = "center|left|right|inner|outer"
 _VALID_POSITIONS = tuple(VALID_POSITION_NAMES.split("|"))

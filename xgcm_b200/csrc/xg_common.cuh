@@ -177,33 +177,6 @@ __device__ __forceinline__ void xg_st_stream(T* p, const XgPack<T, VEC>& r) {
   }
 }
 
-// Load VEC metric values for flat inner indices i .. i+VEC-1 at (outer offset +
-// axis offset) `base`.
-template <typename T, int VEC>
-__device__ __forceinline__ XgPack<T, VEC> xg_ld_operand(const XgOperand& m,
-                                                        int64_t base,
-                                                        int64_t i) {
-  const T* p = reinterpret_cast<const T*>(m.ptr) + base;
-  XgPack<T, VEC> r;
-  if (m.inner_mode == XG_IM_BCAST) {
-    T s = __ldg(p);
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) r.v[k] = s;
-  } else if (m.inner_mode == XG_IM_CONTIG) {
-    if (VEC > 1 && m.vec_ok) {
-      r = xg_ld_cached<T, VEC>(p + i);
-    } else {
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) r.v[k] = __ldg(p + i + k);
-    }
-  } else {
-#pragma unroll
-    for (int k = 0; k < VEC; ++k)
-      r.v[k] = __ldg(p + xg_groups_offset(m.inner, i + k));
-  }
-  return r;
-}
-
 // Per-thread view of a broadcast operand for the VEC elements starting at flat inner index i:
 // computed ONCE per thread (i is fixed while a thread marches along the axis), so the per-row
 // cost of a fused metric is one (vector) load and VEC multiplies / divides.  Kept small on

@@ -21,7 +21,6 @@ face connections, north-fold padding, dask chunking, metadata autoparsing.
 
 from __future__ import annotations
 
-import functools
 import inspect
 import itertools
 import warnings
@@ -42,7 +41,7 @@ from .grid_ufunc import (
 )
 from .labeled import DataArray, Dataset, is_device_array
 from .metrics import iterate_axis_combinations
-from .padding import pad
+from .padding import pad  # noqa: F401  (re-exported like the reference's grid module)
 
 
 def _maybe_promote_str_to_list(a):

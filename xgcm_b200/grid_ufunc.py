@@ -24,7 +24,7 @@ from typing import Any, Callable, Dict, List, Mapping, Optional, Sequence, Tuple
 
 import numpy as np
 
-from .labeled import DataArray, is_device_array
+from .labeled import DataArray
 from .padding import pad
 
 _AXIS_NAME = r"\w+"

@@ -19,7 +19,7 @@ which never calls these operators (see ``grid.py``).
 from __future__ import annotations
 
 from collections import OrderedDict
-from typing import Any, Dict, Hashable, Iterable, Mapping, Optional, Sequence, Tuple, Union
+from typing import Mapping
 
 import numpy as np
 

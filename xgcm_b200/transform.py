@@ -13,7 +13,7 @@ import warnings
 
 import numpy as np
 
-from .labeled import DataArray, is_device_array
+from .labeled import DataArray
 
 
 def interp_1d_linear(phi, theta, target_theta_levels, mask_edges=False, bypass_checks=False,
@@ -21,8 +21,6 @@ def interp_1d_linear(phi, theta, target_theta_levels, mask_edges=False, bypass_c
     """Array-level entry point with the reference's signature (transform.py:44-85):
     ``phi[..., n], theta[..., n], target[m] -> [..., m]`` along the LAST axis.
     numpy in -> numpy out (through the GPU); CUDA tensors stay on the device."""
-    import torch
-
     from . import ops
     from .device import as_device_tensor, result_like
 
