@@ -169,6 +169,9 @@ __global__ void __launch_bounds__(256, 4) k_stencil_multi(const MultiArgs<T> a) 
   constexpr bool kInnerAbove = (LAST > MARCH);
   constexpr int WM = kInnerAbove ? VEC + 1 : VEC;  // window width at the march level
   constexpr int U = 4;
+  // With row ops below the march level the select form wins (Y,Z 1.38 -> 1.29 ms); the plain
+  // X,Y case has a single load per step and measured faster with the branch (1.09 vs 1.20 ms).
+  constexpr bool kBranchFreeMarch = !(K == 2 && LAST >= 0);
   // this block: a segment of the march axis at fixed coordinates of every other row group
   int64_t unit = blockIdx.x;
   const int64_t seg = unit % a.nseg;
@@ -202,11 +205,20 @@ __global__ void __launch_bounds__(256, 4) k_stencil_multi(const MultiArgs<T> a) 
     // padded intermediate below the march op at padded position p of the march axis
     auto below = [&](int64_t p) -> Win<T, WM> {
       int64_t sidx;
-      const bool ok = resolve(mx, p, sidx);  // a fill halo reads the clamped row and is replaced
-      Win<T, WM> r = Eval<T, VEC, K, LAST, OP>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
+      const bool ok = resolve(mx, p, sidx);
+      if constexpr (kBranchFreeMarch) {
+        // a fill halo reads the clamped row and is replaced, so the U loads batch ahead of use
+        Win<T, WM> r = Eval<T, VEC, K, LAST, OP>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
 #pragma unroll
-      for (int q = 0; q < WM; ++q) r.v[q] = ok ? r.v[q] : mx.fill;
-      return r;
+        for (int q = 0; q < WM; ++q) r.v[q] = ok ? r.v[q] : mx.fill;
+        return r;
+      } else {
+        if (ok) return Eval<T, VEC, K, LAST, OP>::template run<MARCH, WM>(a, j, off_in + sidx * mx.in_stride, xw);
+        Win<T, WM> r;
+#pragma unroll
+        for (int q = 0; q < WM; ++q) r.v[q] = mx.fill;
+        return r;
+      }
     };
     auto finish = [&](int64_t jm, const Win<T, WM>& lo_w, const Win<T, WM>& hi_w) {
       Win<T, WM> r;
