@@ -35,9 +35,9 @@ namespace {
 constexpr int kWarps = 8;
 constexpr int kTile = 32;
 constexpr int LIKELY_IN_CACHE_SIZE = 8;
-constexpr int kPrefetchRows = 6;
+constexpr int kPrefetchRows = 6;  // theta-field kernel: phi / theta rows pulled into L1 ahead of the walk
 template <typename T>
-constexpr int kCPLv = 1;  // columns per lane in the shared-theta kernel (2 was measured slower: 3.0 vs 2.7 ms at C5)  // phi rows pulled into L1 ahead of the interval in use
+constexpr int kCPLv = 1;  // columns per lane in the shared-theta kernel (2 was measured slower: 3.0 vs 2.7 ms at C5)
 
 template <typename T>
 struct InterpArgs {
@@ -143,9 +143,11 @@ __device__ __forceinline__ void store_tile(T (*tile)[kTile + 1], T* out, int64_t
 enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NAN = 4 };
 
 struct __align__(16) Run {
-  int t_begin, t_end;  // targets [t_begin, t_end) — never crosses a multiple of 32
-  int j;               // interval index (PK_INTERP / PK_EXACT)
-  int kind;
+  int t_begin;   // targets [t_begin, t_begin + len) — never crosses a multiple of 32
+  int len_kind;  // len | kind << 8
+  int j;         // interval index (PK_INTERP / PK_EXACT)
+  int next_j;    // set on runs that enter a new interval: the interval the NEXT such run enters
+                 // (-1: none), so its two nodes are requested one interval early
 };
 
 template <typename T>
@@ -276,20 +278,30 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
   if (tid == 0) {  // group consecutive targets with the same work into runs, split at tile edges
     int nr = 0;
     for (int t = 0; t < m; ++t) {
-      const bool fresh = (t % kTile == 0) || tk[t] != runs[nr - 1].kind ||
+      const bool fresh = (t % kTile == 0) || tk[t] != (runs[nr - 1].len_kind >> 8) ||
                          (tk[t] <= PK_EXACT && tj[t] != runs[nr - 1].j);
       if (t % kTile == 0) chunk_run[t / kTile] = nr;
       if (fresh) {
         runs[nr].t_begin = t;
-        runs[nr].t_end = t + 1;
+        runs[nr].len_kind = 1 | (tk[t] << 8);
         runs[nr].j = tj[t];
-        runs[nr].kind = tk[t];
+        runs[nr].next_j = -1;
         ++nr;
       } else {
-        runs[nr - 1].t_end = t + 1;
+        runs[nr - 1].len_kind += 1;
       }
     }
     chunk_run[nchunk] = nr;
+    // link the runs that enter a new interval (the column loop memoises the current one)
+    int cjs = -2, last = -1;
+    flags[3] = -1;
+    for (int r = 0; r < nr; ++r) {
+      if ((runs[r].len_kind >> 8) > PK_EXACT || runs[r].j == cjs) continue;
+      cjs = runs[r].j;
+      if (last >= 0) runs[last].next_j = cjs;
+      else flags[3] = cjs;
+      last = r;
+    }
   }
   __syncthreads();
 
@@ -302,31 +314,28 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
   const int64_t group_stride = (int64_t)gridDim.x * kWarps;
   const int64_t ngroups = (a.ntiles + kCPLv<T> - 1) / kCPLv<T>;
   const int64_t step = flip ? -a.inner : a.inner;  // phi pointer step for j -> j + 1
+  const int j_first = flags[3];                    // first interval any column enters (-1: none)
   for (int64_t cg = (int64_t)blockIdx.x * kWarps + w; cg < ngroups; cg += group_stride) {
     const T* phi0[kCPLv<T>];
-    const T* pj1[kCPLv<T>];
-    bool ok[kCPLv<T>];
-    double yj[kCPLv<T>], yj1[kCPLv<T>], slope[kCPLv<T>], y_first[kCPLv<T>], y_last[kCPLv<T>];
+    T raw_a[kCPLv<T>], raw_b[kCPLv<T>];  // nodes j, j + 1 of the NEXT interval to enter, in flight
+    T raw_first[kCPLv<T>], raw_last[kCPLv<T>];
+    double yj[kCPLv<T>], yj1[kCPLv<T>], slope[kCPLv<T>];
 #pragma unroll
     for (int c = 0; c < kCPLv<T>; ++c) {
-      const int64_t col = (cg * kCPLv<T> + c) * kTile + lane;
-      ok[c] = col < ncols;
-      phi0[c] = a.phi;
-      if (ok[c]) {
-        int64_t o, i;
-        xg_divmod(col, a.inner, a.small_cols, o, i);
-        phi0[c] = a.phi + o * a.n * a.inner + i + (flip ? (int64_t)(n - 1) * a.inner : 0);
-#pragma unroll
-        for (int k = 1; k <= kPrefetchRows; ++k)  // warm L1 with the first rows of this column
-          if (k < n) asm volatile("prefetch.global.L1 [%0];" ::"l"(phi0[c] + k * step));
+      const int64_t tile_id = cg * kCPLv<T> + c;
+      int64_t col = tile_id * kTile + lane;
+      if (col >= ncols) col = ncols - 1;  // spare lanes (and a spare tile) shadow the last column
+      int64_t o, i;
+      xg_divmod(col, a.inner, a.small_cols, o, i);
+      phi0[c] = a.phi + o * a.n * a.inner + i + (flip ? (int64_t)(n - 1) * a.inner : 0);
+      raw_first[c] = __ldg(phi0[c]);
+      raw_last[c] = __ldg(phi0[c] + (int64_t)(n - 1) * step);
+      raw_a[c] = raw_b[c] = T(0);
+      if (j_first >= 0) {
+        raw_a[c] = __ldg(phi0[c] + (int64_t)j_first * step);
+        raw_b[c] = __ldg(phi0[c] + (int64_t)(j_first + 1) * step);
       }
-      pj1[c] = phi0[c];
       yj[c] = yj1[c] = slope[c] = 0.0;
-    }
-#pragma unroll
-    for (int c = 0; c < kCPLv<T>; ++c) {
-      y_first[c] = ok[c] ? (double)__ldg(phi0[c]) : 0.0;
-      y_last[c] = ok[c] ? (double)__ldg(phi0[c] + (int64_t)(n - 1) * step) : 0.0;
     }
     int cj = -2;  // memoised interval (common to the kCPLv<T> columns)
     double xj = 0.0, xj1 = 0.0;
@@ -336,30 +345,28 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
       const int r_end = chunk_run[cc + 1];
       for (int r = chunk_run[cc]; r < r_end; ++r) {
         const Run run = runs[r];  // one 16-byte broadcast read
-        const int len = run.t_end - run.t_begin;
+        const int len = run.len_kind & 0xff;
+        const int kind = run.len_kind >> 8;
         const int d0 = run.t_begin - t0;
-        if (run.kind <= PK_EXACT) {
+        if (kind <= PK_EXACT) {
           if (run.j != cj) {
-            const bool jump = (run.j != cj + 1 || cj < 0);  // rare: re-seat on node j first
+            const bool seq = (run.j == cj + 1);  // node j is the old node j + 1
             cj = run.j;
-            const double xj_new = jump ? Xs[cj] : xj1;
-            xj = xj_new;
+            xj = seq ? xj1 : Xs[cj];
             xj1 = Xs[cj + 1];
             const double dxj = xj1 - xj, rr = rdx[cj];
-            const bool pf = cj + 1 + kPrefetchRows < n;
+            const int nj = run.next_j;
 #pragma unroll
             for (int c = 0; c < kCPLv<T>; ++c) {
-              if (ok[c]) {
-                if (jump) {
-                  pj1[c] = phi0[c] + (int64_t)cj * step;
-                  yj1[c] = (double)__ldg(pj1[c]);
-                }
-                // the usual case: walk one interval up; (xj1, yj1) held node j already
-                yj[c] = yj1[c];
-                pj1[c] += step;
-                yj1[c] = (double)__ldg(pj1[c]);
-                // targets normally ascend: pull a row a few intervals ahead into L1 now
-                if (pf) asm volatile("prefetch.global.L1 [%0];" ::"l"(pj1[c] + kPrefetchRows * step));
+              yj[c] = seq ? yj1[c] : (double)raw_a[c];
+              yj1[c] = (double)raw_b[c];
+              // The plan knows which interval is entered next: request its nodes now, a whole
+              // interval of work before they are converted above (the per-interval wait on this
+              // load was 37 % of all stall samples, profiles/r02_vinterp_stalls.txt).
+              if (nj >= 0) {
+                const T* pn = phi0[c] + (int64_t)nj * step;
+                raw_b[c] = __ldg(pn + step);
+                if (nj != cj + 1) raw_a[c] = __ldg(pn);
               }
             }
 #pragma unroll
@@ -368,8 +375,9 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
               slope[c] = (rr != 0.0 && exponent_safe(dyj)) ? div_with_recip(dyj, dxj, rr) : dyj / dxj;
             }
           }
-          if (run.kind == PK_INTERP) {
+          if (kind == PK_INTERP) {
             const double* xp = xt + run.t_begin;
+#pragma unroll 1  // runs hold one or two targets
             for (int q = 0; q < len; ++q) {
               const double x = xp[q];
 #pragma unroll
@@ -380,13 +388,15 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
 #pragma unroll
             for (int c = 0; c < kCPLv<T>; ++c) {
               const T v = (T)yj[c];
+#pragma unroll 1
               for (int q = 0; q < len; ++q) tiles[w][c][lane][d0 + q] = v;
             }
           }
         } else {
 #pragma unroll
           for (int c = 0; c < kCPLv<T>; ++c) {
-            const T v = (run.kind == PK_FIRST) ? (T)y_first[c] : (run.kind == PK_LAST) ? (T)y_last[c] : T(NAN);
+            const T v = (kind == PK_FIRST) ? raw_first[c] : (kind == PK_LAST) ? raw_last[c] : T(NAN);
+#pragma unroll 1
             for (int q = 0; q < len; ++q) tiles[w][c][lane][d0 + q] = v;
           }
         }
@@ -601,8 +611,15 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
                                          (int)plan_bytes);
     if (e != cudaSuccess)
       return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+    // persistent: the plan is amortised over many tiles, and exactly one resident wave so that no
+    // SM runs a half-empty second wave
+    int dev = 0, sms = 148, per_sm = 1;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_vinterp_shared<T>, kWarps * 32, plan_bytes);
+    if (e != cudaSuccess || per_sm < 1) per_sm = 1;
     int64_t blocks = xg_ceil_div(xg_ceil_div(a.ntiles, kCPLv<T>), kWarps);
-    if (blocks > 148 * 6) blocks = 148 * 6;  // persistent-ish: the plan is amortised over many tiles
+    if (blocks > (int64_t)sms * per_sm) blocks = (int64_t)sms * per_sm;
     k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
     return xg_check_launch("xg_vinterp_linear(shared)");
   }
