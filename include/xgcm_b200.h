@@ -17,6 +17,7 @@
  *   xg_vinterp_conservative <- xgcm/transform.py:88-191 (_interp_1d_conservative)
  *   xg_pad             <- xgcm/padding.py:765-871 (pad) for callers that want the
  *                         padded array itself (custom grid ufuncs)
+ *   xg_strided_copy    <- xgcm/padding.py:260-572 (_pad_face_connections: one connected edge)
  *   xg_binary / xg_unary
  *                      <- the xarray broadcast arithmetic around the hot path
  *                         (xgcm/grid.py:808,832,1578,1599,1657)
@@ -189,6 +190,18 @@ XG_API int xg_pad(int dtype, const void* in, void* out, int ndim,
 XG_API int xg_binary(int binop, int dtype, const void* a, const void* b,
               const int64_t* b_strides, void* out, int ndim,
               const int64_t* shape, void* stream);
+
+/*
+ * dst[sum_d i_d * dst_strides[d]] = (negate ? -1 : 1) * src[sum_d i_d * src_strides[d]] for every
+ * index tuple in `shape`.  Strides are in ELEMENTS and may be negative; dst / src point at the
+ * element with index (0, ..., 0).  This is the data movement of face-connection padding
+ * (xgcm/padding.py:414-541: slice the neighbour face, swap the horizontal dims, flip across /
+ * along the seam, sign-flip vector components, concatenate into the halo): each connected edge
+ * is one call, the host works out the strides (xgcm_b200/padding.py:_pad_face_connections).
+ */
+XG_API int xg_strided_copy(int dtype, void* dst, const int64_t* dst_strides, const void* src,
+                    const int64_t* src_strides, int ndim, const int64_t* shape, int negate,
+                    void* stream);
 
 /* Deterministic synthetic field: out[i] = U(0,1) keyed by (seed, offset+i);
  * identical bits on host (xg_fill_uniform_host) and device. */

@@ -1,11 +1,12 @@
 """Host-side logic on CPU: the Grid / Axis / grid-ufunc bookkeeping of the package with the CUDA
 kernels replaced by the oracle (tests/_mock_backend.py).  The SAME test bodies run against the
-real kernels on the GPU box (test_grid_gpu.py / test_transform_gpu.py, marker `gpu`)."""
+real kernels on the GPU box (test_grid_gpu.py / test_transform_gpu.py / test_faces_gpu.py, marker `gpu`)."""
 
 import numpy as np
 import pytest
 import torch
 
+import test_faces_gpu as F
 import test_grid_gpu as G
 import test_transform_gpu as T
 import xgcm_b200 as xg
@@ -25,7 +26,7 @@ def mock_backend(monkeypatch):
     install(monkeypatch)
 
 
-for _mod in (G, T):
+for _mod in (G, T, F):
     for _name in dir(_mod):
         if _name.startswith("test_") and _name not in _NEEDS_REAL_GPU:
             globals()[f"{_name}__hostlogic"] = getattr(_mod, _name)

@@ -111,6 +111,9 @@ class Axis:
             raise TypeError("fill value must be an integer or a float")
         self._fill_value = fill_value
         self._periodic = padding == "periodic"
+        # set by Grid._assign_face_connections (grid.py:407-409)
+        self._facedim = None
+        self._face_connections = None
 
     @property
     def periodic(self) -> bool:

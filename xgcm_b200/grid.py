@@ -16,7 +16,7 @@ produced by a CUDA kernel behind the C-ABI:
 
 Host (numpy-backed) inputs are streamed through the GPU and come back as numpy;
 CUDA-resident inputs stay resident.  Out of scope (raise ``NotImplementedError``):
-face connections, north-fold padding, dask chunking, metadata autoparsing.
+north-fold padding, dask chunking.
 """
 
 from __future__ import annotations
@@ -111,13 +111,12 @@ class Grid:
                 "Could not determine Axis names - please provide them in the coords kwarg "
                 "or provide a dataset from which they can be parsed"
             )
-        if face_connections:
-            raise NotImplementedError(
-                "face_connections (cubed-sphere / LLC tile topology, reference padding.py:230-572) "
-                "are outside the scope of xgcm_b200"
-            )
-        self._facedim = None
-        self._face_connections = None
+        if face_connections is not None and face_connections:  # grid.py:256-261
+            self._facedim = list(face_connections.keys())[0]
+            self._face_connections = face_connections
+        else:
+            self._facedim = None
+            self._face_connections = None
         self._folds = {}
 
         all_axes = list(coords.keys())
@@ -137,11 +136,75 @@ class Grid:
                 fill_value=fill_dict.get(name, None),
             )
 
+        if face_connections is not None:
+            self._assign_face_connections(face_connections)
+
         self._metrics: Dict[frozenset, List[DataArray]] = {}
         self._metric_cache: Dict[Any, Any] = {}
         if metrics is not None:
             for key, value in metrics.items():
                 self.set_metrics(key, value)
+
+    # ------------------------------------------------------------------ topology
+    def _assign_face_connections(self, fc):
+        """Check that every link of a face-connection dict is mirrored by its neighbour and hand
+        each Axis its links (grid.py:334-409).  Structure: ``{facedim: {face: {axis: (left,
+        right)}}}`` with a link ``(neighbour face, neighbour axis, reverse)`` or None."""
+        if len(fc) > 1:
+            raise ValueError(
+                "Only one face dimension is supported for now. Instead found %r" % repr(fc.keys())
+            )
+        facedim = list(fc.keys())[0]
+        if facedim not in self._ds.dims:
+            raise ValueError(
+                f"Face dimension {facedim} does not exist in the dataset. "
+                f"Found {list(self._ds.dims)} instead"
+            )
+        face_values = list(np.asarray(self._ds[facedim].values).tolist())
+        face_links = fc[facedim]
+        axis_connections: Dict[str, Dict[Any, Any]] = {}
+        for fidx, face_axis_links in face_links.items():
+            for axis, axis_links in face_axis_links.items():
+                axis_connections.setdefault(axis, {})
+                link_left, link_right = axis_links
+
+                def check_neighbor(link, position):
+                    if link is None:
+                        return None
+                    idx, ax, rev = link
+                    # a reversed link arrives at the same side of the neighbour
+                    correct_position = int(not position) if rev else position
+                    try:
+                        neighbor_link = face_links[idx][ax][correct_position]
+                    except (KeyError, IndexError):
+                        raise KeyError(
+                            "Couldn't find a face link for face %r"
+                            "in axis %r at position %r" % (idx, ax, correct_position)
+                        )
+                    idx_n, ax_n, rev_n = neighbor_link
+                    if ax not in self.axes:
+                        raise KeyError("axis %r is not a valid axis" % ax)
+                    if ax_n not in self.axes:
+                        raise KeyError("axis %r is not a valid axis" % ax_n)
+                    for i in (idx, idx_n):
+                        if i not in face_values:
+                            raise IndexError(
+                                "%r is not a valid index for face dimension %r" % (i, facedim)
+                            )
+                    if (idx_n != fidx) or (ax_n != axis) or (rev_n != rev):
+                        raise ValueError(
+                            "Face link mismatch: neighbor doesn't correctly link back to this face. "
+                            "face: %r, axis: %r, position: %r, rev: %r, link: %r, neighbor_link: %r"
+                            % (fidx, axis, position, rev, link, neighbor_link)
+                        )
+                    return idx, self.axes[ax], rev
+
+                left = check_neighbor(link_left, 1)
+                right = check_neighbor(link_right, 0)
+                axis_connections[axis][fidx] = (left, right)
+        for axis, axis_links in axis_connections.items():
+            self.axes[axis]._facedim = facedim
+            self.axes[axis]._face_connections = axis_links
 
     # ------------------------------------------------------------------ kwargs plumbing
     def _map_kwargs_over_axes(self, kwargs, axes: Optional[Iterable[str]] = None) -> Dict[str, Any]:
@@ -461,6 +524,8 @@ class Grid:
         from . import ops
         from .device import as_device_tensor, result_like
 
+        if self._face_connections is not None:
+            return None  # halos come from other faces: per-axis pad + stencil
         paddings = self._complete_user_kwargs_using_axis_defaults(kwargs.get("padding"), "padding")
         fills = self._complete_user_kwargs_using_axis_defaults(kwargs.get("fill_value"), "fill_value")
         specs, rename = [], {}
@@ -721,11 +786,50 @@ class Grid:
         return self._wrap_out(transform(self, axis, da, target, **kwargs), as_xarray)
 
     # deprecated 2-D vector wrappers of the reference (grid.py:1420-1532) are not carried over
-    def diff_2d_vector(self, *a, **k):
-        raise NotImplementedError("diff_2d_vector is deprecated upstream; call diff on each component")
+    def _apply_vector_function(self, function, vector, **kwargs):
+        """Apply diff / interp to both components of a C-grid vector, each padded with the other
+        as its partner across rotated face connections (grid.py:1420-1474)."""
+        if not (isinstance(vector, dict) and len(vector) == 2):
+            raise ValueError(
+                "Input is expected to be a dictionary with two key/value pairs which map grid axis "
+                "to the vector component parallel to that axis"
+            )
+        warnings.warn(
+            "`interp_2d_vector` and `diff_2d_vector` will be removed from future releases."
+            "The same functionality will be accessible under the `xgcm.Grid.diff` and "
+            "`xgcm.Grid.interp` methods, please see those docstrings for details.",
+            category=DeprecationWarning,
+        )
+        to = kwargs.get("to", "center")
+        if to != "center":
+            raise NotImplementedError(
+                "Only vector interpolation to cell center is implemented, but got to=%r" % to
+            )
+        for axis_name, component in vector.items():
+            position, _ = self.axes[axis_name]._get_position_name(component)
+            if position == "center":
+                raise NotImplementedError(
+                    "Only vector interpolation to cell center is implemented, but vector %s "
+                    "component is defined at center (dims: %r)" % (axis_name, component.dims)
+                )
+        x_axis_name, y_axis_name = list(vector)
+        x_component = function(
+            {x_axis_name: vector[x_axis_name]}, x_axis_name,
+            other_component={y_axis_name: vector[y_axis_name]}, **kwargs,
+        )
+        y_component = function(
+            {y_axis_name: vector[y_axis_name]}, y_axis_name,
+            other_component={x_axis_name: vector[x_axis_name]}, **kwargs,
+        )
+        return {x_axis_name: x_component, y_axis_name: y_component}
 
-    def interp_2d_vector(self, *a, **k):
-        raise NotImplementedError("interp_2d_vector is deprecated upstream; call interp on each component")
+    def diff_2d_vector(self, vector, **kwargs):
+        """Difference a 2-D vector to the intermediate grid point (grid.py:1476-1495)."""
+        return self._apply_vector_function(self.diff, vector, **kwargs)
+
+    def interp_2d_vector(self, vector, **kwargs):
+        """Interpolate a 2-D vector to the intermediate grid point (grid.py:1497-1530)."""
+        return self._apply_vector_function(self.interp, vector, **kwargs)
 
 
 def _nan_mask_weights(x, w):

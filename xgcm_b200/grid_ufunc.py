@@ -495,7 +495,7 @@ def apply_as_grid_ufunc(
             _apply_fused_stencil(
                 kernel_op, input_arrays[0], grid, axis[0][0], in_core_dims[0][0],
                 out_core_dims[0][0], padding_width_real, padding, fill_value,
-                pre_metric, post_metric_fn,
+                pre_metric, post_metric_fn, raw_arg=args[0], other_component=other_component[0],
             ),
         )
     else:
@@ -514,12 +514,52 @@ def apply_as_grid_ufunc(
     return results
 
 
+def _apply_connected_stencil(op, da, raw_arg, other_component, grid, ax_name, in_dim, out_dim,
+                             padding_width_real, padding, fill_value, pre_metric, post_metric_fn):
+    """Built-in operator on a grid with face connections: the halo is not an affine function of
+    the field any more (it comes from other faces, rotated), so it is materialised once by
+    ``pad`` -> ``xg_strided_copy`` and the stencil then runs on the padded array without a
+    boundary condition (reference: grid_ufunc.py:903-921 pads, then applies the kernel)."""
+    from . import ops
+    from .device import as_device_tensor, result_like
+    from .padding import pad
+
+    lo, hi = padding_width_real.get(ax_name, (0, 0))
+    if pre_metric is not None:
+        if isinstance(raw_arg, dict):
+            raise NotImplementedError(
+                "metric weighting of vector components across face connections is not implemented"
+            )
+        x, was_host = as_device_tensor(da.data, grid._device_for(da))
+        x = ops.binary("mul", x, grid._metric_tensor(pre_metric, da.dims, x))
+        weighted = DataArray(result_like(x, was_host), dims=da.dims, name=da.name, attrs=da.attrs)
+        raw_arg = weighted
+    padded = pad(raw_arg, grid=grid, padding_width={ax_name: (lo, hi)}, padding=padding,
+                 fill_value=fill_value, other_component=other_component)
+    if isinstance(padded, dict):  # zero-width request: pad returns its input untouched
+        [padded] = list(padded.values())
+    axis_num = padded.get_axis_num(in_dim)
+    out_dims = tuple(out_dim if d == in_dim else d for d in padded.dims)
+    out_shape = list(padded.shape)
+    out_shape[axis_num] = padded.shape[axis_num] - 1
+    post_da = post_metric_fn(_ShapeProbe(out_dims, out_shape)) if post_metric_fn is not None else None
+    x, was_host = as_device_tensor(padded.data, grid._device_for(padded))
+    post_t = grid._metric_tensor(post_da, out_dims, x) if post_da is not None else None
+    out = ops.stencil2(x, axis_num, op, 0, 0, None, post=post_t)
+    return DataArray(result_like(out, was_host), dims=out_dims, name=da.name, attrs=da.attrs)
+
+
 def _apply_fused_stencil(op, da, grid, ax_name, in_dim, out_dim, padding_width_real, padding,
-                         fill_value, pre_metric, post_metric_fn):
+                         fill_value, pre_metric, post_metric_fn, raw_arg=None, other_component=None):
     """One ``xg_stencil2`` launch: halo + operator + metric weighting."""
     from . import ops
     from .device import as_device_tensor, result_like
 
+    if grid._face_connections is not None:
+        return _apply_connected_stencil(
+            op, da, da if raw_arg is None else raw_arg, other_component, grid, ax_name, in_dim,
+            out_dim, padding_width_real, padding, fill_value, pre_metric, post_metric_fn,
+        )
     lo, hi = padding_width_real.get(ax_name, (0, 0))
     paddings = grid._complete_user_kwargs_using_axis_defaults(padding, "padding")
     fills = grid._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
@@ -534,8 +574,6 @@ def _apply_fused_stencil(op, da, grid, ax_name, in_dim, out_dim, padding_width_r
         )
     if isinstance(ax_padding, Mapping):
         raise NotImplementedError("fold padding is outside the scope of xgcm_b200")
-    if grid._face_connections is not None:
-        raise NotImplementedError("face connections are outside the scope of xgcm_b200")
     axis_num = da.get_axis_num(in_dim)
     out_dims = tuple(out_dim if d == in_dim else d for d in da.dims)
     out_shape = list(da.shape)

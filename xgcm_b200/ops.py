@@ -204,6 +204,42 @@ def pad(x: torch.Tensor, axis: int, lo: int, hi: int, padding: Optional[str],
     return out
 
 
+def strided_copy(dst: torch.Tensor, dst_offset: int, dst_strides: Sequence[int],
+                 src: torch.Tensor, src_offset: int, src_strides: Sequence[int],
+                 shape: Sequence[int], negate: bool = False) -> None:
+    """``dst.flat[dst_offset + i . dst_strides] = +-src.flat[src_offset + i . src_strides]`` for all
+    index tuples ``i`` in ``shape`` (xg_strided_copy).  Offsets and strides are in elements of the
+    contiguous base tensors; source strides may be negative (flips) or permuted (dim swaps), which
+    is how one connected face edge is written (padding.py:414-541)."""
+    lib = _capi.load()
+    _require_cuda(dst, "dst")
+    _require_cuda(src, "src")
+    if dst.dtype != src.dtype:
+        raise TypeError(f"strided_copy: dtype mismatch {dst.dtype} vs {src.dtype}")
+    if not (dst.is_contiguous() and src.is_contiguous()):
+        raise ValueError("strided_copy: base tensors must be contiguous")
+    shape = [int(v) for v in shape]
+    if len(shape) != len(dst_strides) or len(shape) != len(src_strides):
+        raise ValueError("strided_copy: shape / strides rank mismatch")
+    if any(v == 0 for v in shape):
+        return
+    # bounds of both index maps (the kernel trusts them)
+    for name, t, off, strides in (("dst", dst, dst_offset, dst_strides), ("src", src, src_offset, src_strides)):
+        lo = off + sum(min(0, (n - 1) * int(st)) for n, st in zip(shape, strides))
+        hi = off + sum(max(0, (n - 1) * int(st)) for n, st in zip(shape, strides))
+        if lo < 0 or hi >= t.numel():
+            raise IndexError(f"strided_copy: {name} index map leaves the tensor ([{lo}, {hi}] of {t.numel()})")
+    es = dst.element_size()
+    with torch.cuda.device(dst.device):
+        rc = lib.xg_strided_copy(_dtype_code(dst), dst.data_ptr() + int(dst_offset) * es,
+                                 _capi.i64_array([int(v) for v in dst_strides]),
+                                 src.data_ptr() + int(src_offset) * es,
+                                 _capi.i64_array([int(v) for v in src_strides]),
+                                 len(shape), _capi.i64_array(shape), 1 if negate else 0,
+                                 _stream_ptr(dst))
+    _capi.check(rc)
+
+
 def binary(opname: str, a: torch.Tensor, b: torch.Tensor, shape: Optional[Sequence[int]] = None) -> torch.Tensor:
     """``a (op) b`` with numpy-style broadcasting, on the device (xg_binary).
 

@@ -1,9 +1,17 @@
 """``pad``: halo padding of labelled arrays (reference ``xgcm/padding.py:765-871``).
 
-The built-in operators never call this (their halo is fused into the stencil
-kernel); it exists for user-defined grid ufuncs and for API parity.  The copy
-runs on the device in ``xg_pad``.  Face-connection and north-fold padding
-(padding.py:230-572, :21-181) are out of scope.
+On simply connected grids the built-in operators never call this (their halo
+is fused into the stencil kernel); it exists for user-defined grid ufuncs and
+for API parity, and the copy runs on the device in ``xg_pad``.
+
+On grids with ``face_connections`` (cubed sphere, LLC tiles) every operator
+pads through ``_pad_face_connections`` (reference padding.py:260-572): faces
+are pre-padded with the ordinary boundary condition, then the halo of every
+connected edge is overwritten with the neighbour face's rim — sliced, swapped,
+flipped and sign-flipped as the connection demands.  Each of those edge
+transfers is one ``xg_strided_copy`` launch whose signed strides encode the
+whole index map.  North-fold padding (padding.py:21-181, :619-762) is out of
+scope.
 """
 
 from __future__ import annotations
@@ -55,6 +63,240 @@ def _pad_basic(da: DataArray, grid, padding_width, padding, fill_value):
     return out
 
 
+def _get_all_connection_axes(connections, facedim):
+    all_axes = []
+    for c in connections[facedim].values():
+        all_axes.extend(list(c.keys()))
+    return list(dict.fromkeys(all_axes))
+
+
+def _infer_vector_component_axis(grid, da) -> str:
+    """The axis a bare vector component is aligned with: the only axis on which it is not at
+    the cell centre (padding.py:230-257)."""
+    edge_axes = []
+    for axname, axis in grid.axes.items():
+        try:
+            position, _ = axis._get_position_name(da)
+        except KeyError:
+            continue
+        if position != "center":
+            edge_axes.append(axname)
+    if len(edge_axes) == 1:
+        return edge_axes[0]
+    raise ValueError(
+        "Could not unambiguously infer the axis of the vector component being "
+        f"padded from its staggered position (edge axes found: {edge_axes}). "
+        "Pass the component as a `{axis_name: DataArray}` dict so its "
+        "orientation is explicit, e.g. "
+        "`pad({'Y': v}, ..., other_component={'X': u})`."
+    )
+
+
+def _contiguous_strides(shape):
+    strides, acc = [], 1
+    for n in reversed(shape):
+        strides.append(acc)
+        acc *= int(n)
+    return list(reversed(strides))
+
+
+def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_component=None):
+    """Padding across face connections (padding.py:260-572), on the device.
+
+    Same steps as the reference: (1) pad every face on every connection axis to the largest
+    requested width with the ordinary boundary condition, (2) overwrite the halo of each
+    CONNECTED edge with the neighbour's rim, always read from the pre-padded arrays, (3) trim
+    back to the requested widths.  Step 2 is one ``xg_strided_copy`` per edge.
+
+    The reference visits the axes in ``set`` order (hash-seed dependent, padding.py:307-309);
+    only halo corners depend on it.  Here the order is that of ``grid.axes``.
+    """
+    from . import ops
+    from .device import as_device_tensor, result_like
+
+    facedim = grid._facedim
+    connections = grid._face_connections
+    if connections is None:
+        raise ValueError("Grid connections cannot be None")
+    if facedim is None:
+        raise ValueError("Face dimension cannot be None")
+
+    if isinstance(da, dict):
+        isvector = True
+        da = dict(da)
+        vectoraxis, da = da.popitem()
+    elif other_component is not None:
+        isvector = True
+        vectoraxis = _infer_vector_component_axis(grid, da)
+    else:
+        isvector = False
+        vectoraxis = None
+    da_partner = None
+    if isvector:
+        if other_component is not None:
+            _, da_partner = dict(other_component).popitem()
+            da_partner = _strip_all_coords(da_partner)
+        else:
+            raise ValueError("Padding vector components requires `other_component` input.")
+
+    wanted = set(_get_all_connection_axes(connections, facedim)) | set(padding_width.keys())
+    pad_axes = [ax for ax in grid.axes if ax in wanted] + [ax for ax in wanted if ax not in grid.axes]
+    padding_width = {ax: tuple(padding_width.get(ax, (0, 0))) for ax in pad_axes}
+    width = max(max(w) for w in padding_width.values())
+    max_padding_width = {ax: (width, width) for ax in pad_axes}
+
+    n_facedim = da.sizes[facedim]
+    face_links = connections[facedim]
+    prepad_padding = dict(padding)
+    for axname in pad_axes:
+        if prepad_padding.get(axname) is not None:
+            continue
+        for side, side_name in [(0, "left"), (1, "right")]:
+            if padding_width[axname][side] == 0:
+                continue
+            unconnected_faces = [
+                i for i in range(n_facedim)
+                if face_links.get(i, {}).get(axname, (None, None))[side] is None
+            ]
+            if unconnected_faces:
+                raise ValueError(
+                    f"No boundary condition was specified for axis {axname!r}, "
+                    f"but the requested operation needs to pad the {side_name} "
+                    f"edge of face(s) {unconnected_faces}, which have no face "
+                    f"connection there. Set a boundary condition, e.g. "
+                    f"``padding='fill'`` (or 'extend'/'periodic'), on the Grid "
+                    f"(``Grid(..., padding=...)``) or pass ``padding=`` to the "
+                    f"grid method."
+                )
+        # every padded edge of this axis is connected: its pre-padded halo is a placeholder
+        prepad_padding[axname] = "fill"
+
+    prepadded = _pad_basic(da, grid, max_padding_width, prepad_padding, fill_value)
+    p, was_host = as_device_tensor(prepadded.data, grid._device_for(prepadded))
+    p_dims = tuple(prepadded.dims)
+    p_shape = [int(v) for v in p.shape]
+    p_strides = _contiguous_strides(p_shape)
+    sources = {"self": (p, p_dims, p_shape, p_strides)}
+    if isvector:
+        partner = _pad_basic(da_partner, grid, max_padding_width, prepad_padding, fill_value)
+        q, _ = as_device_tensor(partner.data, p.device)
+        if q.dtype != p.dtype:
+            q = q.to(p.dtype)
+        q_shape = [int(v) for v in q.shape]
+        sources["partner"] = (q, tuple(partner.dims), q_shape, _contiguous_strides(q_shape))
+
+    out = p.clone()
+    face_pos = p_dims.index(facedim)
+
+    def axis_dim(dims, axname):
+        for d in grid.axes[axname].coords.values():
+            if d in dims:
+                return d
+        raise KeyError(f"None of the DataArray's dims {dims} were found in axis coords.")
+
+    def source_dim_for(target_dim, s_dims):
+        """The source dim a target dim reads from: same name, else the source's dim on the same
+        grid axis (padding.py:183-198 renames the partner component's dims this way)."""
+        if target_dim in s_dims:
+            return target_dim
+        for axname in grid.axes:
+            positions = list(grid.axes[axname].coords.values())
+            if target_dim in positions:
+                for d in positions:
+                    if d in s_dims:
+                        return d
+        raise ValueError(f"cannot match dimension {target_dim!r} against the source dims {s_dims}")
+
+    if width > 0:
+        for i in range(n_facedim):
+            connection_single = face_links.get(i, {})
+            for axname in pad_axes:
+                left_connection, right_connection = connection_single.get(axname, (None, None))
+                target_dim = axis_dim(p_dims, axname)
+                for connection, is_right in [(left_connection, False), (right_connection, True)]:
+                    if not connection:
+                        continue
+                    source_face, source_axis, reverse = connection
+                    swap_axis = axname != source_axis
+                    key = "partner" if (isvector and swap_axis) else "self"
+                    s, s_dims, s_shape, s_strides = sources[key]
+                    # positional face index like the reference's isel
+                    if source_face < 0 or source_face >= s_shape[s_dims.index(facedim)]:
+                        raise IndexError(f"face {source_face} is not a valid index for {facedim!r}")
+
+                    loop_dims = [d for d in p_dims if d != facedim]
+                    shape = [width if d == target_dim else p_shape[p_dims.index(d)] for d in loop_dims]
+                    dst_strides = [p_strides[p_dims.index(d)] for d in loop_dims]
+                    t_len = p_shape[p_dims.index(target_dim)]
+                    dst_offset = i * p_strides[face_pos]
+                    if is_right:
+                        dst_offset += (t_len - width) * p_strides[p_dims.index(target_dim)]
+
+                    src_offset = source_face * s_strides[s_dims.index(facedim)]
+                    src_strides = []
+                    if swap_axis:
+                        cross_dim = axis_dim(p_dims, source_axis)  # target dim along the seam
+                        s_sliced = source_dim_for(cross_dim, s_dims)  # source dim along source_axis
+                        s_along = source_dim_for(target_dim, s_dims)  # source dim along axname
+                    else:
+                        cross_dim = None
+                        s_sliced = source_dim_for(target_dim, s_dims)
+                        s_along = None
+                    s_len = s_shape[s_dims.index(s_sliced)]
+                    if is_right:  # padding.py:443-459
+                        s0 = s_len - 2 * width if reverse else width
+                    else:
+                        s0 = width if reverse else s_len - 2 * width
+                    for d, n in zip(loop_dims, shape):
+                        if d == target_dim:
+                            st = s_strides[s_dims.index(s_sliced)]
+                            if reverse:  # flip across the seam (padding.py:478-487)
+                                src_offset += (s0 + width - 1) * st
+                                src_strides.append(-st)
+                            else:
+                                src_offset += s0 * st
+                                src_strides.append(st)
+                        elif swap_axis and d == cross_dim:
+                            st = s_strides[s_dims.index(s_along)]
+                            if s_shape[s_dims.index(s_along)] != n:
+                                raise ValueError(
+                                    "a face connection that swaps axes needs faces of equal size along "
+                                    f"{axname!r} and {source_axis!r}"
+                                )
+                            if reverse:
+                                src_strides.append(st)
+                            else:  # flip along the seam (padding.py:489-498)
+                                src_offset += (n - 1) * st
+                                src_strides.append(-st)
+                        else:
+                            sd = source_dim_for(d, s_dims)
+                            if s_shape[s_dims.index(sd)] != n:
+                                raise ValueError(f"dimension {d!r} differs between connected arrays")
+                            src_strides.append(s_strides[s_dims.index(sd)])
+                    negate = isvector and (
+                        (reverse and vectoraxis == axname)
+                        or (swap_axis and not reverse and vectoraxis != axname)
+                    )
+                    ops.strided_copy(out, dst_offset, dst_strides, s, src_offset, src_strides, shape, negate)
+
+    # trim back to the requested widths (padding.py:557-572)
+    starts, final_shape = [], []
+    for d, n in zip(p_dims, p_shape):
+        lo_cut = hi_cut = 0
+        for axname in pad_axes:
+            if d in grid.axes[axname].coords.values():
+                lo_cut = width - padding_width[axname][0]
+                hi_cut = width - padding_width[axname][1]
+        starts.append(lo_cut)
+        final_shape.append(n - lo_cut - hi_cut)
+    if any(starts) or final_shape != p_shape:
+        trimmed = out.new_empty(final_shape)
+        offset = sum(st * k for st, k in zip(p_strides, starts))
+        ops.strided_copy(trimmed, 0, _contiguous_strides(final_shape), out, offset, p_strides, final_shape)
+        out = trimmed
+    return DataArray(result_like(out, was_host), dims=p_dims, name=prepadded.name, attrs=prepadded.attrs)
+
+
 def pad(
     data: Union[DataArray, Dict[str, DataArray]],
     grid,
@@ -82,7 +324,9 @@ def pad(
 
     data = _strip_all_coords(data)
     if grid._face_connections is not None:
-        raise NotImplementedError("face-connection padding is outside the scope of xgcm_b200")
+        return _pad_face_connections(
+            data, grid, padding_width, padding, fill_value, other_component=other_component
+        )
     if isinstance(data, dict):
         [data] = list(data.values())
     return _pad_basic(data, grid, padding_width, padding, fill_value)
