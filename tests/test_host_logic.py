@@ -94,7 +94,7 @@ def test_grid_kwargs_precedence_and_repr():
         xg.Grid(np.zeros(3), coords={})
     with pytest.warns(DeprecationWarning):
         xg.Grid(ds, coords={"X": {"center": "xc"}}, fill_value=1.0)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError, match="Face dimension face does not exist"):
         xg.Grid(ds, coords={"X": {"center": "xc"}}, face_connections={"face": {}})
     with pytest.raises(KeyError):
         grid.set_metrics(("Q",), "xc")
