@@ -48,6 +48,20 @@ def install(monkeypatch):
                  halo_hi=None, out=None):
         if (lo or hi) and padding is None:
             raise ValueError("no boundary condition was specified")
+        if halo_lo is not None or halo_hi is not None:
+            # explicit halo planes replace the boundary condition on their side (xgcm_b200.h:109-112)
+            a = _np(x) if pre is None else _np(x) * _np(pre)
+            padded = oracle.pad_axis(a, axis, lo if halo_lo is None else 0, hi if halo_hi is None else 0,
+                                     padding, fill_value)
+            parts = ([_np(halo_lo).reshape([1 if d == axis % a.ndim else n for d, n in enumerate(a.shape)])]
+                     if halo_lo is not None and lo else []) + [padded] + (
+                [_np(halo_hi).reshape([1 if d == axis % a.ndim else n for d, n in enumerate(a.shape)])]
+                if halo_hi is not None and hi else [])
+            padded = np.concatenate(parts, axis=axis)
+            r = np.moveaxis(oracle.KERNELS[op](np.moveaxis(padded, axis, -1)), -1, axis)
+            if post is not None:
+                r = r / _np(post)
+            return _t(r.astype(_np(x).dtype))
         r = oracle.stencil2(op, _np(x), axis, lo, hi, padding if (lo or hi) else None, fill_value,
                             _np(pre), _np(post))
         return _t(r.astype(_np(x).dtype))

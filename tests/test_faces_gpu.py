@@ -291,3 +291,58 @@ def test_multi_axis_on_connected_grid_goes_axis_by_axis():
     both = grid.interp(ds["data_c"], ["X", "Y"])
     chained = grid.interp(grid.interp(ds["data_c"], "X"), "Y")
     np.testing.assert_array_equal(both.values, chained.values)
+
+
+def test_metric_weighted_and_derivative_on_connected_grid():
+    """metric_weighted multiplies BEFORE the (face-connected) halo is taken and divides after
+    (grid.py:806-808,830-832); derivative divides the difference by the metric at the new
+    position (grid.py:1576-1578)."""
+    from oracle import stencil as so
+
+    ds = _ds(6)
+    rng = np.random.default_rng(7)
+    dx_c = 1.0 + rng.random((6, N, N))
+    dx_l = 1.0 + rng.random((6, N, N))
+    ds2 = xg.Dataset(
+        data_vars={"data_c": (("face", "y", "x"), ds["data_c"].values)},
+        coords={"x": ds["x"].values, "xl": ds["xl"].values, "y": ds["y"].values, "yl": ds["yl"].values,
+                "face": np.arange(6), "dx_c": (("face", "y", "x"), dx_c), "dx_l": (("face", "y", "xl"), dx_l)},
+    )
+    grid = xg.Grid(ds2, coords=COORDS, face_connections=CUBED_SPHERE, metrics={("X",): ["dx_c", "dx_l"]})
+    d = ds2["data_c"]
+    out = grid.interp(d, "X", metric_weighted="X")
+    weighted = xg.DataArray(d.values * dx_c, dims=d.dims)
+    padded = _oracle(weighted, CUBED_SPHERE, {"X": (1, 0)}, None, 0.0)
+    np.testing.assert_array_equal(out.values, so.interp_forward(padded) / dx_l)
+    der = grid.derivative(d, "X")
+    padded = _oracle(d, CUBED_SPHERE, {"X": (1, 0)}, None, 0.0)
+    np.testing.assert_array_equal(der.values, so.diff_forward(padded) / dx_l)
+
+
+@pytest.mark.parametrize("padding", ["fill", "extend", "periodic"])
+@pytest.mark.parametrize("fc", [X_TO_X, X_TO_X_REV, X_TO_Y, X_TO_Y_REV], ids=["xx", "xx_rev", "xy", "xy_rev"])
+def test_operator_halo_planes_match_padded_oracle(fc, padding):
+    """The operator fast path (halo planes gathered from the neighbours, fused kernel) against
+    oracle pad + pairwise kernel: lower halo (center -> left) and upper halo (left -> center),
+    scalars and vector components, every basic padding on the unconnected edges."""
+    from oracle import stencil as so
+
+    ds = _ds()
+    grid = xg.Grid(ds, coords=COORDS, face_connections=fc)
+    d, u, v = ds["data_c"], ds["u"], ds["v"]
+    for ax, dim in (("X", "x"), ("Y", "y")):
+        out = grid.diff(d, ax, padding=padding, fill_value=2.5)
+        padded = _oracle(d, fc, {ax: (1, 0)}, padding, 2.5)
+        k = d.dims.index(dim)
+        np.testing.assert_array_equal(
+            out.values, np.moveaxis(so.diff_forward(np.moveaxis(padded, k, -1)), -1, k))
+    out = grid.interp({"X": u}, "X", other_component={"Y": v}, padding=padding, fill_value=2.5)
+    padded = _oracle(u, fc, {"X": (0, 1)}, padding, 2.5, "X", v)
+    k = u.dims.index("xl")
+    np.testing.assert_array_equal(
+        out.values, np.moveaxis(so.interp_forward(np.moveaxis(padded, k, -1)), -1, k))
+    out = grid.interp({"Y": v}, "Y", other_component={"X": u}, padding=padding, fill_value=2.5)
+    padded = _oracle(v, fc, {"Y": (0, 1)}, padding, 2.5, "Y", u)
+    k = v.dims.index("yl")
+    np.testing.assert_array_equal(
+        out.values, np.moveaxis(so.interp_forward(np.moveaxis(padded, k, -1)), -1, k))

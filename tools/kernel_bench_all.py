@@ -93,6 +93,35 @@ def main():
     del theta3
     report("pad X periodic (1,1)", timeit(lambda: ops.pad(x, 2, 1, 1, "periodic")), 2 * cells * es)
     report("binary mul x * dx(Y,X)", timeit(lambda: ops.binary("mul", x, dx)), 2 * cells * es)
+    # ---- face connections: cubed sphere, 6 faces x 50 levels x 1020^2 ----------
+    import xgcm_b200 as xg
+
+    del x
+    torch.cuda.empty_cache()
+    nz, nf, n = (10, 6, 510) if args.small else (50, 6, 1020)
+    cs = {
+        "face": {
+            0: {"X": ((3, "X", False), (1, "X", False)), "Y": ((4, "Y", False), (5, "Y", False))},
+            1: {"X": ((0, "X", False), (2, "X", False)), "Y": ((4, "X", False), (5, "X", True))},
+            2: {"X": ((1, "X", False), (3, "X", False)), "Y": ((4, "Y", True), (5, "Y", True))},
+            3: {"X": ((2, "X", False), (0, "X", False)), "Y": ((4, "X", True), (5, "X", False))},
+            4: {"X": ((3, "Y", True), (1, "Y", False)), "Y": ((2, "Y", True), (0, "Y", False))},
+            5: {"X": ((3, "Y", False), (1, "Y", True)), "Y": ((0, "Y", False), (2, "Y", True))},
+        }
+    }
+    f = torch.empty((nz, nf, n, n), dtype=dt, device="cuda")
+    ops.fill_uniform(f, 3)
+    fcells = f.numel()
+    ds = xg.Dataset(coords={"z": np.arange(nz), "face": np.arange(nf), "y": np.arange(n), "yl": np.arange(n) - 0.5,
+                            "x": np.arange(n), "xl": np.arange(n) - 0.5})
+    grid = xg.Grid(ds, coords={"X": {"center": "x", "left": "xl"}, "Y": {"center": "y", "left": "yl"}},
+                   face_connections=cs)
+    da = xg.DataArray(f, dims=("z", "face", "y", "x"))
+    report("cubed sphere Grid.diff X (halo planes + fused stencil)", timeit(lambda: grid.diff(da, "X"), iters=6), 2 * fcells * es)
+    report("cubed sphere Grid.interp Y (halo planes + fused stencil)", timeit(lambda: grid.interp(da, "Y"), iters=6), 2 * fcells * es)
+    from xgcm_b200.padding import pad as xpad
+
+    report("cubed sphere pad X,Y (1,1) materialised", timeit(lambda: xpad(da, grid, {"X": (1, 1), "Y": (1, 1)}), iters=4), 2 * fcells * es)
     out_path = os.path.join("gpurun_out", "kernel_bench_all.json")
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump([dict(name=r[0], ms=r[1], GBps=r[2], frac_of_measured_peak=r[3]) for r in rows], open(out_path, "w"), indent=1)

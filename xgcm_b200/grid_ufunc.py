@@ -525,6 +525,21 @@ def _apply_connected_stencil(op, da, raw_arg, other_component, grid, ax_name, in
     from .padding import pad
 
     lo, hi = padding_width_real.get(ax_name, (0, 0))
+    if pre_metric is None and lo <= 1 and hi <= 1:
+        # halo planes gathered from the neighbour faces, then the ordinary fused launch
+        from .padding import connected_halo_planes
+
+        x, halo_lo, halo_hi, was_host, dims = connected_halo_planes(
+            raw_arg, grid, ax_name, lo, hi, padding, fill_value, other_component)
+        axis_num = dims.index(in_dim)
+        out_dims = tuple(out_dim if d == in_dim else d for d in dims)
+        out_shape = list(x.shape)
+        out_shape[axis_num] = x.shape[axis_num] + lo + hi - 1
+        post_da = post_metric_fn(_ShapeProbe(out_dims, out_shape)) if post_metric_fn is not None else None
+        post_t = grid._metric_tensor(post_da, out_dims, x) if post_da is not None else None
+        out = ops.stencil2(x, axis_num, op, lo, hi, "fill" if (lo or hi) else None, 0.0,
+                           post=post_t, halo_lo=halo_lo, halo_hi=halo_hi)
+        return DataArray(result_like(out, was_host), dims=out_dims, name=da.name, attrs=da.attrs)
     if pre_metric is not None:
         if isinstance(raw_arg, dict):
             raise NotImplementedError(

@@ -100,6 +100,191 @@ def _contiguous_strides(shape):
     return list(reversed(strides))
 
 
+def _axis_dim(grid, dims, axname):
+    for d in grid.axes[axname].coords.values():
+        if d in dims:
+            return d
+    raise KeyError(f"None of the DataArray's dims {dims} were found in axis coords.")
+
+
+def _source_dim_for(grid, target_dim, s_dims):
+    """The source dim a target dim reads from: same name, else the source's dim on the same grid
+    axis (padding.py:183-198 renames the partner component's dims this way)."""
+    if target_dim in s_dims:
+        return target_dim
+    for axname in grid.axes:
+        positions = list(grid.axes[axname].coords.values())
+        if target_dim in positions:
+            for d in positions:
+                if d in s_dims:
+                    return d
+    raise ValueError(f"cannot match dimension {target_dim!r} against the source dims {s_dims}")
+
+
+def _copy_connected_edge(grid, facedim, dst, d_dims, d_shape, face, axname, d_start, width, prepad,
+                         connection, is_right, sources, isvector, vectoraxis):
+    """Write the ``width`` halo cells of one connected edge of ``face`` into ``dst`` (dims
+    ``d_dims``, starting at index ``d_start`` along the dim of ``axname``) from the neighbour
+    named by ``connection`` (padding.py:414-541) with ONE ``xg_strided_copy``.
+
+    ``sources``: {"self": (tensor, dims, shape, strides), "partner": ...}; the source arrays carry
+    ``prepad`` halo cells on the sliced dim (the reference slices pre-padded arrays; the operator
+    fast path reads the bare field, prepad = 0).  Every dim of ``dst`` other than the face dim and
+    the padded one is copied over its full extent, which must match the source's.
+    """
+    from . import ops
+
+    source_face, source_axis, reverse = connection
+    swap_axis = axname != source_axis
+    s, s_dims, s_shape, s_strides = sources["partner" if (isvector and swap_axis) else "self"]
+    # positional face index like the reference's isel
+    if source_face < 0 or source_face >= s_shape[s_dims.index(facedim)]:
+        raise IndexError(f"face {source_face} is not a valid index for {facedim!r}")
+    d_strides = _contiguous_strides(d_shape)
+    target_dim = _axis_dim(grid, d_dims, axname)
+    loop_dims = [d for d in d_dims if d != facedim]
+    shape = [width if d == target_dim else d_shape[d_dims.index(d)] for d in loop_dims]
+    dst_strides = [d_strides[d_dims.index(d)] for d in loop_dims]
+    dst_offset = face * d_strides[d_dims.index(facedim)] + d_start * d_strides[d_dims.index(target_dim)]
+
+    src_offset = source_face * s_strides[s_dims.index(facedim)]
+    src_strides = []
+    if swap_axis:
+        cross_dim = _axis_dim(grid, d_dims, source_axis)        # target dim along the seam
+        s_sliced = _source_dim_for(grid, cross_dim, s_dims)    # source dim along source_axis
+        s_along = _source_dim_for(grid, target_dim, s_dims)    # source dim along axname
+    else:
+        cross_dim = None
+        s_sliced = _source_dim_for(grid, target_dim, s_dims)
+        s_along = None
+    s_len = s_shape[s_dims.index(s_sliced)]
+    if is_right:  # padding.py:443-459: the neighbour's first cells, or its last ones if reversed
+        s0 = s_len - prepad - width if reverse else prepad
+    else:
+        s0 = prepad if reverse else s_len - prepad - width
+    for d, n in zip(loop_dims, shape):
+        if d == target_dim:
+            st = s_strides[s_dims.index(s_sliced)]
+            if reverse:  # flip across the seam (padding.py:478-487)
+                src_offset += (s0 + width - 1) * st
+                src_strides.append(-st)
+            else:
+                src_offset += s0 * st
+                src_strides.append(st)
+        elif swap_axis and d == cross_dim:
+            st = s_strides[s_dims.index(s_along)]
+            if s_shape[s_dims.index(s_along)] != n:
+                raise ValueError(
+                    "a face connection that swaps axes needs faces of equal size along "
+                    f"{axname!r} and {source_axis!r}"
+                )
+            if reverse:
+                src_strides.append(st)
+            else:  # flip along the seam (padding.py:489-498)
+                src_offset += (n - 1) * st
+                src_strides.append(-st)
+        else:
+            sd = _source_dim_for(grid, d, s_dims)
+            if s_shape[s_dims.index(sd)] != n:
+                raise ValueError(f"dimension {d!r} differs between connected arrays")
+            src_strides.append(s_strides[s_dims.index(sd)])
+    negate = isvector and (
+        (reverse and vectoraxis == axname) or (swap_axis and not reverse and vectoraxis != axname)
+    )
+    ops.strided_copy(dst, dst_offset, dst_strides, s, src_offset, src_strides, shape, negate)
+
+
+def _unpack_vector(grid, da, other_component):
+    """(field, is vector, its axis, partner component) — padding.py:277-303."""
+    if isinstance(da, dict):
+        vectoraxis, da = dict(da).popitem()
+        isvector = True
+    elif other_component is not None:
+        isvector = True
+        vectoraxis = _infer_vector_component_axis(grid, da)
+    else:
+        return da, False, None, None
+    if other_component is None:
+        raise ValueError("Padding vector components requires `other_component` input.")
+    _, da_partner = dict(other_component).popitem()
+    return da, isvector, vectoraxis, da_partner
+
+
+def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_component=None):
+    """The one-cell halo planes of ``da`` along ``ax_name`` on a grid with face connections, for
+    the fused stencil kernel (``xg_stencil2`` takes them as ``halo_lo`` / ``halo_hi``).
+
+    Equals the first / last plane of ``pad(da, {ax_name: (lo, hi)})`` — basic boundary values on
+    unconnected edges, the neighbour's rim (rotated, flipped, sign-flipped) on connected ones —
+    without materialising the padded field: the planes are thin, so an operator on a connected
+    grid costs one read and one write of the field like on a simple one.  Returns
+    ``(field tensor, halo_lo or None, halo_hi or None, was_host, dims)``.
+    """
+    import torch
+
+    from . import ops
+    from .device import as_device_tensor
+
+    facedim = grid._facedim
+    face_links = grid._face_connections[facedim]
+    da, isvector, vectoraxis, da_partner = _unpack_vector(grid, da, other_component)
+    x, was_host = as_device_tensor(da.data, grid._device_for(da))
+    dims = tuple(da.dims)
+    shape = [int(v) for v in x.shape]
+    strides = _contiguous_strides(shape)
+    sources = {"self": (x, dims, shape, strides)}
+    if isvector:
+        q, _ = as_device_tensor(_strip_all_coords(da_partner).data, x.device)
+        if q.dtype != x.dtype:
+            q = q.to(x.dtype)
+        q_shape = [int(v) for v in q.shape]
+        sources["partner"] = (q, tuple(da_partner.dims), q_shape, _contiguous_strides(q_shape))
+    target_dim = _axis_dim(grid, dims, ax_name)
+    t = dims.index(target_dim)
+    n = shape[t]
+    n_face = shape[dims.index(facedim)]
+    paddings = grid._complete_user_kwargs_using_axis_defaults(padding, "padding")
+    fills = grid._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
+    ax_padding = paddings[ax_name]
+    planes = []
+    for side, w in ((0, lo), (1, hi)):
+        if not w:
+            planes.append(None)
+            continue
+        unconnected = [i for i in range(n_face)
+                       if face_links.get(i, {}).get(ax_name, (None, None))[side] is None]
+        if ax_padding is None and unconnected:
+            raise ValueError(
+                f"No boundary condition was specified for axis {ax_name!r}, "
+                f"but the requested operation needs to pad the {'right' if side else 'left'} "
+                f"edge of face(s) {unconnected}, which have no face "
+                f"connection there. Set a boundary condition, e.g. "
+                f"``padding='fill'`` (or 'extend'/'periodic'), on the Grid "
+                f"(``Grid(..., padding=...)``) or pass ``padding=`` to the "
+                f"grid method."
+            )
+        p_shape = list(shape)
+        p_shape[t] = 1
+        mode = ax_padding if ax_padding is not None else "fill"
+        if mode == "fill":
+            fv = fills[ax_name] if fills[ax_name] is not None else 0.0
+            plane = torch.full(p_shape, float(fv), dtype=x.dtype, device=x.device)
+        else:  # extend: nearest cell; periodic: the cell at the other end
+            plane = torch.empty(p_shape, dtype=x.dtype, device=x.device)
+            if mode == "extend":
+                row = (n - 1) if side else 0
+            else:
+                row = 0 if side else (n - 1)
+            ops.strided_copy(plane, 0, _contiguous_strides(p_shape), x, row * strides[t], strides, p_shape)
+        for i in range(n_face):
+            connection = face_links.get(i, {}).get(ax_name, (None, None))[side]
+            if connection:
+                _copy_connected_edge(grid, facedim, plane, dims, p_shape, i, ax_name, 0, 1, 0,
+                                     connection, bool(side), sources, isvector, vectoraxis)
+        planes.append(plane)
+    return x, planes[0], planes[1], was_host, dims
+
+
 def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_component=None):
     """Padding across face connections (padding.py:260-572), on the device.
 
@@ -121,23 +306,9 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
     if facedim is None:
         raise ValueError("Face dimension cannot be None")
 
-    if isinstance(da, dict):
-        isvector = True
-        da = dict(da)
-        vectoraxis, da = da.popitem()
-    elif other_component is not None:
-        isvector = True
-        vectoraxis = _infer_vector_component_axis(grid, da)
-    else:
-        isvector = False
-        vectoraxis = None
-    da_partner = None
+    da, isvector, vectoraxis, da_partner = _unpack_vector(grid, da, other_component)
     if isvector:
-        if other_component is not None:
-            _, da_partner = dict(other_component).popitem()
-            da_partner = _strip_all_coords(da_partner)
-        else:
-            raise ValueError("Padding vector components requires `other_component` input.")
+        da_partner = _strip_all_coords(da_partner)
 
     wanted = set(_get_all_connection_axes(connections, facedim)) | set(padding_width.keys())
     pad_axes = [ax for ax in grid.axes if ax in wanted] + [ax for ax in wanted if ax not in grid.axes]
@@ -188,96 +359,21 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
     out = p.clone()
     face_pos = p_dims.index(facedim)
 
-    def axis_dim(dims, axname):
-        for d in grid.axes[axname].coords.values():
-            if d in dims:
-                return d
-        raise KeyError(f"None of the DataArray's dims {dims} were found in axis coords.")
-
-    def source_dim_for(target_dim, s_dims):
-        """The source dim a target dim reads from: same name, else the source's dim on the same
-        grid axis (padding.py:183-198 renames the partner component's dims this way)."""
-        if target_dim in s_dims:
-            return target_dim
-        for axname in grid.axes:
-            positions = list(grid.axes[axname].coords.values())
-            if target_dim in positions:
-                for d in positions:
-                    if d in s_dims:
-                        return d
-        raise ValueError(f"cannot match dimension {target_dim!r} against the source dims {s_dims}")
-
     if width > 0:
         for i in range(n_facedim):
             connection_single = face_links.get(i, {})
             for axname in pad_axes:
                 left_connection, right_connection = connection_single.get(axname, (None, None))
-                target_dim = axis_dim(p_dims, axname)
+                target_dim = _axis_dim(grid, p_dims, axname)
+                t_len = p_shape[p_dims.index(target_dim)]
                 for connection, is_right in [(left_connection, False), (right_connection, True)]:
                     if not connection:
                         continue
-                    source_face, source_axis, reverse = connection
-                    swap_axis = axname != source_axis
-                    key = "partner" if (isvector and swap_axis) else "self"
-                    s, s_dims, s_shape, s_strides = sources[key]
-                    # positional face index like the reference's isel
-                    if source_face < 0 or source_face >= s_shape[s_dims.index(facedim)]:
-                        raise IndexError(f"face {source_face} is not a valid index for {facedim!r}")
-
-                    loop_dims = [d for d in p_dims if d != facedim]
-                    shape = [width if d == target_dim else p_shape[p_dims.index(d)] for d in loop_dims]
-                    dst_strides = [p_strides[p_dims.index(d)] for d in loop_dims]
-                    t_len = p_shape[p_dims.index(target_dim)]
-                    dst_offset = i * p_strides[face_pos]
-                    if is_right:
-                        dst_offset += (t_len - width) * p_strides[p_dims.index(target_dim)]
-
-                    src_offset = source_face * s_strides[s_dims.index(facedim)]
-                    src_strides = []
-                    if swap_axis:
-                        cross_dim = axis_dim(p_dims, source_axis)  # target dim along the seam
-                        s_sliced = source_dim_for(cross_dim, s_dims)  # source dim along source_axis
-                        s_along = source_dim_for(target_dim, s_dims)  # source dim along axname
-                    else:
-                        cross_dim = None
-                        s_sliced = source_dim_for(target_dim, s_dims)
-                        s_along = None
-                    s_len = s_shape[s_dims.index(s_sliced)]
-                    if is_right:  # padding.py:443-459
-                        s0 = s_len - 2 * width if reverse else width
-                    else:
-                        s0 = width if reverse else s_len - 2 * width
-                    for d, n in zip(loop_dims, shape):
-                        if d == target_dim:
-                            st = s_strides[s_dims.index(s_sliced)]
-                            if reverse:  # flip across the seam (padding.py:478-487)
-                                src_offset += (s0 + width - 1) * st
-                                src_strides.append(-st)
-                            else:
-                                src_offset += s0 * st
-                                src_strides.append(st)
-                        elif swap_axis and d == cross_dim:
-                            st = s_strides[s_dims.index(s_along)]
-                            if s_shape[s_dims.index(s_along)] != n:
-                                raise ValueError(
-                                    "a face connection that swaps axes needs faces of equal size along "
-                                    f"{axname!r} and {source_axis!r}"
-                                )
-                            if reverse:
-                                src_strides.append(st)
-                            else:  # flip along the seam (padding.py:489-498)
-                                src_offset += (n - 1) * st
-                                src_strides.append(-st)
-                        else:
-                            sd = source_dim_for(d, s_dims)
-                            if s_shape[s_dims.index(sd)] != n:
-                                raise ValueError(f"dimension {d!r} differs between connected arrays")
-                            src_strides.append(s_strides[s_dims.index(sd)])
-                    negate = isvector and (
-                        (reverse and vectoraxis == axname)
-                        or (swap_axis and not reverse and vectoraxis != axname)
+                    _copy_connected_edge(
+                        grid, facedim, out, p_dims, p_shape, i, axname,
+                        (t_len - width) if is_right else 0, width, width, connection, is_right,
+                        sources, isvector, vectoraxis,
                     )
-                    ops.strided_copy(out, dst_offset, dst_strides, s, src_offset, src_strides, shape, negate)
 
     # trim back to the requested widths (padding.py:557-572)
     starts, final_shape = [], []
