@@ -203,6 +203,16 @@ XG_API int xg_strided_copy(int dtype, void* dst, const int64_t* dst_strides, con
                     const int64_t* src_strides, int ndim, const int64_t* shape, int negate,
                     void* stream);
 
+/*
+ * `count` strided copies of the same rank in ONE launch (all connected edges of a field:
+ * padding.py:398-541 loops over faces x axes x sides).  dst[i] / src[i]: per-copy base pointers;
+ * shapes, dst_strides, src_strides: count x ndim, row-major; negate: count flags.  XG_ENOTIMPL if
+ * a copy does not collapse to 5 dims (callers then fall back to xg_strided_copy).
+ */
+XG_API int xg_strided_copy_batch(int dtype, int count, void* const* dst, const void* const* src,
+                          int ndim, const int64_t* shapes, const int64_t* dst_strides,
+                          const int64_t* src_strides, const int* negate, void* stream);
+
 /* Deterministic synthetic field: out[i] = U(0,1) keyed by (seed, offset+i);
  * identical bits on host (xg_fill_uniform_host) and device. */
 XG_API int xg_fill_uniform(int dtype, void* out, int64_t count, uint64_t seed,

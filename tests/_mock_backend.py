@@ -127,6 +127,7 @@ def install(monkeypatch):
         d[di] = -s[si] if negate else s[si]
 
     monkeypatch.setattr(ops, "strided_copy", strided_copy)
+    monkeypatch.setattr(ops, "strided_copy_batch", lambda copies: [strided_copy(*c) for c in copies] and None)
 
     for name, fn in dict(stencil2=stencil2, stencil2_host=stencil2_host, pad=pad, binary=binary,
                          cumscan=cumscan, wreduce=wreduce, vinterp_linear=vinterp_linear).items():

@@ -240,6 +240,55 @@ def strided_copy(dst: torch.Tensor, dst_offset: int, dst_strides: Sequence[int],
     _capi.check(rc)
 
 
+def strided_copy_batch(copies: Sequence[tuple]) -> None:
+    """Several :func:`strided_copy` calls — tuples ``(dst, dst_offset, dst_strides, src, src_offset,
+    src_strides, shape, negate)`` of one rank and dtype — in ONE launch (xg_strided_copy_batch):
+    all connected edges of a field at once.  Falls back to one launch per copy when an index map
+    does not collapse to 5 dims."""
+    import ctypes as C
+
+    copies = [c for c in copies if all(int(n) > 0 for n in c[6])]
+    if not copies:
+        return
+    if len(copies) == 1:
+        return strided_copy(*copies[0])
+    lib = _capi.load()
+    first = copies[0][0]
+    ndim = len(copies[0][6])
+    es = first.element_size()
+    dptr, sptr, shapes, dstr, sstr, neg, keep = [], [], [], [], [], [], []
+    for dst, doff, dstrides, src, soff, sstrides, shape, negate in copies:
+        _require_cuda(dst, "dst")
+        _require_cuda(src, "src")
+        if dst.dtype != first.dtype or src.dtype != first.dtype or dst.device != first.device:
+            raise TypeError("strided_copy_batch: all tensors must share dtype and device")
+        if not (dst.is_contiguous() and src.is_contiguous()) or len(shape) != ndim:
+            raise ValueError("strided_copy_batch: contiguous base tensors and one common rank are required")
+        for name, t, off, strides in (("dst", dst, doff, dstrides), ("src", src, soff, sstrides)):
+            lo = off + sum(min(0, (int(n) - 1) * int(st)) for n, st in zip(shape, strides))
+            hi = off + sum(max(0, (int(n) - 1) * int(st)) for n, st in zip(shape, strides))
+            if lo < 0 or hi >= t.numel():
+                raise IndexError(f"strided_copy_batch: {name} index map leaves the tensor ([{lo}, {hi}] of {t.numel()})")
+        dptr.append(dst.data_ptr() + int(doff) * es)
+        sptr.append(src.data_ptr() + int(soff) * es)
+        shapes += [int(v) for v in shape]
+        dstr += [int(v) for v in dstrides]
+        sstr += [int(v) for v in sstrides]
+        neg.append(1 if negate else 0)
+        keep += [dst, src]
+    n = len(copies)
+    with torch.cuda.device(first.device):
+        rc = lib.xg_strided_copy_batch(
+            _dtype_code(first), n, (C.c_void_p * n)(*dptr), (C.c_void_p * n)(*sptr), ndim,
+            _capi.i64_array(shapes), _capi.i64_array(dstr), _capi.i64_array(sstr), (C.c_int * n)(*neg),
+            _stream_ptr(first))
+    if rc == -2:  # XG_ENOTIMPL: an edge with more than 5 collapsed dims
+        for c in copies:
+            strided_copy(*c)
+        return
+    _capi.check(rc)
+
+
 def binary(opname: str, a: torch.Tensor, b: torch.Tensor, shape: Optional[Sequence[int]] = None) -> torch.Tensor:
     """``a (op) b`` with numpy-style broadcasting, on the device (xg_binary).
 

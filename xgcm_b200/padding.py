@@ -122,18 +122,17 @@ def _source_dim_for(grid, target_dim, s_dims):
 
 
 def _copy_connected_edge(grid, facedim, dst, d_dims, d_shape, face, axname, d_start, width, prepad,
-                         connection, is_right, sources, isvector, vectoraxis):
+                         connection, is_right, sources, isvector, vectoraxis, batch):
     """Write the ``width`` halo cells of one connected edge of ``face`` into ``dst`` (dims
     ``d_dims``, starting at index ``d_start`` along the dim of ``axname``) from the neighbour
-    named by ``connection`` (padding.py:414-541) with ONE ``xg_strided_copy``.
+    named by ``connection`` (padding.py:414-541): ONE strided copy, appended to ``batch`` (all edges
+    of a field go out in one ``xg_strided_copy_batch`` launch).
 
     ``sources``: {"self": (tensor, dims, shape, strides), "partner": ...}; the source arrays carry
     ``prepad`` halo cells on the sliced dim (the reference slices pre-padded arrays; the operator
     fast path reads the bare field, prepad = 0).  Every dim of ``dst`` other than the face dim and
     the padded one is copied over its full extent, which must match the source's.
     """
-    from . import ops
-
     source_face, source_axis, reverse = connection
     swap_axis = axname != source_axis
     s, s_dims, s_shape, s_strides = sources["partner" if (isvector and swap_axis) else "self"]
@@ -191,7 +190,7 @@ def _copy_connected_edge(grid, facedim, dst, d_dims, d_shape, face, axname, d_st
     negate = isvector and (
         (reverse and vectoraxis == axname) or (swap_axis and not reverse and vectoraxis != axname)
     )
-    ops.strided_copy(dst, dst_offset, dst_strides, s, src_offset, src_strides, shape, negate)
+    batch.append((dst, dst_offset, dst_strides, s, src_offset, src_strides, shape, negate))
 
 
 def _unpack_vector(grid, da, other_component):
@@ -246,7 +245,7 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
     paddings = grid._complete_user_kwargs_using_axis_defaults(padding, "padding")
     fills = grid._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
     ax_padding = paddings[ax_name]
-    planes = []
+    planes, batch = [], []
     for side, w in ((0, lo), (1, hi)):
         if not w:
             planes.append(None)
@@ -280,8 +279,9 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
             connection = face_links.get(i, {}).get(ax_name, (None, None))[side]
             if connection:
                 _copy_connected_edge(grid, facedim, plane, dims, p_shape, i, ax_name, 0, 1, 0,
-                                     connection, bool(side), sources, isvector, vectoraxis)
+                                     connection, bool(side), sources, isvector, vectoraxis, batch)
         planes.append(plane)
+    ops.strided_copy_batch(batch)  # both planes, every connected face: one launch
     return x, planes[0], planes[1], was_host, dims
 
 
@@ -359,6 +359,7 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
     out = p.clone()
     face_pos = p_dims.index(facedim)
 
+    by_axis = {}
     if width > 0:
         for i in range(n_facedim):
             connection_single = face_links.get(i, {})
@@ -372,8 +373,12 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
                     _copy_connected_edge(
                         grid, facedim, out, p_dims, p_shape, i, axname,
                         (t_len - width) if is_right else 0, width, width, connection, is_right,
-                        sources, isvector, vectoraxis,
+                        sources, isvector, vectoraxis, by_axis.setdefault(axname, []),
                     )
+    # Edges only read the pre-padded arrays and, halo corners aside, write disjoint cells; corner
+    # cells are written by both axes, so the axes go out in order (one launch each).
+    for axname in pad_axes:
+        ops.strided_copy_batch(by_axis.get(axname, []))
 
     # trim back to the requested widths (padding.py:557-572)
     starts, final_shape = [], []
