@@ -209,7 +209,8 @@ def _unpack_vector(grid, da, other_component):
     return da, isvector, vectoraxis, da_partner
 
 
-def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_component=None):
+def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_component=None,
+                          face_offset=0, remote_edges=None):
     """The one-cell halo planes of ``da`` along ``ax_name`` on a grid with face connections, for
     the fused stencil kernel (``xg_stencil2`` takes them as ``halo_lo`` / ``halo_hi``).
 
@@ -218,6 +219,11 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
     without materialising the padded field: the planes are thin, so an operator on a connected
     grid costs one read and one write of the field like on a simple one.  Returns
     ``(field tensor, halo_lo or None, halo_hi or None, was_host, dims)``.
+
+    ``face_offset`` / ``remote_edges``: ``da`` holds the contiguous block of faces that starts at
+    global face ``face_offset`` (faces sharded across GPUs, ``parallel.sharded_connected_stencil2``);
+    edges whose neighbour lives in another block are not filled here but appended to
+    ``remote_edges`` as ``(side, local face, connection)``.
     """
     import torch
 
@@ -250,8 +256,8 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
         if not w:
             planes.append(None)
             continue
-        unconnected = [i for i in range(n_face)
-                       if face_links.get(i, {}).get(ax_name, (None, None))[side] is None]
+        unconnected = [face_offset + i for i in range(n_face)
+                       if face_links.get(face_offset + i, {}).get(ax_name, (None, None))[side] is None]
         if ax_padding is None and unconnected:
             raise ValueError(
                 f"No boundary condition was specified for axis {ax_name!r}, "
@@ -276,10 +282,16 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
                 row = 0 if side else (n - 1)
             ops.strided_copy(plane, 0, _contiguous_strides(p_shape), x, row * strides[t], strides, p_shape)
         for i in range(n_face):
-            connection = face_links.get(i, {}).get(ax_name, (None, None))[side]
-            if connection:
-                _copy_connected_edge(grid, facedim, plane, dims, p_shape, i, ax_name, 0, 1, 0,
-                                     connection, bool(side), sources, isvector, vectoraxis, batch)
+            connection = face_links.get(face_offset + i, {}).get(ax_name, (None, None))[side]
+            if not connection:
+                continue
+            src_local = connection[0] - face_offset
+            if remote_edges is not None and not 0 <= src_local < n_face:
+                remote_edges.append((side, i, connection))
+                continue
+            _copy_connected_edge(grid, facedim, plane, dims, p_shape, i, ax_name, 0, 1, 0,
+                                 (src_local,) + tuple(connection[1:]), bool(side), sources, isvector,
+                                 vectoraxis, batch)
         planes.append(plane)
     ops.strided_copy_batch(batch)  # both planes, every connected face: one launch
     return x, planes[0], planes[1], was_host, dims

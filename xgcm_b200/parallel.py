@@ -12,6 +12,12 @@ sends ONE boundary plane to a neighbour and receives one (``exchange_halo``; NCC
 NVLink on GPUs, gloo on CPU for tests), and the received plane enters the fused stencil kernel
 through its ``halo_lo`` / ``halo_hi`` operands (``sharded_stencil2``).  Same restrictions as the
 reference: no ``inner`` / ``outer`` outputs (grid_ufunc.py:1136-1159), no cumsum (grid.py:813-816).
+
+Grids with ``face_connections`` (cubed sphere, LLC tiles) add a second natural decomposition: the
+FACES.  ``sharded_connected_stencil2`` gives every rank a contiguous block of faces; the one-cell
+rims that cross a block boundary — already rotated / flipped / sign-flipped by their owner with the
+same signed-stride copies the single-GPU path uses — travel in one NCCL group, everything else is
+the single-GPU fused stencil.
 """
 
 from __future__ import annotations
@@ -146,3 +152,96 @@ def sharded_stencil2(
     )
     return ops.stencil2(x_local, axis, op, lo, hi, padding, fill_value, pre=pre, post=post,
                         halo_lo=halo_lo, halo_hi=halo_hi)
+
+
+def sharded_connected_stencil2(grid, da_local, ax_name: str, op: str, lo: int, hi: int, padding=None,
+                               fill_value=None, other_component_local=None, post: Optional[torch.Tensor] = None,
+                               group=None) -> torch.Tensor:
+    """``diff / interp / min / max`` along ``ax_name`` of a field on a grid with face connections
+    whose FACES are split across the ranks of ``group``.
+
+    ``grid``: the GLOBAL topology (``Grid(ds, face_connections=...)`` — only dims and links are
+    used, so ``ds`` may hold coordinates only).  ``da_local`` (and ``other_component_local`` for a
+    vector component, as ``{axis: DataArray}`` like ``Grid.diff``): this rank's contiguous block of
+    faces, ``shard_bounds(n_faces, world, rank)`` along the face dim.  Returns the local block of
+    the result as a tensor.  Rims whose neighbour face lives on another rank are produced BY THE
+    OWNER of that face (slice / swap / flip / negate: ``padding._copy_connected_edge``) and sent
+    as thin contiguous slabs; sends and receives of all edges form one ``batch_isend_irecv``.
+    """
+    from . import ops
+    from . import padding as P
+
+    if lo > 1 or hi > 1 or lo + hi == 0:
+        raise NotImplementedError("face-sharded operators take one halo cell (center <-> left / right / outer)")
+    facedim = grid._facedim
+    if facedim is None:
+        raise ValueError("the grid has no face connections")
+    face_links = grid._face_connections[facedim]
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    n_global = grid._ds.sizes[facedim]
+    block = -(-n_global // world)
+    start, stop = shard_bounds(n_global, world, rank)
+    raw = da_local
+    field = P._unpack_vector(grid, raw, other_component_local)[0]
+    if field.sizes[facedim] != stop - start:
+        raise ValueError(
+            f"rank {rank} must hold faces [{start}, {stop}) along {facedim!r}, got {field.sizes[facedim]}"
+        )
+    remote: list = []
+    x, halo_lo, halo_hi, _, dims = P.connected_halo_planes(
+        raw, grid, ax_name, lo, hi, padding, fill_value, other_component_local,
+        face_offset=start, remote_edges=remote)
+    planes = (halo_lo, halo_hi)
+
+    # what this rank's faces owe to other ranks: the same enumeration on every rank (global face
+    # order, then side) so that sends and receives pair up
+    _, isvector, vectoraxis, partner = P._unpack_vector(grid, raw, other_component_local)
+    shape = [int(v) for v in x.shape]
+    sources = {"self": (x, dims, shape, P._contiguous_strides(shape))}
+    if isvector:
+        from .device import as_device_tensor
+
+        q, _ = as_device_tensor(P._strip_all_coords(partner).data, x.device)
+        q = q.to(x.dtype)
+        q_shape = [int(v) for v in q.shape]
+        sources["partner"] = (q, tuple(partner.dims), q_shape, P._contiguous_strides(q_shape))
+    fpos = dims.index(facedim)
+    tpos = dims.index(P._axis_dim(grid, dims, ax_name))
+    slab_shape = list(shape)
+    slab_shape[fpos] = 1
+    slab_shape[tpos] = 1
+    p2p, recvs, keep, batch = [], [], [], []
+    for f in range(n_global):
+        for side, w in ((0, lo), (1, hi)):
+            connection = face_links.get(f, {}).get(ax_name, (None, None))[side] if w else None
+            if not connection:
+                continue
+            owner_f, owner_s = f // block, connection[0] // block
+            if owner_f == owner_s:
+                continue
+            if owner_s == rank:  # I own the neighbour face: build the finished rim and send it
+                slab = torch.empty(slab_shape, dtype=x.dtype, device=x.device)
+                P._copy_connected_edge(grid, facedim, slab, dims, slab_shape, 0, ax_name, 0, 1, 0,
+                                       (connection[0] - start,) + tuple(connection[1:]), bool(side),
+                                       sources, isvector, vectoraxis, batch)
+                keep.append(slab)
+                p2p.append(dist.P2POp(dist.isend, slab, _global_rank(owner_f, group), group))
+            elif owner_f == rank:
+                buf = torch.empty(slab_shape, dtype=x.dtype, device=x.device)
+                recvs.append((side, f - start, buf))
+                p2p.append(dist.P2POp(dist.irecv, buf, _global_rank(owner_s, group), group))
+    ops.strided_copy_batch(batch)  # all outgoing rims: one launch, before they are sent
+    if p2p:
+        for req in dist.batch_isend_irecv(p2p):
+            req.wait()
+    assert sorted((s_, i_) for s_, i_, _ in recvs) == sorted((s_, i_) for s_, i_, _ in remote)
+    p_shape = list(shape)
+    p_shape[tpos] = 1
+    p_strides = P._contiguous_strides(p_shape)
+    s_strides = P._contiguous_strides(slab_shape)
+    ops.strided_copy_batch([
+        (planes[side], i * p_strides[fpos], p_strides, buf, 0, s_strides, slab_shape, False)
+        for side, i, buf in recvs
+    ])
+    return ops.stencil2(x, tpos, op, lo, hi, "fill", 0.0, post=post, halo_lo=halo_lo, halo_hi=halo_hi)
