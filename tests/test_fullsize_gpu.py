@@ -132,3 +132,30 @@ def test_cubed_sphere_full_size_operators():
         k = 3 if ax == "X" else 2
         want = np.moveaxis(oracle.KERNELS[op](np.moveaxis(padded, k, -1)), -1, k)
         np.testing.assert_array_equal(out.data[levels].cpu().numpy(), want.astype(np.float32))
+
+
+def test_config4_sampled_steps():
+    """BASELINE configs[3] (x365 time steps, time-sharded): the field of ANY global step is
+    regenerated on the device from the step index (tools/bench_c4.py uses the same generator), so
+    parity is checked on sampled steps — first, middle, last of the year — exactly as a rank that
+    owns them would compute them: Grid.diff / Grid.interp on X (periodic), Y (fill), Z (extend),
+    random full lines of every result against the oracle, bit for bit."""
+    import xgcm_b200 as xg
+    from xgcm_b200 import ops
+
+    shape = (75, 2400, 3600)
+    nz, ny, nx = shape
+    ds = xg.Dataset(coords={"Z": np.arange(nz) + 0.5, "Zl": np.arange(nz) + 0.0, "YC": np.arange(ny) + 0.5,
+                            "YG": np.arange(ny) + 0.0, "XC": np.arange(nx) + 0.5, "XG": np.arange(nx) + 0.0})
+    grid = xg.Grid(ds, coords={"X": {"center": "XC", "left": "XG"}, "Y": {"center": "YC", "left": "YG"},
+                               "Z": {"center": "Z", "left": "Zl"}},
+                   padding={"X": "periodic", "Y": "fill", "Z": "extend"}, autoparse_metadata=False)
+    x = torch.empty(shape, dtype=torch.float32, device=DEV)
+    da = xg.DataArray(x, dims=("Z", "YC", "XC"))
+    rng = np.random.default_rng(4)
+    for t in (0, 182, 364):
+        ops.fill_uniform(x, 0xC0FFEE, offset=t * x.numel())
+        for ax, k, bc in (("X", 2, "periodic"), ("Y", 1, "fill"), ("Z", 0, "extend")):
+            for op in ("diff", "interp"):
+                out = getattr(grid, op)(da, ax)
+                _check_axis_blocks(x, out.data, k, op, 1, 0, bc, 0.0, rng, nblocks=4)
