@@ -346,3 +346,29 @@ def test_operator_halo_planes_match_padded_oracle(fc, padding):
     k = v.dims.index("yl")
     np.testing.assert_array_equal(
         out.values, np.moveaxis(so.interp_forward(np.moveaxis(padded, k, -1)), -1, k))
+
+
+def test_cumsum_and_integrate_on_connected_grid():
+    """cumsum pads the CUMSUM'D data with ``pad`` (grid.py:1385-1391): on a connected grid the
+    boundary cell of a connected edge comes from the neighbour face's cumsum.  (Across an
+    axis-swapping seam the trimmed array is no longer square, in the reference as here: same-axis
+    seams only.)  integrate has no halo at all."""
+    from oracle import stencil as so
+
+    ds = _ds()
+    d = ds["data_c"]
+    for fc in (X_TO_X, X_TO_X_REV):
+        grid = xg.Grid(ds, coords=COORDS, face_connections=fc)
+        with pytest.raises(ValueError, match="No boundary condition was specified"):
+            grid.cumsum(d, "X", to="left")  # the outer edges are not connected
+        out = grid.cumsum(d, "X", to="left", padding="fill", fill_value=0.0)
+        assert out.dims == ("face", "y", "xl")
+        scanned = so.cumscan(d.values, 2, False, "drop_last", 0, 0, None)
+        expect = _oracle(xg.DataArray(scanned, dims=d.dims), fc, {"X": (1, 0)}, "fill", 0.0)
+        np.testing.assert_array_equal(out.values, expect)
+        u = ds["u"]  # left -> center along X: the natural landing position, no padding involved
+        np.testing.assert_array_equal(grid.cumsum(u, "X").values, so.cumscan(u.values, 1, False, "none", 0, 0, None))
+    ds6 = _ds(6)
+    grid6 = xg.Grid(ds6, coords=COORDS, face_connections=CUBED_SPHERE)
+    with pytest.raises(ValueError, match="equal size"):
+        grid6.cumsum(ds6["data_c"], "X", to="left")

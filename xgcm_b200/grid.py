@@ -664,7 +664,7 @@ class Grid:
                     f"shift for cumsum operation along axis {ax}."
                 )
             ax_padding = paddings[ax.name]
-            if (pad_lo or pad_hi) and ax_padding is None:
+            if (pad_lo or pad_hi) and ax_padding is None and self._face_connections is None:
                 raise ValueError(
                     f"No boundary condition was specified for axis {ax.name!r}, but the "
                     f"requested operation needs to pad it. Set a boundary condition, "
@@ -682,10 +682,22 @@ class Grid:
                 probe._dims = out_dims
                 post_t = self._metric_tensor(self.get_metric(probe, weighted), out_dims, data.data)
             fv = fills[ax.name] if fills[ax.name] is not None else 0.0
-            y = ops.cumscan(
-                data.data, axis_num, ax_reverse, trim, pad_lo, pad_hi,
-                ax_padding if (pad_lo or pad_hi) else None, fv, pre=pre_t, post=post_t, skipna=True,
-            )
+            if self._face_connections is not None and (pad_lo or pad_hi):
+                # the reference pads the cumsum'd data with ``pad`` (grid.py:1385-1391), which on a
+                # connected grid takes the halo from the neighbour face: scan + trim in the
+                # kernel, halo through the face-connection padding, metric divide last
+                y = ops.cumscan(data.data, axis_num, ax_reverse, trim, 0, 0, None, fv, pre=pre_t,
+                                post=None, skipna=True)
+                scanned = DataArray(y, dims=data.dims, name=da.name, attrs=da.attrs)
+                y = pad(scanned, grid=self, padding_width={ax.name: (pad_lo, pad_hi)}, padding=padding,
+                        fill_value=fill_value).data
+                if post_t is not None:
+                    y = ops.binary("div", y, post_t)
+            else:
+                y = ops.cumscan(
+                    data.data, axis_num, ax_reverse, trim, pad_lo, pad_hi,
+                    ax_padding if (pad_lo or pad_hi) else None, fv, pre=pre_t, post=post_t, skipna=True,
+                )
             coordless = DataArray(y, dims=out_dims, name=da.name, attrs=da.attrs)
             data = _reattach_coords(
                 [coordless], grid=self, padding_width={ax.name: (pad_lo, pad_hi)},
