@@ -6,6 +6,7 @@ import numpy as np
 import pytest
 import torch
 
+import test_apply_ufunc_gpu as A
 import test_faces_gpu as F
 import test_grid_gpu as G
 import test_transform_gpu as T
@@ -26,7 +27,7 @@ def mock_backend(monkeypatch):
     install(monkeypatch)
 
 
-for _mod in (G, T, F):
+for _mod in (G, T, F, A):
     for _name in dir(_mod):
         if _name.startswith("test_") and _name not in _NEEDS_REAL_GPU:
             globals()[f"{_name}__hostlogic"] = getattr(_mod, _name)
