@@ -1,0 +1,234 @@
+"""More of the reference's Grid-level tests (xgcm/test/test_grid.py:299-1010), transcribed: kwarg
+handling, boundary defaults, coordinate bookkeeping, vector-input validation, 2-D vector wrappers,
+interp_like, cumsum / cumint ``reverse`` forms.  The same bodies run on CPU against the mock
+backend (tests/test_host_logic.py)."""
+
+import warnings
+
+import numpy as np
+import pytest
+
+import xgcm_b200 as xg
+from xgcm_b200 import apply_as_grid_ufunc
+
+from _fixtures import grid_metric_dataset
+
+pytestmark = pytest.mark.gpu
+
+
+def _ds_1d_left(n=9):
+    x_c = np.arange(n) + 0.5
+    return xg.Dataset(
+        data_vars={"data_c": (("XC",), np.sin(2 * np.pi * x_c / n) + 2.0), "data_g": (("XG",), np.cos(np.arange(n) + 0.0))},
+        coords={"XC": x_c, "XG": np.arange(n) + 0.0},
+    )
+
+
+COORDS_1D = {"X": {"center": "XC", "left": "XG"}}
+
+
+def _metric_grid(grid_type="C", **kw):
+    ds, coords, metrics = grid_metric_dataset(grid_type)
+    return ds, coords, metrics, xg.Grid(ds, coords=coords, autoparse_metadata=False, **kw)
+
+
+def test_cumsum_reverse_per_axis_dict_and_cumint_reverse():
+    """test_grid.py:299-370"""
+    ds, coords, metrics, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="fill", autoparse_metadata=False)
+    da = ds["tracer"]
+    result = grid.cumsum(da, ["X", "Y"], padding="fill", reverse={"X": True, "Y": False})
+    expected = grid.cumsum(grid.cumsum(da, "X", padding="fill", reverse=True), "Y", padding="fill", reverse=False)
+    np.testing.assert_array_equal(result.values, expected.values)
+    result_all = grid.cumsum(da, ["X", "Y"], padding="fill", reverse=True)
+    expected_all = grid.cumsum(grid.cumsum(da, "X", padding="fill", reverse=True), "Y", padding="fill", reverse=True)
+    np.testing.assert_array_equal(result_all.values, expected_all.values)
+    np.testing.assert_array_equal(grid.cumsum(da, "X", padding="fill").values,
+                                  grid.cumsum(da, "X", padding="fill", reverse=False).values)
+    # cumint forwards `reverse` (test_grid.py:329-349)
+    weight = grid.get_metric(da, ("X",))
+    expected = grid.cumsum(da * weight, "X", padding="fill", reverse=True)
+    result = grid.cumint(da, "X", padding="fill", reverse=True)
+    np.testing.assert_allclose(result.values, expected.values, rtol=1e-12)
+    assert not np.allclose(result.values, grid.cumint(da, "X", padding="fill").values)
+    for fn in (grid.cumsum, grid.cumint):
+        with pytest.raises(ValueError, match="reverse.*not being cumulatively summed"):
+            fn(da, "X", padding="fill", reverse={"X": True, "Y": False})
+
+
+@pytest.mark.parametrize("func", ["diff_2d_vector", "interp_2d_vector"])
+@pytest.mark.parametrize("padding", ["fill", "extend"])
+def test_2d_vector_dict_input_no_face_connections(func, padding):
+    """test_grid.py:399-430 (GH #581): the vector wrappers on a simply connected grid equal the
+    scalar operators on each component."""
+    ds, coords, _, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, padding="periodic", autoparse_metadata=False)
+    scalar = getattr(grid, func.replace("_2d_vector", ""))
+    expected = {"X": scalar(ds["u"], "X", padding=padding), "Y": scalar(ds["v"], "Y", padding=padding)}
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        result = getattr(grid, func)({"X": ds["u"], "Y": ds["v"]}, padding=padding)
+    for axis, component in result.items():
+        assert component.dims == expected[axis].dims
+        np.testing.assert_array_equal(component.values, expected[axis].values)
+
+
+def test_grid_kwargs_dict_and_invalid_values():
+    """test_grid.py:433-483,555-568"""
+    ds = _ds_1d_left()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        grid_direct = xg.Grid(ds, coords=COORDS_1D, padding="fill", fill_value=5, autoparse_metadata=False)
+        grid_dict = xg.Grid(ds, coords=COORDS_1D, padding={"X": "fill"}, fill_value={"X": 5}, autoparse_metadata=False)
+    assert grid_direct.axes["X"].fill_value == grid_dict.axes["X"].fill_value == 5
+    assert grid_direct.axes["X"].padding == grid_dict.axes["X"].padding == "fill"
+    for bad in ("bad", {"X": "bad"}, {"X": 0}, 0):
+        with pytest.raises(ValueError):
+            xg.Grid(ds, coords=COORDS_1D, padding=bad, autoparse_metadata=False)
+    with pytest.raises(ValueError, match="periodic.*has been removed"):
+        xg.Grid(ds, coords=COORDS_1D, periodic=True, autoparse_metadata=False)
+    with pytest.raises(ValueError, match="padding='periodic'"):
+        xg.Grid(ds, coords=COORDS_1D, periodic=False, autoparse_metadata=False)
+    with pytest.raises(TypeError, match="unexpected keyword"):
+        xg.Grid(ds, coords=COORDS_1D, not_a_real_kwarg=True, autoparse_metadata=False)
+    for bad in ("bad", {"X": "bad"}):
+        with pytest.raises(TypeError), warnings.catch_warnings():
+            warnings.simplefilter("ignore", DeprecationWarning)
+            xg.Grid(ds, coords=COORDS_1D, fill_value=bad, autoparse_metadata=False)
+
+
+def test_default_boundary_is_not_periodic_and_declared_fill_does_not_wrap():
+    """test_grid.py:485-525 (GH #509 / #604 / #624)"""
+    ds = _ds_1d_left()
+    grid = xg.Grid(ds, coords=COORDS_1D, autoparse_metadata=False)
+    assert grid.axes["X"].padding is None and grid.axes["X"].periodic is False
+    with pytest.raises(ValueError, match="No boundary condition was specified"):
+        grid.diff(ds["data_c"], "X")
+    diff_fill = xg.Grid(ds, coords=COORDS_1D, padding="fill", autoparse_metadata=False).diff(ds["data_c"], "X")
+    diff_periodic = xg.Grid(ds, coords=COORDS_1D, padding="periodic", autoparse_metadata=False).diff(ds["data_c"], "X")
+    assert not np.allclose(diff_fill.values, diff_periodic.values)
+    np.testing.assert_array_equal(diff_fill.values[0], ds["data_c"].values[0])
+
+
+def test_cumsum_nonperiodic_does_not_wrap():
+    """test_grid.py:528-552 (GH #625)"""
+    ds = xg.Dataset(coords={"zl": np.arange(1.0, 15.0), "zi": np.arange(0.5, 15.5)})
+    coords = {"Z": {"center": "zl", "outer": "zi"}}
+    zl = ds["zl"]
+    with pytest.raises(ValueError, match="No boundary condition was specified"):
+        xg.Grid(ds, coords=coords, autoparse_metadata=False).cumsum(zl, "Z")
+    result = xg.Grid(ds, coords=coords, padding="fill", autoparse_metadata=False).cumsum(
+        zl, "Z", padding="fill", fill_value=0.0)
+    np.testing.assert_array_equal(result.values, np.hstack([0.0, np.cumsum(zl.values)]))
+
+
+def test_keep_coords_removed():
+    """test_grid.py:614-644 (GH #382 / #696)"""
+    ds, coords, metrics, _ = _metric_grid("B")
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="periodic", autoparse_metadata=False)
+    for axis_name in grid.axes:
+        with pytest.raises(ValueError, match="has been removed"):
+            grid.diff(ds["tracer"], axis_name, keep_coords=False)
+        with pytest.raises(ValueError, match="has been removed"):
+            grid.cumsum(ds["tracer"], axis_name, keep_coords=False)
+    with pytest.raises(ValueError, match="has been removed"):
+        apply_as_grid_ufunc(lambda x: x, ds["tracer"], axis=[("X",)], grid=grid,
+                            signature="(X:center)->(X:center)", keep_coords=False)
+
+
+@pytest.mark.parametrize("funcname", ["interp", "diff", "cumsum"])
+def test_preserve_input_noncore_coords(funcname):
+    """test_grid.py:647-764 (GH #496 / #575): coordinates the user set on the INPUT survive for
+    non-core dims; the shifted core dim takes its coordinate from the grid; coordinates living on
+    the consumed core dim disappear."""
+    N = 8
+    ds = xg.Dataset(
+        data_vars={"v": (("time", "XC"), np.random.default_rng(0).random((N, N)))},
+        coords={"XC": np.arange(N) + 0.5, "XG": np.arange(N) + 0.0, "time": np.arange(N) * 600.0,
+                "t_label": (("time",), np.arange(N) + 0.0), "xc_aux": (("XC",), np.arange(N) * 10.0)},
+    )
+    grid = xg.Grid(ds, coords=COORDS_1D, padding="periodic", autoparse_metadata=False)
+    new_time = (np.arange(N) * 600 / 3600.0).astype(np.float32)
+    new_t_label = (np.arange(N) + 100).astype(np.float32)
+    v = ds["v"].assign_coords(time=new_time, t_label=(("time",), new_t_label),
+                              xc_aux=(("XC",), (np.arange(N) + 500).astype(np.float32)))
+    out = grid.cumsum(v, "X", to="left") if funcname == "cumsum" else getattr(grid, funcname)(v, "X")
+    assert out.coords["time"].values.dtype == np.float32
+    np.testing.assert_array_equal(out.coords["time"].values, new_time)
+    assert "t_label" in out.coords and out.coords["t_label"].values.dtype == np.float32
+    np.testing.assert_array_equal(out.coords["t_label"].values, new_t_label)
+    np.testing.assert_array_equal(out.coords["XG"].values, ds["XG"].values)
+    assert "XC" not in out.dims and "xc_aux" not in out.coords
+
+
+def test_boundary_kwarg_same_as_grid_constructor_kwarg():
+    """test_grid.py:767-782"""
+    ds, coords, _, _ = _metric_grid()
+    grid1 = xg.Grid(ds, coords=coords, autoparse_metadata=False)
+    grid2 = xg.Grid(ds, coords=coords, padding={"X": "fill", "Y": "fill"}, autoparse_metadata=False)
+    actual1 = grid1.interp(ds["tracer"], ("X", "Y"), padding={"X": "fill", "Y": "fill"})
+    actual2 = grid2.interp(ds["tracer"], ("X", "Y"))
+    assert actual1.dims == actual2.dims
+    np.testing.assert_array_equal(actual1.values, actual2.values)
+
+
+@pytest.mark.parametrize("metric_axes,metric_name", [(["Y", "X"], "area_n"), ("X", "dx_t"), ("Y", "dy_ne"),
+                                                     (["Y", "X"], "dy_n"), (["X"], "tracer")])
+@pytest.mark.parametrize("padding", [{"X": "fill", "Y": "fill"}, "extend", {"X": "extend", "Y": "fill"}])
+@pytest.mark.parametrize("fill_value", [None, 0.1])
+def test_interp_like(metric_axes, metric_name, padding, fill_value):
+    """test_grid.py:785-830"""
+    ds, coords, _, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, padding="periodic", autoparse_metadata=False)
+    grid.set_metrics(metric_axes, metric_name)
+    axes_key = frozenset([metric_axes] if isinstance(metric_axes, str) else metric_axes)
+    metric_available = grid._metrics[axes_key][0]
+    interp_metric = grid.interp_like(metric_available, ds["u"], padding=padding, fill_value=fill_value)
+    expected_metric = grid.interp(ds[metric_name], metric_axes, padding=padding, fill_value=fill_value)
+    assert interp_metric.dims == expected_metric.dims
+    np.testing.assert_allclose(interp_metric.values, expected_metric.values, rtol=1e-12)
+
+
+@pytest.mark.parametrize("funcname", ["interp", "diff", "min", "max", "cumsum", "derivative", "cumint"])
+@pytest.mark.parametrize("padding", ["fill", "extend"])
+@pytest.mark.parametrize("fill_value", [0, 10, None])
+def test_boundary_global_input(funcname, padding, fill_value):
+    """test_grid.py:851-893: padding / fill_value given to the Grid == given to the method."""
+    ds, coords, metrics, _ = _metric_grid()
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        grid_global = xg.Grid(ds, coords=coords, metrics=metrics, padding=padding, fill_value=fill_value,
+                              autoparse_metadata=False)
+    global_result = getattr(grid_global, funcname)(ds["tracer"], "X")
+    grid_manual = xg.Grid(ds, coords=coords, metrics=metrics, padding=padding, autoparse_metadata=False)
+    manual_result = getattr(grid_manual, funcname)(ds["tracer"], "X", padding=padding, fill_value=fill_value)
+    assert global_result.dims == manual_result.dims
+    np.testing.assert_array_equal(global_result.values, manual_result.values)
+
+
+def test_vector_input_validation():
+    """test_grid.py:896-1010: the same messages from the Grid methods and apply_as_grid_ufunc."""
+    ds, coords, _, grid = _metric_grid()
+    empty = xg.DataArray(np.zeros(()), dims=())
+    calls = (lambda data, **kw: grid.diff(data, "X", **kw),
+             lambda data, **kw: grid.apply_as_grid_ufunc(lambda x: x, data, axis="X", **kw))
+    for call in calls:
+        with pytest.raises(ValueError, match="Vector components provided as dictionaries should contain exactly one key/value pair"):
+            call({"X": empty, "Y": empty})
+        with pytest.raises(TypeError, match="All data arguments must be either a DataArray or Dictionary"):
+            call("not_a_dataarray")
+        with pytest.raises(TypeError, match="Dictionary inputs must have a DataArray as value. Got"):
+            call({"X": "not_a_dataarray"})
+        with pytest.raises(ValueError, match="Vector component with unknown axis provided. Grid has axes"):
+            call({"wrong": empty})
+    with pytest.raises(ValueError, match="When providing multiple input arguments, `other_component` needs to provide one dictionary per input"):
+        grid.apply_as_grid_ufunc(lambda x: x, {"X": empty}, {"Y": empty}, {"Z": empty}, axis="X",
+                                 other_component=[{"X": empty}, {"Y": empty}])
+
+
+def test_axis_validation_at_grid_creation():
+    """test_grid.py:838-848 and xgcm/test/test_grid.py:60-110: missing dims, dims reused across axes."""
+    ds = xg.Dataset(data_vars={"data": (("x", "y"), np.zeros((4, 5)))}, coords={"x": np.arange(4.0), "y": np.arange(5.0)})
+    msg = r"Could not find dimension `other` \(for the `center` position on axis `X`\) in input dataset."
+    with pytest.raises(ValueError, match=msg):
+        xg.Grid(ds, coords={"X": {"center": "other"}}, autoparse_metadata=False)

@@ -9,6 +9,7 @@ import torch
 import test_apply_ufunc_gpu as A
 import test_faces_gpu as F
 import test_grid_gpu as G
+import test_grid_more_gpu as M
 import test_transform_gpu as T
 import xgcm_b200 as xg
 from _mock_backend import install
@@ -27,7 +28,7 @@ def mock_backend(monkeypatch):
     install(monkeypatch)
 
 
-for _mod in (G, T, F, A):
+for _mod in (G, T, F, A, M):
     for _name in dir(_mod):
         if _name.startswith("test_") and _name not in _NEEDS_REAL_GPU:
             globals()[f"{_name}__hostlogic"] = getattr(_mod, _name)
