@@ -204,3 +204,50 @@ def test_labeled_arithmetic_broadcasts_by_name():
     with pytest.raises(ValueError):
         a * xg.DataArray(np.ones(5), dims=("x",))
     assert a.equals(a.copy()) and not a.equals(a + 1)
+
+
+def test_deprecations_match_reference():
+    """xgcm/test/test_deprecations.py: removed / renamed arguments and attributes raise the
+    reference's messages."""
+    ds = _ds()
+    coords = {"X": {"center": "xc", "left": "xg"}}
+    with pytest.raises(ValueError, match="The `periodic` argument has been removed"):
+        xg.Grid(ds, coords=coords, autoparse_metadata=False, periodic=True)
+    with pytest.raises(ValueError, match="Argument 'boundary' has been renamed to 'padding'"):
+        xg.Grid(ds, coords=coords, autoparse_metadata=False, boundary="periodic")
+    with pytest.raises(ValueError, match="Argument 'boundary_width' has been renamed to 'padding_width'"):
+        xg.as_grid_ufunc("(X:center)->(X:left)", boundary_width={"X": (1, 0)})
+    grid = xg.Grid(ds, coords=coords, autoparse_metadata=False, padding="periodic")
+    with pytest.raises(AttributeError, match="Attribute 'boundary' has been renamed to 'padding'"):
+        grid.axes["X"].boundary
+    gf = xg.as_grid_ufunc("(X:center)->(X:left)")(lambda a: a)
+    with pytest.raises(AttributeError, match="Attribute 'boundary' has been renamed to 'padding'"):
+        gf.boundary
+    with pytest.raises(AttributeError, match="Attribute 'boundary_width' has been renamed to 'padding_width'"):
+        gf.boundary_width
+
+
+def test_axis_reference_cases():
+    """xgcm/test/test_axis.py:9-115"""
+    ds = _ds()
+    axis = xg.Axis(name="X", ds=ds, coords={"center": "xc", "left": "xg"})
+    assert axis.name == "X" and axis.coords == {"center": "xc", "left": "xg"}
+    assert axis.default_shifts == {"left": "center", "center": "left"}
+    assert axis.padding is None
+    assert repr(axis).startswith("<xgcm.Axis 'X'")
+    axis = xg.Axis(name="foo", ds=ds, coords={"center": "xc", "left": "xg"},
+                   default_shifts={"left": "inner", "center": "outer"}, padding="fill")
+    assert axis.default_shifts == {"left": "inner", "center": "outer"} and axis.padding == "fill"
+    with pytest.raises(ValueError, match="Could not find dimension"):
+        xg.Axis(name="X", ds=ds, coords={"center": "lat", "left": "lon"})
+    with pytest.raises(ValueError, match="same dimension cannot be assigned to multiple positions"):
+        xg.Axis(name="X", ds=ds, coords={"center": "xc", "outer": "xc"})
+    with pytest.raises(ValueError, match="Can't set the default"):
+        xg.Axis(name="foo", ds=ds, coords={"center": "xc", "left": "xg"},
+                default_shifts={"left": "left", "center": "center"})
+    with pytest.raises(ValueError, match="padding must be one of"):
+        xg.Axis(name="foo", ds=ds, coords={"center": "xc", "left": "xg"}, padding="blargh")
+    da = xg.DataArray(np.zeros((3, 4)), dims=("yc", "xg"))
+    axis = xg.Axis(name="X", ds=ds, coords={"center": "xc", "left": "xg"})
+    assert axis._get_position_name(da) == ("left", "xg")
+    assert axis._get_axis_dim_num(da) == da.get_axis_num("xg") == 1
