@@ -232,3 +232,93 @@ def test_axis_validation_at_grid_creation():
     msg = r"Could not find dimension `other` \(for the `center` position on axis `X`\) in input dataset."
     with pytest.raises(ValueError, match=msg):
         xg.Grid(ds, coords={"X": {"center": "other"}}, autoparse_metadata=False)
+
+
+# ---------------------------------------------------------------- metrics (xgcm/test/test_metrics_ops.py)
+def _run_single_derivative_test(grid, axis, fld, dx):
+    """test_metrics_ops.py:125-131: derivative == diff / THE NAMED metric, bit for bit."""
+    dvar_dx = grid.derivative(fld, axis)
+    expected = grid.diff(fld, axis) / dx
+    assert dvar_dx.dims == expected.dims
+    np.testing.assert_array_equal(dvar_dx.values, expected.transpose(*dvar_dx.dims).values)
+
+
+@pytest.mark.parametrize("grid_type", ["C", "B"])
+def test_derivative_picks_the_named_metric(grid_type):
+    """test_metrics_ops.py:180-252: which metric array ``derivative`` divides by, per variable
+    position and axis, on C- and B-grids."""
+    ds, coords, metrics, _ = _metric_grid(grid_type)
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="periodic", autoparse_metadata=False)
+    table = {
+        "C": {"tracer": ["dx_e", "dy_n", "dz_w"], "u": ["dx_t", "dy_ne", "dz_w_e"],
+              "v": ["dx_ne", "dy_t", "dz_w_n"], "wt": ["dx_e", "dy_n", "dz_t"]},
+        "B": {"tracer": ["dx_e", "dy_n", "dz_w"], "u": ["dx_n", "dy_e", "dz_w_ne"],
+              "v": ["dx_n", "dy_e", "dz_w_ne"], "wt": ["dx_e", "dy_n", "dz_t"]},
+    }[grid_type]
+    for var, names in table.items():
+        for ax, dx in zip(["X", "Y", "Z"], names):
+            _run_single_derivative_test(grid, ax, ds[var], ds[dx])
+
+
+def _expected_result(da, metric, grid, dims, axes, funcname, padding=None):
+    """test_metrics_ops.py:255-265"""
+    prod = da * metric
+    if funcname == "integrate":
+        return prod.sum(dims)
+    if funcname == "average":
+        return prod.sum(dims) / metric.sum(dims)
+    return grid.cumsum(prod, axes, padding=padding)
+
+
+@pytest.mark.parametrize("funcname", ["integrate", "average", "cumint"])
+@pytest.mark.parametrize("padding", ["fill", "extend"])
+@pytest.mark.parametrize("padding_init", ["fill", "periodic", {"X": "periodic", "Y": "fill"}, {"X": "fill", "Y": "periodic"}])
+@pytest.mark.parametrize("grid_type", ["B", "C"])
+def test_metric_reductions_on_every_position(grid_type, funcname, padding, padding_init):
+    """test_metrics_ops.py:268-398: integrate / average / cumint with the metric named by the
+    reference for tracer, u and v points; list and tuple axis arguments."""
+    ds, coords, metrics, _ = _metric_grid(grid_type)
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding=padding_init, autoparse_metadata=False)
+    kwargs = dict(padding=padding) if funcname == "cumint" else {}
+    func = getattr(grid, funcname)
+    cases = [(ds["tracer"], ["X", "Y", "Z", ["X", "Y"], ["X", "Y", "Z"]],
+              ["dx_t", "dy_t", "dz_t", "area_t", "volume_t"],
+              ["xt", "yt", "zt", ["xt", "yt"], ["xt", "yt", "zt"]])]
+    if grid_type == "B":
+        for v in ("u", "v"):
+            cases.append((ds[v], ["X", "Y", ["X", "Y"]], ["dx_ne", "dy_ne", "area_ne"], ["xu", "yu", ["xu", "yu"]]))
+    else:
+        cases.append((ds["u"], ["X", "Y", ["X", "Y"]], ["dx_e", "dy_e", "area_e"], ["xu", "yt", ["xu", "yt"]]))
+        cases.append((ds["v"], ["X", "Y", ["X", "Y"]], ["dx_n", "dy_n", "area_n"], ["xt", "yu", ["xt", "yu"]]))
+    for da, axes, metric_names, dims in cases:
+        for axis, metric_name, dim in zip(axes, metric_names, dims):
+            expected = _expected_result(da, ds[metric_name], grid, dim, axis, funcname, **kwargs)
+            for ax_arg in ([axis, tuple(axis)] if isinstance(axis, list) else [axis]):
+                new = func(da, ax_arg, **kwargs)
+                assert set(new.dims) == set(expected.dims)
+                np.testing.assert_allclose(new.values, expected.transpose(*new.dims).values, rtol=1e-12)
+
+
+@pytest.mark.parametrize("funcname", ["integrate", "average", "cumint"])
+@pytest.mark.parametrize("axis", ["X", "Y", "Z"])
+def test_missingaxis(axis, funcname):
+    """test_metrics_ops.py:400-447: an application axis the grid does not have is a KeyError."""
+    ds, coords, metrics, _ = _metric_grid("C")
+    coords = {k: v for k, v in coords.items() if k != axis}
+    metrics = {k: v for k, v in metrics.items() if axis not in k}
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="fill", autoparse_metadata=False)
+    kwargs = dict(padding="fill") if funcname == "cumint" else {}
+    with pytest.raises(KeyError, match="Did not find axis"):
+        getattr(grid, funcname)(ds["tracer"], ["X", "Y", "Z"], **kwargs)
+
+
+@pytest.mark.parametrize("funcname", ["integrate", "average", "cumint"])
+def test_metric_axes_missing_from_array(funcname):
+    """test_metrics_ops.py:449-479: the array lost the dim of an application axis."""
+    ds, coords, metrics, _ = _metric_grid("C")
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="fill", autoparse_metadata=False)
+    kwargs = dict(padding="fill") if funcname == "cumint" else {}
+    reduced = ds["tracer"].mean("xt")
+    for axes in ("X", ["X", "Y", "Z"]):
+        with pytest.raises(ValueError, match="Did not find single matching dimension"):
+            getattr(grid, funcname)(reduced, axes, **kwargs)
