@@ -322,3 +322,162 @@ def test_metric_axes_missing_from_array(funcname):
     for axes in ("X", ["X", "Y", "Z"]):
         with pytest.raises(ValueError, match="Did not find single matching dimension"):
             getattr(grid, funcname)(reduced, axes, **kwargs)
+
+
+# ---------------------------------------------------------------- metric selection (xgcm/test/test_metrics.py)
+def _same(a, b):
+    assert set(a.dims) == set(b.dims)
+    np.testing.assert_allclose(a.values, b.transpose(*a.dims).values, rtol=1e-12)
+
+
+def test_multiple_metrics_per_axis_and_2d_grid():
+    """test_metrics.py:14-86"""
+    dx, dy, area, ny, nx = 10.0, 11.0, 120.0, 7, 9
+    ds = xg.Dataset(
+        data_vars={"foo": (("XC",), np.array([1.0, 2.0, 4.0, 3.0])), "bar": (("XG",), np.array([10.0, 20.0, 30.0, 40.0]))},
+        coords={"XC": np.arange(4) + 0.5, "XG": np.arange(4.0), "dXC": (("XC",), np.full(4, dx)), "dXG": (("XG",), np.full(4, dx))},
+    )
+    grid = xg.Grid(ds, coords={"X": {"center": "XC", "left": "XG"}}, metrics={("X",): ["dXC", "dXG"]},
+                   padding="periodic", autoparse_metadata=False)
+    assert grid.get_metric(ds["foo"], ("X",)).dims == ("XC",)
+    assert grid.get_metric(ds["bar"], ("X",)).dims == ("XG",)
+    ds = xg.Dataset(
+        data_vars={"foo": (("YC", "XC"), np.ones((ny, nx)))},
+        coords={"XC": np.arange(nx) + 0.0, "dX": (("XC",), np.full(nx, dx)), "YC": np.arange(ny) + 0.0,
+                "dY": (("YC",), np.full(ny, dy)), "area": (("YC", "XC"), np.full((ny, nx), area))},
+    )
+    coords = {"X": {"center": "XC"}, "Y": {"center": "YC"}}
+    grid = xg.Grid(ds, coords=coords, metrics={("X",): ["dX"], ("Y",): ["dY"], ("X", "Y"): ["area"]}, autoparse_metadata=False)
+    _same(grid.get_metric(ds["foo"], ("X",)), ds["dX"])
+    _same(grid.get_metric(ds["foo"], ("Y",)), ds["dY"])
+    _same(grid.get_metric(ds["foo"], ("X", "Y")), ds["area"])
+    _same(grid.get_metric(ds["foo"], ("Y", "X")), ds["area"])
+    grid = xg.Grid(ds, coords=coords, metrics={("X",): ["dX"], ("Y",): ["dY"]}, autoparse_metadata=False)
+    actual = grid.get_metric(ds["foo"], ("Y", "X")).transpose("YC", "XC")
+    np.testing.assert_array_equal(actual.values, np.full((ny, nx), dx * dy))
+
+
+@pytest.mark.parametrize("key, metric_vars", [(("X",), ["dx_t"]), ("X", "dx_t"), (("X", "Y"), ["area_t"]),
+                                              (("X", "Y"), ["area_t", "area_e", "area_n", "area_ne"]),
+                                              (("X", "Y", "Z"), ["volume_t"])])
+def test_assign_metric(key, metric_vars):
+    """test_metrics.py:89-107"""
+    ds, coords, _, _ = _metric_grid()
+    xg.Grid(ds, coords=coords, metrics={key: metric_vars}, autoparse_metadata=False)
+
+
+def test_iterate_axis_combinations():
+    """test_metrics.py:110-150"""
+    from xgcm_b200.metrics import iterate_axis_combinations
+
+    fs = frozenset
+    expected = {
+        ("X", "Y"): [(fs("XY"),), (fs("X"), fs("Y"))],
+        ("X", "Y", "Z"): [(fs("XYZ"),), (fs("X"), fs("Y"), fs("Z")), (fs("YZ"), fs("X")), (fs("XY"), fs("Z")), (fs("XZ"), fs("Y"))],
+    }
+    for axes, want in expected.items():
+        actual = {frozenset(a) for a in iterate_axis_combinations(axes)}
+        assert actual == {frozenset(w) for w in want}
+
+
+@pytest.mark.parametrize("axes, data_var, metric_expected", [("X", "tracer", "dx_t"), (["X", "Y"], "tracer", "area_t"),
+                                                             (("X", "Y"), "tracer", "area_t"), (["X", "Y", "Z"], "tracer", "volume_t"),
+                                                             (["X"], "u", "dx_e"), (["X", "Y"], "u", "area_e")])
+def test_get_metric_orig(axes, data_var, metric_expected):
+    """test_metrics.py:153-172"""
+    ds, coords, metrics, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, autoparse_metadata=False)
+    _same(grid.get_metric(ds[data_var], axes), ds[metric_expected])
+
+
+def test_get_metric_with_conditions():
+    """test_metrics.py:175-285: the four selection rules of get_metric (grid.py:534-657).  Metrics
+    are interpolated with ``extend`` whatever the grid's padding (grid.py:591-593,644-648); the
+    reference's test compares with the grid's own padding and only passes because its metrics are
+    spatially uniform — the fixture here is not, so the expectation names ``extend``."""
+    ds, coords, metrics, _ = _metric_grid()
+    # 1: a metric on the right axes and position exists
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, autoparse_metadata=False)
+    _same(grid.get_metric(ds["v"], ("X", "Y")), ds["area_n"])
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", UserWarning)
+        # 2a / 2b: interpolate the metric with matching AXES, even if others sit on the position
+        grid = xg.Grid(ds, coords=coords, padding="extend", autoparse_metadata=False)
+        grid.set_metrics(("X", "Y"), "area_e")
+        _same(grid.get_metric(ds["v"], ("X", "Y")), grid.interp(ds["area_e"], ("X", "Y")))
+        grid = xg.Grid(ds, coords=coords, padding="periodic", autoparse_metadata=False)
+        grid.set_metrics(("X", "Y"), "area_e")
+        grid.set_metrics(("X"), "dx_n")
+        grid.set_metrics(("Y"), "dx_n")
+        _same(grid.get_metric(ds["v"], ("X", "Y")), grid.interp(ds["area_e"], ("X", "Y"), padding="extend"))
+        # 3a / 3b: multiply metrics that sit on the right position
+        grid = xg.Grid(ds, coords=coords, autoparse_metadata=False)
+        grid.set_metrics(("X"), "dx_n")
+        grid.set_metrics(("Y"), "dy_n")
+        _same(grid.get_metric(ds["v"], ("X", "Y")), ds["dx_n"] * ds["dy_n"])
+        grid = xg.Grid(ds, coords=coords, autoparse_metadata=False)
+        grid.set_metrics(("X", "Y"), "area_t")
+        grid.set_metrics(("Z"), "dz_t")
+        _same(grid.get_metric(ds["tracer"], ("X", "Y", "Z")), ds["area_t"] * ds["dz_t"])
+        # 4a / 4b: interpolate one or both factors first
+        grid = xg.Grid(ds, coords=coords, padding="periodic", autoparse_metadata=False)
+        grid.set_metrics(("X"), "dx_t")
+        grid.set_metrics(("Y"), "dy_n")
+        _same(grid.get_metric(ds["v"], ("X", "Y")), grid.interp(ds["dx_t"], "Y", padding="extend") * ds["dy_n"])
+        grid = xg.Grid(ds, coords=coords, padding="periodic", autoparse_metadata=False)
+        grid.set_metrics(("X"), "dx_t")
+        grid.set_metrics(("Y"), "dy_t")
+        _same(grid.get_metric(ds["v"], ("X", "Y")),
+              grid.interp(ds["dx_t"], "Y", padding="extend") * grid.interp(ds["dy_t"], "Y", padding="extend"))
+
+
+@pytest.mark.parametrize("data_var, z_metrics, expected_dz", [
+    ("tracer", ["dz_w", "dz_w_ne", "dz_w_n", "dz_w_e", "dz_t"], "dz_t"), ("wt", ["dz_t", "dz_w"], "dz_w")])
+def test_get_metric_no_spurious_interpolation_warning(data_var, z_metrics, expected_dz):
+    """test_metrics.py:288-324 (GH #756)"""
+    ds, coords, _, _ = _metric_grid()
+    metrics = {("X", "Y"): ["area_t", "area_n", "area_e", "area_ne"], ("Z",): z_metrics}
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, autoparse_metadata=False)
+    with warnings.catch_warnings(record=True) as caught:
+        warnings.simplefilter("always")
+        metric = grid.get_metric(ds[data_var], ("X", "Y", "Z"))
+    assert [str(w.message) for w in caught if "being interpolated" in str(w.message)] == []
+    _same(metric, ds["area_t"] * ds[expected_dz])
+
+
+def test_set_metric_and_overwrite_and_errors():
+    """test_metrics.py:327-460"""
+    ds, coords, metrics, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, autoparse_metadata=False)
+    grid_manual = xg.Grid(ds, coords=coords, autoparse_metadata=False)
+    for key, value in metrics.items():
+        grid_manual.set_metrics(key, value)
+    for k, names in metrics.items():
+        for g in (grid, grid_manual):
+            assert [m.name for m in g._metrics[frozenset(k)]] == list(names)
+            for name, m in zip(names, g._metrics[frozenset(k)]):
+                np.testing.assert_array_equal(m.values, ds[name].values)
+    # overwrite=True replaces the metric on the same dims and appends new ones
+    for metric_axes, exist, add, expected in [
+        ("X", ["dx_t", "dx_n", "dx_e", "dx_ne"], ["dx_n_overwrite"], ["dx_t", "dx_n_overwrite", "dx_e", "dx_ne"]),
+        (("Y", "X"), ["area_t", "area_n", "area_e", "area_ne"], ["area_n_overwrite"], ["area_t", "area_n_overwrite", "area_e", "area_ne"]),
+        ("X", ["dx_t", "dx_n", "dx_e"], ["dx_n_overwrite", "dx_ne"], ["dx_t", "dx_n_overwrite", "dx_e", "dx_ne"]),
+    ]:
+        ds2 = ds.assign_coords({add[0]: ds[exist[1]] * 10})
+        sub = {k: [m for m in v if m in exist] for k, v in metrics.items()}
+        g = xg.Grid(ds2, coords=coords, metrics=sub, autoparse_metadata=False)
+        for av in add:
+            g.set_metrics(metric_axes, av, overwrite=True)
+        got = g._metrics[frozenset(list(metric_axes))]
+        assert len(got) == len(expected)
+        for m, name in zip(got, expected):
+            np.testing.assert_array_equal(m.values, ds2[name].values)
+    ds3 = ds.assign_coords({"dx_t_overwrite": ds["dx_t"] * 10})
+    g = xg.Grid(ds3, coords=coords, metrics=metrics, autoparse_metadata=False)
+    for name in ("dx_t_overwrite", "dx_e"):
+        with pytest.raises(ValueError, match="setting overwrite=True."):
+            g.set_metrics("X", name)
+    with pytest.raises(KeyError, match="not found in dataset."):
+        grid.set_metrics("X", "foo")
+    with pytest.raises(KeyError, match="not compatible with grid axes"):
+        grid.set_metrics(("U", "V"), "area_n")
