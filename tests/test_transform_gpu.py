@@ -248,3 +248,167 @@ def test_transform_errors():
         grid.transform(ds["t"], "Z", [1, 2, 3])  # list target: must be ndarray / DataArray
     with pytest.raises(RuntimeError, match="outer"):
         grid.transform(ds["t"], "Z", np.arange(3.0), method="conservative")
+
+
+# ---------------------------------------------------------------- more of xgcm/test/test_transform.py:920-1430
+def _construct(name):
+    """test_transform.py:685-760 (construct_test_source_data) on the labelled arrays of this package:
+    (source Dataset, grid kwargs, target DataArray, transform kwargs, expected values)."""
+    c = json.load(open(os.path.join(GOLDEN, "transform_cases.json")))[name]
+    sdim, scoord = c["source_coord"]
+    data_vars = {c["source_data"][0]: ((sdim,), _arr(c["source_data"][1]).astype(float))}
+    if "source_additional_data" in c:
+        data_vars[c["source_additional_data"][0]] = (
+            (c["source_additional_data_coord"][0],), _arr(c["source_additional_data"][1]).astype(float))
+    coords = {sdim: _arr(scoord).astype(float)}
+    if "source_bounds_coord" in c:
+        coords[c["source_bounds_coord"][0]] = _arr(c["source_bounds_coord"][1]).astype(float)
+    ds = xg.Dataset(data_vars=data_vars, coords=coords)
+    tdim, tvals = c["target_coord"]
+    target = xg.DataArray(_arr(c["target_data"][1]).astype(float), dims=(tdim,),
+                          coords={tdim: _arr(tvals).astype(float)}, name=c["target_data"][0])
+    kw = dict(c["transform_kwargs"])
+    if kw.get("target_data"):
+        kw["target_data"] = ds[kw["target_data"]]
+    want = _arr(c["expected_data"][1]).astype(float)
+    for ii in c.get("expected_data_mask_index", []):
+        want[ii] = np.nan
+    return ds, dict(c["grid_kwargs"]), target, kw, want
+
+
+MULTIDIM = ["conservative_depth_dens_nonmono_edge", "linear_depth_dens", "linear_depth_depth", "conservative_depth_temp"]
+
+
+def test_mid_level_rejects_numpy_targets():
+    """test_transform.py:924-947: the labelled wrappers need a labelled target."""
+    from xgcm_b200.transform import conservative_interpolation, linear_interpolation
+
+    for name, fn in (("linear_depth_depth", linear_interpolation), ("conservative_depth_depth", conservative_interpolation)):
+        ds, _, target, _, _ = _construct(name)
+        (dim,) = ds["data"].dims
+        (tdim,) = target.dims
+        with pytest.raises((ValueError, AttributeError, TypeError)):
+            fn(ds["data"], ds[dim], target.values, dim, dim, tdim)
+
+
+def test_conservative_multidim_target_and_explicit_target_dim_and_bounds_warning():
+    """test_transform.py:1056-1116"""
+    import warnings
+
+    c = json.load(open(os.path.join(GOLDEN, "transform_cases.json")))["conservative_depth_depth_multidim_target"]
+    sdim, scoord = c["source_coord"]
+    ds = xg.Dataset(data_vars={c["source_data"][0]: ((sdim,), _arr(c["source_data"][1]).astype(float))},
+                    coords={sdim: _arr(scoord).astype(float),
+                            c["source_bounds_coord"][0]: _arr(c["source_bounds_coord"][1]).astype(float)})
+    target = xg.DataArray(np.array(c["target_data"][1], dtype=float), dims=tuple(c["target_dims"]), name=c["target_data"][0])
+    kw = dict(c["transform_kwargs"])
+    if kw.get("target_data"):
+        kw["target_data"] = ds[kw["target_data"]]
+    with pytest.raises(NotImplementedError):
+        xg.Grid(ds, **c["grid_kwargs"]).transform(ds[c["source_data"][0]], "Z", target, **kw)
+
+    ds, gk, target, kw, want = _construct("conservative_depth_depth_rename")
+    (target_dim,) = target.dims
+    assert len(target_dim) > 1
+    got = xg.Grid(ds, **gk).transform(ds["data"], "Z", target, target_dim=target_dim, **kw)
+    np.testing.assert_allclose(got.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+    ds, gk, target, kw, _ = _construct("conservative_depth_temp")
+    with pytest.warns(UserWarning, match="The `target data` input is not located on the cell bounds"):
+        xg.Grid(ds, **gk).transform(ds["data"], "Z", target, **kw)
+    warnings.resetwarnings()
+
+
+@pytest.mark.parametrize("name", MULTIDIM)
+def test_grid_transform_names_and_auto_naming(name):
+    """test_transform.py:1129-1205: an unnamed input gives an unnamed output; with a numpy target the
+    new dimension is named after ``target_data`` (or the axis coordinate)."""
+    import warnings
+
+    ds, gk, target, kw, _ = _construct(name)
+    grid = xg.Grid(ds, **gk)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        unnamed = ds["data"].copy()
+        unnamed.name = None
+        assert grid.transform(unnamed, "Z", target, **kw).name is None
+        kw2 = dict(kw)
+        target_data = kw2.setdefault("target_data", None)
+        if target_data is None:
+            expected_coord = grid.axes["Z"].coords["center" if kw2["method"] == "linear" else "outer"]
+        else:
+            expected_coord = target_data.name
+        got = grid.transform(ds["data"], "Z", target.values, **kw2)
+    assert expected_coord in got.coords
+
+
+def test_grid_transform_noname_targetdata():
+    """test_transform.py:1147-1171"""
+    ds, gk, target, kw, _ = _construct("linear_depth_dens")
+    target_data = kw.pop("target_data").copy()
+    target_data.name = None
+    with pytest.warns(UserWarning):
+        got = xg.Grid(ds, **gk).transform(ds["data"], "Z", target.values, target_data=target_data, **kw)
+    assert "TRANSFORMED_DIMENSION" in got.dims
+
+
+@pytest.mark.parametrize("name", MULTIDIM)
+def test_transform_error_periodic(name):
+    """test_transform.py:1174-1185"""
+    ds, gk, target, kw, _ = _construct(name)
+    with pytest.raises(ValueError):
+        xg.Grid(ds, padding="periodic", **gk).transform(ds["data"], "Z", target, **kw)
+
+
+@pytest.mark.parametrize("bypass_checks", [True, False])
+def test_grid_transform_bypass_checks(bypass_checks):
+    """test_transform.py:1208-1235"""
+    ds, gk, target, kw, want = _construct("linear_depth_dens")
+    got = xg.Grid(ds, **gk).transform(ds["data"], "Z", target, bypass_checks=bypass_checks, **kw)
+    np.testing.assert_allclose(got.values, want, rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+@pytest.mark.parametrize("name", MULTIDIM)
+def test_grid_transform_multidim_broadcast(name):
+    """test_transform.py:1280-1313: the 1-D column broadcast against another dim gives the 1-D
+    result in every column."""
+    import warnings
+
+    ds, gk, target, kw, want = _construct(name)
+    na = 8
+    data_vars = {k: (("a",) + ds[k].dims, np.broadcast_to(ds[k].values, (na,) + ds[k].shape).copy())
+                 for k in ds.data_vars}
+    coords = {k: ds[k].values for k in ds.dims}
+    ds2 = xg.Dataset(data_vars=data_vars, coords=coords)
+    target_data = kw.pop("target_data", None)
+    if target_data is not None:
+        target_data = ds2[target_data.name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        got = xg.Grid(ds2, **gk).transform(ds2["data"], "Z", target, target_data=target_data, **kw)
+    assert got.shape == (na, want.size)
+    np.testing.assert_allclose(got.values, np.broadcast_to(want, (na, want.size)), rtol=1e-5, atol=1e-6, equal_nan=True)
+
+
+def test_grid_transform_other_dims_error_and_input_check():
+    """test_transform.py:1339-1430: target_data on a differently named horizontal dim; Datasets
+    where DataArrays are expected."""
+    ds, gk, target, kw, _ = _construct("linear_depth_dens")
+    na = 3
+    src = xg.DataArray(ds["data"].values[:, None] * np.ones((1, na)), dims=("depth", "a"), name="data",
+                       coords={"depth": ds["depth"].values})
+    other = xg.DataArray(kw["target_data"].values[:, None] * np.ones((1, na)), dims=("depth", "a_other"), name="dens")
+    grid = xg.Grid(ds, **gk)
+    kw2 = dict(kw)
+    kw2["target_data"] = other
+    with pytest.raises(ValueError):
+        grid.transform(src, "Z", target, **kw2)
+    with pytest.raises(ValueError, match=r"`da` needs to be a"):
+        grid.transform(ds, "Z", target, **kw)
+    tds = xg.Dataset(data_vars={"dummy": (target.dims, target.values)})
+    with pytest.raises(ValueError, match="needs to be a"):
+        grid.transform(ds["data"], "Z", tds, **kw)
+    kw3 = dict(kw)
+    kw3["target_data"] = xg.Dataset(data_vars={"dummy": (kw["target_data"].dims, kw["target_data"].values)})
+    with pytest.raises(ValueError, match="needs to be a"):
+        grid.transform(ds["data"], "Z", target, **kw3)
