@@ -251,3 +251,67 @@ def test_axis_reference_cases():
     axis = xg.Axis(name="X", ds=ds, coords={"center": "xc", "left": "xg"})
     assert axis._get_position_name(da) == ("left", "xg")
     assert axis._get_axis_dim_num(da) == da.get_axis_num("xg") == 1
+
+
+# ---- xgcm/test/test_grid_ufunc.py:20-213, the parametrized lists verbatim -------------------------
+@pytest.mark.parametrize(
+    "sig_str, exp_in_ax_names, exp_in_ax_pos, exp_out_ax_names, exp_out_ax_pos",
+    [
+        ("()->()", [()], [()], [()], [()]),
+        ("(X:center)->()", [("X",)], [()], [("center",)], [()]),
+        ("()->(X:left)", [()], [("X",)], [()], [("left",)]),
+        ("(X:center)->(X:left)", [("X",)], [("X",)], [("center",)], [("left",)]),
+        ("(X:left)->(Y:center)", [("X",)], [("Y",)], [("left",)], [("center",)]),
+        ("(X:left),(X:right)->(Y:center)", [("X",), ("X",)], [("Y",)], [("left",), ("right",)], [("center",)]),
+        ("(X:center)->(Y:inner),(Y:outer)", [("X",)], [("Y",), ("Y",)], [("center",)], [("inner",), ("outer",)]),
+        ("(X:center,Y:center)->(Z:center)", [("X", "Y")], [("Z",)], [("center", "center")], [("center",)]),
+    ],
+)
+def test_parse_valid_signatures(sig_str, exp_in_ax_names, exp_out_ax_names, exp_in_ax_pos, exp_out_ax_pos):
+    """test_grid_ufunc.py:21-67 (the reference's argument order: the 2nd / 4th lists are names / positions
+    of the INPUTS, the 3rd / 5th of the outputs) and :84-103 (round trip through ``str``)."""
+    from xgcm_b200.grid_ufunc import _GridUFuncSignature, _parse_signature_from_string
+
+    in_ax_names, out_ax_names, in_ax_pos, out_ax_pos = _parse_signature_from_string(sig_str)
+    assert in_ax_names == exp_in_ax_names
+    assert in_ax_pos == exp_in_ax_pos
+    assert out_ax_names == exp_out_ax_names
+    assert out_ax_pos == exp_out_ax_pos
+    assert str(_GridUFuncSignature.from_string(sig_str)) == sig_str
+
+
+@pytest.mark.parametrize("signature", ["(x:left)(y:left)->()", "(x:left),(y:left)->", "((x:left))->(x:left)",
+                                       "(x:left)->(x:left),(i)->(i)", "(X:centre)->()"])
+def test_invalid_signatures(signature):
+    """test_grid_ufunc.py:69-82"""
+    from xgcm_b200.grid_ufunc import _parse_signature_from_string
+
+    with pytest.raises(ValueError):
+        _parse_signature_from_string(signature)
+
+
+def test_signatures_from_type_hints():
+    """test_grid_ufunc.py:106-213"""
+    from typing import Annotated, Tuple
+
+    with pytest.raises(ValueError, match="Must specify axis positions"):
+
+        @xg.as_grid_ufunc()
+        def nothing(): ...
+
+    def sig_of(fn):
+        return str(xg.as_grid_ufunc()(fn).signature)
+
+    def f1(a: Annotated[np.ndarray, "X:center"]) -> Annotated[np.ndarray, "X:center"]: ...
+    def f2(a: Annotated[np.ndarray, "X:center,Y:center"]) -> Annotated[np.ndarray, "X:center"]: ...
+    def f3(a: Annotated[np.ndarray, "X:left"], b: Annotated[np.ndarray, "Y:right"]) -> Annotated[np.ndarray, "X:center"]: ...
+    def f4(a: Annotated[np.ndarray, "X:center"]) -> Annotated[np.ndarray, "X:left,Y:right"]: ...
+    def f5(a: Annotated[np.ndarray, "X:center"]) -> Tuple[Annotated[np.ndarray, "X:left"], Annotated[np.ndarray, "Y:right"]]: ...
+
+    assert sig_of(f1) == "(X:center)->(X:center)"
+    assert sig_of(f2) == "(X:center,Y:center)->(X:center)"
+    assert sig_of(f3) == "(X:left),(Y:right)->(X:center)"
+    assert sig_of(f4) == "(X:center)->(X:left,Y:right)"
+    assert sig_of(f5) == "(X:center)->(X:left),(Y:right)"
+    with pytest.raises(ValueError, match="only one of either type hints or signature kwarg"):
+        xg.as_grid_ufunc(signature="(X:center)->(X:left)")(f1)
