@@ -303,7 +303,8 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
     Same steps as the reference: (1) pad every face on every connection axis to the largest
     requested width with the ordinary boundary condition, (2) overwrite the halo of each
     CONNECTED edge with the neighbour's rim, always read from the pre-padded arrays, (3) trim
-    back to the requested widths.  Step 2 is one ``xg_strided_copy`` per edge.
+    back to the requested widths.  Step 2 is one batched strided-copy launch per axis.  When
+    only one axis is padded the three steps collapse into ``xg_pad`` + one batched copy.
 
     The reference visits the axes in ``set`` order (hash-seed dependent, padding.py:307-309);
     only halo corners depend on it.  Here the order is that of ``grid.axes``.
@@ -353,6 +354,38 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
                 )
         # every padded edge of this axis is connected: its pre-padded halo is a placeholder
         prepad_padding[axname] = "fill"
+
+    active = [ax for ax in pad_axes if any(padding_width[ax])]
+    if len(active) == 1:
+        # One padded axis (every built-in operator, most user ufuncs): no halo corners exist, so the
+        # three steps collapse — basic-pad that axis straight into the final shape (one pass), then
+        # overwrite the connected halos from the UNPADDED neighbours.  Same values as the general
+        # route below, two passes over the field instead of five.
+        ax = active[0]
+        lo, hi = padding_width[ax]
+        padded = _pad_basic(da, grid, {ax: (lo, hi)}, prepad_padding, fill_value)
+        out, was_host = as_device_tensor(padded.data, grid._device_for(padded))  # fresh: xg_pad allocated it
+        o_dims = tuple(padded.dims)
+        o_shape = [int(v) for v in out.shape]
+        x, _ = as_device_tensor(da.data, out.device)
+        x_shape = [int(v) for v in x.shape]
+        sources = {"self": (x, tuple(da.dims), x_shape, _contiguous_strides(x_shape))}
+        if isvector:
+            q, _ = as_device_tensor(da_partner.data, out.device)
+            if q.dtype != out.dtype:
+                q = q.to(out.dtype)
+            q_shape = [int(v) for v in q.shape]
+            sources["partner"] = (q, tuple(da_partner.dims), q_shape, _contiguous_strides(q_shape))
+        t_len = o_shape[o_dims.index(_axis_dim(grid, o_dims, ax))]
+        batch = []
+        for i in range(n_facedim):
+            links = face_links.get(i, {}).get(ax, (None, None))
+            for connection, is_right, w in ((links[0], False, lo), (links[1], True, hi)):
+                if connection and w:
+                    _copy_connected_edge(grid, facedim, out, o_dims, o_shape, i, ax, (t_len - w) if is_right else 0,
+                                         w, 0, connection, is_right, sources, isvector, vectoraxis, batch)
+        ops.strided_copy_batch(batch)
+        return DataArray(result_like(out, was_host), dims=o_dims, name=padded.name, attrs=padded.attrs)
 
     prepadded = _pad_basic(da, grid, max_padding_width, prepad_padding, fill_value)
     p, was_host = as_device_tensor(prepadded.data, grid._device_for(prepadded))
