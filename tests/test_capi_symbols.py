@@ -43,3 +43,35 @@ def test_loader_attaches_prototypes_and_reports_errors_without_gpu():
         pass
     else:  # pragma: no cover
         raise AssertionError("XG_EINVAL must map to ValueError")
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """The boundary is a C ABI: the header must compile as C99 (no C++-isms, no torch types) and a
+    C program must link against the library and call it (argument validation needs no GPU)."""
+    import shutil
+    import subprocess
+
+    gcc = shutil.which("gcc")
+    if gcc is None:  # pragma: no cover
+        import pytest
+
+        pytest.skip("gcc not available")
+    lib = _build.build()
+    src = tmp_path / "capi_c.c"
+    src.write_text(
+        '#include "xgcm_b200.h"\n'
+        "#include <stdio.h>\n"
+        "#include <string.h>\n"
+        "int main(void) {\n"
+        "  int64_t shape[1] = {4};\n"
+        "  int rc = xg_pad(XG_F32, 0, 0, 1, shape, 0, 1, 0, XG_BC_FILL, 0.0, 0);\n"
+        '  printf("%d %d %d\\n", xg_version(), rc, (int)(strstr(xg_last_error(), "null") != 0));\n'
+        "  return rc == XG_EINVAL ? 0 : 1;\n"
+        "}\n"
+    )
+    exe = tmp_path / "capi_c"
+    subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src),
+                    "-L", os.path.dirname(str(lib)), "-l:" + os.path.basename(str(lib)),
+                    "-Wl,-rpath," + os.path.dirname(str(lib)), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
+    assert out == ["100", "-1", "1"]
