@@ -122,7 +122,7 @@ def _source_dim_for(grid, target_dim, s_dims):
 
 
 def _copy_connected_edge(grid, facedim, dst, d_dims, d_shape, face, axname, d_start, width, prepad,
-                         connection, is_right, sources, isvector, vectoraxis, batch):
+                         connection, is_right, sources, isvector, vectoraxis, batch, cross_pads=None):
     """Write the ``width`` halo cells of one connected edge of ``face`` into ``dst`` (dims
     ``d_dims``, starting at index ``d_start`` along the dim of ``axname``) from the neighbour
     named by ``connection`` (padding.py:414-541): ONE strided copy, appended to ``batch`` (all edges
@@ -132,6 +132,12 @@ def _copy_connected_edge(grid, facedim, dst, d_dims, d_shape, face, axname, d_st
     ``prepad`` halo cells on the sliced dim (the reference slices pre-padded arrays; the operator
     fast path reads the bare field, prepad = 0).  Every dim of ``dst`` other than the face dim and
     the padded one is copied over its full extent, which must match the source's.
+
+    ``cross_pads`` (with prepad = 0): ``{dst dim: (lo, hi)}`` for ONE other dim of ``dst`` that is
+    itself padded.  The reference takes the rim from the PRE-PADDED neighbour, so along that dim the
+    slab continues into the neighbour's own basic halo (fill constant / edge cell / wrapped cells,
+    ``cross_pads["modes"][axis] = (mode, fill value)``): those corner blocks are written by extra
+    strided copies with zero or wrapped source strides.
     """
     source_face, source_axis, reverse = connection
     swap_axis = axname != source_axis
@@ -161,36 +167,72 @@ def _copy_connected_edge(grid, facedim, dst, d_dims, d_shape, face, axname, d_st
         s0 = s_len - prepad - width if reverse else prepad
     else:
         s0 = prepad if reverse else s_len - prepad - width
+    negate = isvector and (
+        (reverse and vectoraxis == axname) or (swap_axis and not reverse and vectoraxis != axname)
+    )
+    # per loop dim: segments (dst start, length, src start, src stride, constant or None)
+    per_dim = []
     for d, n in zip(loop_dims, shape):
         if d == target_dim:
             st = s_strides[s_dims.index(s_sliced)]
             if reverse:  # flip across the seam (padding.py:478-487)
-                src_offset += (s0 + width - 1) * st
-                src_strides.append(-st)
+                per_dim.append([(0, n, (s0 + width - 1) * st, -st, None)])
             else:
-                src_offset += s0 * st
-                src_strides.append(st)
-        elif swap_axis and d == cross_dim:
-            st = s_strides[s_dims.index(s_along)]
-            if s_shape[s_dims.index(s_along)] != n:
+                per_dim.append([(0, n, s0 * st, st, None)])
+            continue
+        lo_d, hi_d = (cross_pads or {}).get(d, (0, 0))
+        n_in = n - lo_d - hi_d
+        if swap_axis and d == cross_dim:
+            sd, flip, src_axis_name = s_along, not reverse, axname  # flip along the seam (padding.py:489-498)
+            if s_shape[s_dims.index(sd)] != n_in:
                 raise ValueError(
                     "a face connection that swaps axes needs faces of equal size along "
                     f"{axname!r} and {source_axis!r}"
                 )
-            if reverse:
-                src_strides.append(st)
-            else:  # flip along the seam (padding.py:489-498)
-                src_offset += (n - 1) * st
-                src_strides.append(-st)
         else:
-            sd = _source_dim_for(grid, d, s_dims)
-            if s_shape[s_dims.index(sd)] != n:
+            sd, flip = _source_dim_for(grid, d, s_dims), False
+            src_axis_name = next((ax for ax in grid.axes if sd in grid.axes[ax].coords.values()), None)
+            if s_shape[s_dims.index(sd)] != n_in:
                 raise ValueError(f"dimension {d!r} differs between connected arrays")
-            src_strides.append(s_strides[s_dims.index(sd)])
-    negate = isvector and (
-        (reverse and vectoraxis == axname) or (swap_axis and not reverse and vectoraxis != axname)
-    )
-    batch.append((dst, dst_offset, dst_strides, s, src_offset, src_strides, shape, negate))
+        st = s_strides[s_dims.index(sd)]
+        segs = [(lo_d, n_in, (n_in - 1) * st if flip else 0, -st if flip else st, None)]
+        if lo_d or hi_d:
+            mode, fv = cross_pads["modes"][src_axis_name]
+            for length, lower in ((lo_d, True), (hi_d, False)):
+                if not length:
+                    continue
+                dst0 = 0 if lower else lo_d + n_in
+                # the neighbour's halo this dst halo reads: its lower one, or the upper one if flipped
+                src_lower = lower != flip
+                if mode == "fill":
+                    segs.append((dst0, length, 0, 0, float(fv if fv is not None else 0.0)))
+                elif mode == "extend":
+                    segs.append((dst0, length, 0 if src_lower else (n_in - 1) * st, 0, None))
+                else:  # periodic: the cells at the other end, in dst order
+                    if src_lower:   # virtual source index -length .. -1  (or reversed when flipped)
+                        first, last = n_in - length, n_in - 1
+                    else:           # virtual source index n .. n + length - 1
+                        first, last = 0, length - 1
+                    # identity walks the virtual index upwards; the flip walks it downwards
+                    if flip:
+                        # dst lower halo (D = -length..-1) -> u = n-1-D = n-1+length .. n  -> wrapped: length-1 .. 0
+                        # dst upper halo (D = n..n+length-1) -> u = -1 .. -length -> wrapped: n-1 .. n-length
+                        segs.append((dst0, length, last * st, -st, None))
+                    else:
+                        segs.append((dst0, length, first * st, st, None))
+        per_dim.append(segs)
+    import itertools
+
+    for combo in itertools.product(*per_dim):
+        const = [c[4] for c in combo if c[4] is not None]
+        sub_shape = [c[1] for c in combo]
+        d_off = dst_offset + sum(c[0] * ds for c, ds in zip(combo, dst_strides))
+        if const:
+            cval = cross_pads["const"](const[0])
+            batch.append((dst, d_off, dst_strides, cval, 0, [0] * len(sub_shape), sub_shape, negate))
+        else:
+            s_off = src_offset + sum(c[2] for c in combo)
+            batch.append((dst, d_off, dst_strides, s, s_off, [c[3] for c in combo], sub_shape, negate))
 
 
 def _unpack_vector(grid, da, other_component):
@@ -385,6 +427,53 @@ def _pad_face_connections(da, grid, padding_width, padding, fill_value, other_co
                     _copy_connected_edge(grid, facedim, out, o_dims, o_shape, i, ax, (t_len - w) if is_right else 0,
                                          w, 0, connection, is_right, sources, isvector, vectoraxis, batch)
         ops.strided_copy_batch(batch)
+        return DataArray(result_like(out, was_host), dims=o_dims, name=padded.name, attrs=padded.attrs)
+
+    if len(active) == 2:
+        # Two padded axes (2-D stencils of user ufuncs): still no pre-padded copies.  Basic-pad both
+        # axes straight into the final shape; then, axis by axis in the reference's order, write
+        # each connected halo slab over the FULL extent of the other axis — its corner blocks are
+        # the neighbour's own basic halo (what the reference finds in the pre-padded neighbour),
+        # produced by zero-stride / wrapped strided copies.  Two passes instead of five.
+        import torch
+
+        widths = {ax: padding_width[ax] for ax in active}
+        padded = _pad_basic(da, grid, widths, prepad_padding, fill_value)
+        out, was_host = as_device_tensor(padded.data, grid._device_for(padded))  # fresh: xg_pad allocated it
+        o_dims = tuple(padded.dims)
+        o_shape = [int(v) for v in out.shape]
+        x, _ = as_device_tensor(da.data, out.device)
+        x_shape = [int(v) for v in x.shape]
+        sources = {"self": (x, tuple(da.dims), x_shape, _contiguous_strides(x_shape))}
+        if isvector:
+            q, _ = as_device_tensor(da_partner.data, out.device)
+            if q.dtype != out.dtype:
+                q = q.to(out.dtype)
+            q_shape = [int(v) for v in q.shape]
+            sources["partner"] = (q, tuple(da_partner.dims), q_shape, _contiguous_strides(q_shape))
+        consts = {}
+
+        def const(value):
+            key = repr(float(value))
+            if key not in consts:
+                consts[key] = torch.full((1,), float(value), dtype=out.dtype, device=out.device)
+            return consts[key]
+
+        modes = {ax: (prepad_padding[ax], fill_value.get(ax)) for ax in pad_axes}
+        for ax in active:
+            other = active[1] if ax == active[0] else active[0]
+            cross = {_axis_dim(grid, o_dims, other): padding_width[other], "modes": modes, "const": const}
+            lo, hi = padding_width[ax]
+            t_len = o_shape[o_dims.index(_axis_dim(grid, o_dims, ax))]
+            batch = []
+            for i in range(n_facedim):
+                links = face_links.get(i, {}).get(ax, (None, None))
+                for connection, is_right, w in ((links[0], False, lo), (links[1], True, hi)):
+                    if connection and w:
+                        _copy_connected_edge(grid, facedim, out, o_dims, o_shape, i, ax, (t_len - w) if is_right else 0,
+                                             w, 0, connection, is_right, sources, isvector, vectoraxis, batch,
+                                             cross_pads=cross)
+            ops.strided_copy_batch(batch)  # the second axis overwrites the corners, like the reference
         return DataArray(result_like(out, was_host), dims=o_dims, name=padded.name, attrs=padded.attrs)
 
     prepadded = _pad_basic(da, grid, max_padding_width, prepad_padding, fill_value)
