@@ -75,3 +75,27 @@ def test_header_is_plain_c_and_links(tmp_path):
                     "-Wl,-rpath," + os.path.dirname(str(lib)), "-o", str(exe)], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()
     assert out == ["100", "-1", "1"]
+
+
+def test_strided_copy_argument_validation_without_gpu():
+    """xg_strided_copy(_batch) validate their arguments before any CUDA call: null pointers, bad
+    rank, negative extents, and (batch) a copy that does not collapse to 5 dims -> XG_ENOTIMPL, the
+    signal on which ops.strided_copy_batch falls back to one launch per copy."""
+    import ctypes as C
+
+    lib = _capi.load()
+    i64 = _capi.i64_array
+    one = (C.c_void_p * 1)(1)  # never dereferenced: validation fails (or nothing launches) first
+    assert lib.xg_strided_copy(0, None, i64([1]), None, i64([1]), 1, i64([4]), 0, None) == -1
+    assert lib.xg_strided_copy(0, 1, i64([1]), 1, i64([1]), 9, i64([4]), 0, None) == -1
+    assert lib.xg_strided_copy(0, 1, i64([1]), 1, i64([1]), 1, i64([-4]), 0, None) == -1
+    assert lib.xg_strided_copy(7, 1, i64([1]), 1, i64([1]), 1, i64([4]), 0, None) == -1
+    assert lib.xg_strided_copy_batch(0, 0, None, None, 1, None, None, None, None, None) == 0
+    assert lib.xg_strided_copy_batch(0, -1, None, None, 1, None, None, None, None, None) == -1
+    assert lib.xg_strided_copy_batch(0, 1, None, None, 1, None, None, None, None, None) == -1
+    # six dims with pairwise incompatible strides cannot be collapsed below six
+    shape = i64([2, 2, 2, 2, 2, 2])
+    dst_strides = i64([32, 16, 8, 4, 2, 1])
+    src_strides = i64([1, 2, 4, 8, 16, 32])
+    rc = lib.xg_strided_copy_batch(0, 1, one, one, 6, shape, dst_strides, src_strides, (C.c_int * 1)(0), None)
+    assert rc == -2 and "5" in _capi.last_error()
