@@ -323,18 +323,40 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
             else:
                 row = 0 if side else (n - 1)
             ops.strided_copy(plane, 0, _contiguous_strides(p_shape), x, row * strides[t], strides, p_shape)
-        for i in range(n_face):
-            connection = face_links.get(face_offset + i, {}).get(ax_name, (None, None))[side]
-            if not connection:
-                continue
-            src_local = connection[0] - face_offset
-            if remote_edges is not None and not 0 <= src_local < n_face:
-                remote_edges.append((side, i, connection))
-                continue
-            _copy_connected_edge(grid, facedim, plane, dims, p_shape, i, ax_name, 0, 1, 0,
-                                 (src_local,) + tuple(connection[1:]), bool(side), sources, isvector,
-                                 vectoraxis, batch)
         planes.append(plane)
+
+    # The index maps of the connected edges depend only on the topology and the array layout, not
+    # on the values: derive them once per (axis, widths, layout) and keep them on the grid.
+    cache = grid.__dict__.setdefault("_halo_plan_cache", {})
+    key = (ax_name, lo, hi, dims, tuple(shape), vectoraxis,
+           None if not isvector else (sources["partner"][1], tuple(sources["partner"][2])))
+    plan = cache.get(key) if remote_edges is None else None
+    if plan is None:
+        plan = []
+        p_shape = list(shape)
+        p_shape[t] = 1
+        for side, w in ((0, lo), (1, hi)):
+            if not w:
+                continue
+            for i in range(n_face):
+                connection = face_links.get(face_offset + i, {}).get(ax_name, (None, None))[side]
+                if not connection:
+                    continue
+                src_local = connection[0] - face_offset
+                if remote_edges is not None and not 0 <= src_local < n_face:
+                    remote_edges.append((side, i, connection))
+                    continue
+                one = []
+                _copy_connected_edge(grid, facedim, planes[side], dims, p_shape, i, ax_name, 0, 1, 0,
+                                     (src_local,) + tuple(connection[1:]), bool(side), sources, isvector,
+                                     vectoraxis, one)
+                for _, doff, dstr, src, soff, sstr, shp, neg in one:
+                    src_key = "partner" if (isvector and src is sources["partner"][0]) else "self"
+                    plan.append((side, doff, dstr, src_key, soff, sstr, shp, neg))
+        if remote_edges is None:
+            cache[key] = plan
+    batch = [(planes[side], doff, dstr, sources[src_key][0], soff, sstr, shp, neg)
+             for side, doff, dstr, src_key, soff, sstr, shp, neg in plan]
     ops.strided_copy_batch(batch)  # both planes, every connected face: one launch
     return x, planes[0], planes[1], was_host, dims
 
