@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--shape", type=int, nargs=3, default=list(SHAPE))
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the per-config records (C1, C2, C3 integrate, C4 loop, C5)")
     return ap.parse_args()
 
 
@@ -147,8 +148,10 @@ class ClockSampler:
 
 
 # --------------------------------------------------------------------------- the oracle legs (CPU)
-def oracle_step(a, pool=None, nchunks=1):
-    """The reference's numpy calls for the six ops (np.pad copy + kernel on a moveaxis view)."""
+def oracle_step(a, pool=None, nchunks=1, out_buf=None):
+    """The reference's numpy calls for the six ops (np.pad copy + kernel on a moveaxis view).
+    out_buf: a preallocated result array re-used by every op (no first-touch page faults per call) —
+    kinder than the reference, which returns a fresh array per op."""
     from oracle import stencil as oracle
 
     def one(op, axis_i, bc, fill):
@@ -159,7 +162,7 @@ def oracle_step(a, pool=None, nchunks=1):
         chunk_axis = 0 if axis_i != 0 else 1
         nch = max(1, min(nchunks, a.shape[chunk_axis]))
         bounds = np.linspace(0, a.shape[chunk_axis], nch + 1).astype(int)
-        out = np.empty(a.shape, a.dtype)
+        out = np.empty(a.shape, a.dtype) if out_buf is None else out_buf
 
         def task(i):
             sl = [slice(None)] * a.ndim
@@ -180,53 +183,244 @@ def oracle_step(a, pool=None, nchunks=1):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU path on all host cores (rank 0 only)."""
+    """--impl reference: the reference's CPU path on the host cores (rank 0 only).  Nothing of the product
+    is imported here: inputs come from oracle/synth.py (same bits as the device generator)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from concurrent.futures import ThreadPoolExecutor
 
-    from xgcm_b200 import ops
+    from oracle import synth
 
     cores = os.cpu_count() or 1
     shape = tuple(args.shape)
     a = np.empty(shape, DTYPE)
-    ops.fill_uniform_host(a.reshape(-1), SEED)
-    nchunks = cores
-    budget_s = 150.0  # the whole --steps K --warmup W run should end within a few minutes
-    with ThreadPoolExecutor(max_workers=cores) as pool:
-        # calibrate on one full step, then bound the per-step sample to a leading block of Z levels
-        t0 = time.perf_counter()
-        oracle_step(a, pool, nchunks)
-        t_full = time.perf_counter() - t0
-        steps_total = args.steps + max(args.warmup - 1, 0)
-        nz = shape[0]
-        nz_s = nz if t_full * steps_total <= budget_s else max(2, int(nz * budget_s / (t_full * steps_total)))
-        sub = a if nz_s == nz else np.ascontiguousarray(a[:nz_s])
+    with ThreadPoolExecutor(max_workers=min(cores, 32)) as gen:  # numpy releases the GIL: generate planes in parallel
+        plane = int(np.prod(shape[1:]))
+        list(gen.map(lambda k: synth.fill_uniform(a[k], SEED, k * plane), range(shape[0])))
+
+    out_buf = np.empty(shape, DTYPE)
+    out_buf.fill(0)  # touch the pages once
+
+    def timed_step(workers, buf=out_buf):
+        with ThreadPoolExecutor(max_workers=workers) as pool:
+            t0 = time.perf_counter()
+            oracle_step(a, pool, workers, buf)
+            return time.perf_counter() - t0
+
+    t_alloc = timed_step(cores, None)  # the untuned figure: every hardware thread, a fresh result per op
+
+    # pool calibration, one full step each: every hardware thread (dask's default) and one worker per
+    # physical core (SMT siblings share the load/store ports this path saturates)
+    candidates = sorted({cores, max(1, cores // 2), max(1, cores // 4)}, reverse=True)
+    calib = {w: timed_step(w) for w in candidates}
+    workers = min(calib, key=calib.get)
+    t_full = calib[workers]
+    steps_total = args.steps + max(args.warmup - 1, 0)
+    budget_s = 240.0  # the whole --steps K --warmup W run should end within a few minutes
+    nz = shape[0]
+    nz_s = nz if t_full * steps_total <= budget_s else max(2, int(nz * budget_s / (t_full * steps_total)))
+    sub = a if nz_s == nz else np.ascontiguousarray(a[:nz_s])
+    sub_out = out_buf[:nz_s]
+    with ThreadPoolExecutor(max_workers=workers) as pool:
         for _ in range(max(args.warmup - 1, 0)):
-            oracle_step(sub, pool, nchunks)
+            oracle_step(sub, pool, workers, sub_out)
         t0 = time.perf_counter()
         cells = 0
         for _ in range(args.steps):
-            cells += oracle_step(sub, pool, nchunks)
+            cells += oracle_step(sub, pool, workers, sub_out)
         dt = time.perf_counter() - t0
     value = cells / dt
-    sample = (f"{'full workload' if nz_s == nz else f'first {nz_s} of {nz} Z levels of the field'} per step, "
-              f"{args.steps} steps; thread pool of {cores} over broadcast-dim chunks (dask='parallelized' analogue); "
-              f"one full step took {t_full:.2f} s")
+    cells_full = 6 * int(np.prod(shape))
+    sample = (f"{'the full workload' if nz_s == nz else f'first {nz_s} of {nz} Z levels of the field'} per step, "
+              f"{args.steps} steps; thread pool of {workers} workers over broadcast-dim chunks (dask='parallelized' "
+              f"analogue, xgcm/grid.py:786-789) writing into ONE preallocated result array; one-step calibration, "
+              f"workers -> cells/s: " + ", ".join(f"{w}: {cells_full / t:.3g}" for w, t in sorted(calib.items())) +
+              f"; untuned ({cores} workers, fresh result array per op as the reference returns): "
+              f"{cells_full / t_alloc:.3g} cells/s; np.pad still copies the field per call, so the path scales poorly")
     line = {
         "impl": "reference",
         "metric": METRIC, "value": value, "unit": "cells/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "shape": list(shape), "cells_per_step": cells // args.steps},
-        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": cores, "kind": "port", "sample": sample},
+        "config": {"workload": WORKLOAD, "shape": list(shape), "cells_per_step": cells // args.steps,
+                   "same_config": nz_s == nz},
+        "cpu_baseline": {"value": value, "unit": "cells/s", "cores": workers, "kind": "port", "sample": sample,
+                         "host_cores": cores,
+                         "calibration_cells_per_s": {str(w): cells_full / t for w, t in sorted(calib.items())},
+                         "untuned_cells_per_s": cells_full / t_alloc},
         "e2e": {"value": value, "unit": "cells/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
         "numpy": np.__version__,
     }
     print(json.dumps(line), flush=True)
 
+
+
+# --------------------------------------------------------------------------- every BASELINE config, one record each
+def run_extras(torch, dist, ops, _capi, x, rank, world, peak):
+    """`extra`: ms, cells/s, algorithmic bytes and fraction of the measured HBM peak for the BASELINE configs
+    the headline does not cover (configs[0], [1], the integrate('Z') half of [2], [3] as a 32-step loop with
+    device-generated steps, [4]).  Device-resident, CUDA events, median of the timed repeats, max over ranks;
+    a buffer larger than L2 is rewritten between the repeats of the L2-sized configs (C1, C2)."""
+    import xgcm_b200 as xg
+
+    dev = x.device
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def timed(fn, iters, flush_l2=False, warmup=2):
+        for _ in range(warmup):
+            fn()
+        ts = []
+        for _ in range(iters):
+            if flush_l2:
+                flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            fn()
+            e.record()
+            torch.cuda.synchronize()
+            ts.append(s.elapsed_time(e))
+        ms = torch.tensor([statistics.median(ts)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    def rec(name, ms, cells, nbytes, launches, note):
+        return {"config": name, "ms": ms, "cells_per_s": cells * world / (ms * 1e-3),
+                "algorithmic_bytes": nbytes, "GBps_per_gpu": nbytes / (ms * 1e-3) / 1e9,
+                "frac_of_peak": nbytes / (ms * 1e-3) / 1e9 / peak, "launches_per_call": launches, "note": note}
+
+    out = []
+
+    def count(fn):
+        n0 = _capi.load().xg_launch_count()
+        fn()
+        return int(_capi.load().xg_launch_count() - n0)
+
+    # ---- C1: 1-D periodic, 1e6 fp64, Grid.diff('X') + Grid.interp('X') -------------------------------------
+    n1 = 1_000_000
+    a1 = torch.empty(n1, dtype=torch.float64, device=dev)
+    ops.fill_uniform(a1, SEED + 1)
+    ds1 = xg.Dataset(coords={"XC": np.arange(n1) + 0.5, "XG": np.arange(n1) + 0.0})
+    g1 = xg.Grid(ds1, coords={"X": {"center": "XC", "left": "XG"}}, padding="periodic", autoparse_metadata=False)
+    d1 = xg.DataArray(a1, dims=("XC",))
+
+    def c1():
+        g1.diff(d1, "X")
+        g1.interp(d1, "X")
+
+    out.append(rec("C1 (configs[0]): 1e6 fp64 periodic, Grid.diff('X') + Grid.interp('X')", timed(c1, 20, True), 2 * n1,
+                   2 * 16 * n1, count(c1), "16 MB per launch: launch/latency bound, L2 flushed between repeats"))
+
+    # ---- C2: 360x240x50 fp32, derivative('X') with dx(Y,X); metric-weighted interp('Z') ---------------------
+    nz2, ny2, nx2 = 50, 240, 360
+    a2 = torch.empty((nz2, ny2, nx2), dtype=torch.float32, device=dev)
+    ops.fill_uniform(a2, SEED + 2)
+    jj = np.arange(ny2, dtype=np.float64)[:, None]
+    dx2 = (1e3 * (1 + 0.1 * np.cos(2 * np.pi * jj / ny2)) * np.ones((1, nx2))).astype(np.float32)
+    dz2 = (10 * 1.05 ** np.arange(nz2)).astype(np.float32)
+    ds2 = xg.Dataset(coords={"Z": np.arange(nz2) + 0.5, "Zl": np.arange(nz2) + 0.0, "YC": np.arange(ny2) + 0.5,
+                             "YG": np.arange(ny2) + 0.0, "XC": np.arange(nx2) + 0.5, "XG": np.arange(nx2) + 0.0})
+    for nm, dims, arr in (("dxC", ("YC", "XC"), dx2), ("dxG", ("YC", "XG"), dx2), ("drF", ("Z",), dz2), ("drC", ("Zl",), dz2)):
+        ds2[nm] = xg.DataArray(torch.from_numpy(arr).to(dev), dims=dims)
+    g2 = xg.Grid(ds2, coords={"X": {"center": "XC", "left": "XG"}, "Y": {"center": "YC", "left": "YG"},
+                              "Z": {"center": "Z", "left": "Zl"}},
+                 metrics={("X",): ["dxC", "dxG"], ("Z",): ["drF", "drC"]},
+                 padding={"X": "periodic", "Y": "fill", "Z": "extend"}, autoparse_metadata=False)
+    d2 = xg.DataArray(a2, dims=("Z", "YC", "XC"))
+    c2 = a2.numel()
+    f_der2 = lambda: g2.derivative(d2, "X")
+    out.append(rec("C2 (configs[1]): 50x240x360 fp32 Grid.derivative('X'), dx(Y,X) fused", timed(f_der2, 20, True), c2,
+                   8 * c2 + 4 * ny2 * nx2, count(f_der2), "17 MB per launch: launch/latency bound, L2 flushed"))
+    f_mw2 = lambda: g2.interp(d2, "Z", metric_weighted="X")
+    out.append(rec("C2: Grid.interp('Z', metric_weighted='X') (x dx, / dx fused)", timed(f_mw2, 20, True), c2,
+                   8 * c2 + 8 * ny2 * nx2, count(f_mw2), "launch/latency bound"))
+    del a2, d2
+
+    # ---- C3-sized metric-fused stencils and integrate('Z') ----------------------------------------------------
+    nz, ny, nx = x.shape
+    cells = x.numel()
+    jj = np.arange(ny, dtype=np.float64)[:, None]
+    dx3 = (1e3 * (1 + 0.1 * np.cos(2 * np.pi * jj / ny)) * np.ones((1, nx))).astype(np.float32)
+    dz3 = (10 * 1.05 ** np.arange(nz)).astype(np.float32)
+    ds3 = xg.Dataset(coords={"Z": np.arange(nz) + 0.5, "Zl": np.arange(nz) + 0.0, "YC": np.arange(ny) + 0.5,
+                             "YG": np.arange(ny) + 0.0, "XC": np.arange(nx) + 0.5, "XG": np.arange(nx) + 0.0})
+    for nm, dims, arr in (("dxC", ("YC", "XC"), dx3), ("dxG", ("YC", "XG"), dx3), ("drF", ("Z",), dz3), ("drC", ("Zl",), dz3)):
+        ds3[nm] = xg.DataArray(torch.from_numpy(arr).to(dev), dims=dims)
+    g3 = xg.Grid(ds3, coords={"X": {"center": "XC", "left": "XG"}, "Y": {"center": "YC", "left": "YG"},
+                              "Z": {"center": "Z", "left": "Zl"}},
+                 metrics={("X",): ["dxC", "dxG"], ("Z",): ["drF", "drC"]},
+                 padding={"X": "periodic", "Y": "fill", "Z": "extend"}, autoparse_metadata=False)
+    d3 = xg.DataArray(x, dims=("Z", "YC", "XC"))
+    f_int = lambda: g3.integrate(d3, "Z")
+    out.append(rec("C3 (configs[2]): Grid.integrate('Z'), 1-D dz", timed(f_int, 8), cells, 4 * cells + 4 * ny * nx + 4 * nz,
+                   count(f_int), "cells = input cells; 2.59 GB in, 34.6 MB out"))
+    f_der3 = lambda: g3.derivative(d3, "X")
+    out.append(rec("C3-sized Grid.derivative('X'), dx(Y,X) fused", timed(f_der3, 8), cells, 8 * cells + 4 * ny * nx,
+                   count(f_der3), "the C2 operation at a bandwidth-bound size"))
+    f_cum = lambda: g3.cumsum(d3, "Z", padding="fill")
+    try:
+        out.append(rec("C3-sized Grid.cumsum('Z')", timed(f_cum, 6), cells, 8 * cells, count(f_cum), ""))
+    except Exception as exc:  # keep the bench line alive if an optional record fails
+        out.append({"config": "C3-sized Grid.cumsum('Z')", "error": repr(exc)})
+
+    # ---- C5: Grid.transform Z -> 100 levels (linear, mask_edges), Y-sharded when N > 1 ------------------------
+    m = 100
+    y0, y1 = (0, ny) if world == 1 else (ny * rank // world, ny * (rank + 1) // world)
+    dzf = 10 * 1.05 ** np.arange(nz)
+    depth = (np.cumsum(dzf) - dzf / 2).astype(np.float32)
+    levels = np.linspace(depth[0] - 5, depth[-1] + 5, m).astype(np.float32)
+    ds5 = xg.Dataset(coords={"Z": depth})
+    g5 = xg.Grid(ds5, coords={"Z": {"center": "Z"}}, autoparse_metadata=False)
+    xs = x[:, y0:y1, :].contiguous() if world > 1 else x
+    d5 = xg.DataArray(xs, dims=("Z", "Y", "X"))
+    f_tr = lambda: g5.transform(d5, "Z", levels)
+    cols = (y1 - y0) * nx
+    ms5 = timed(f_tr, 6)
+    r5 = rec("C5 (configs[4]): Grid.transform('Z' -> 100 levels, linear, mask_edges)" + (f", Y sharded x{world}" if world > 1 else ""),
+             ms5, cols * m, cols * (nz + m) * 4, count(f_tr), "cells = output cells; (n + m) * 4 B per column")
+    r5["kernel"] = _capi.last_launch()
+    out.append(r5)
+    del xs, d5
+
+    # ---- C4: >= 32 time steps, each generated on the device, then the six ops of the headline -----------------
+    grid, da = make_dataset(tuple(x.shape), x)
+    nsteps = 32
+    t_first = rank * nsteps  # this rank's block of the time axis
+    torch.cuda.synchronize()
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    gen_ms = []
+    if world > 1:
+        dist.barrier()
+    e[0].record()
+    for t in range(nsteps):
+        g0, g1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        ops.fill_uniform(x, SEED, offset=(t_first + t) * cells)
+        g1_.record()
+        gen_ms.append((g0, g1_))
+        for ax, bc, fill in AXES:
+            for op in OPS:
+                r = getattr(grid, op)(da, ax)
+                del r
+    e[1].record()
+    torch.cuda.synchronize()
+    tot = torch.tensor([e[0].elapsed_time(e[1])], device=dev, dtype=torch.float64)
+    gen = torch.tensor([sum(a.elapsed_time(b) for a, b in gen_ms)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        dist.all_reduce(gen, op=dist.ReduceOp.MAX)
+    tot, gen = float(tot.item()), float(gen.item())
+    out.append({"config": f"C4 (configs[3]) as a {nsteps}-step loop per GPU: generate the step's 75x2400x3600 field on the device, "
+                          f"then the 6 ops (time shards x{world}; the full 365 steps: tools/bench_c4.py)",
+                "ms_per_step_incl_generation": tot / nsteps, "ms_per_step_ops_only": (tot - gen) / nsteps,
+                "cells_per_s": 6 * cells * nsteps * world / (tot * 1e-3),
+                "cells_per_s_ops_only": 6 * cells * nsteps * world / ((tot - gen) * 1e-3),
+                "frac_of_peak_ops_only": 6 * 8 * cells * nsteps / ((tot - gen) * 1e-3) / 1e9 / peak})
+    ops.fill_uniform(x, SEED, offset=rank * cells)  # restore this rank's headline field
+    del flush
+    return out
 
 # --------------------------------------------------------------------------- our arm
 def run_ours(args):
@@ -323,6 +517,13 @@ def run_ours(args):
         "per_op_GBps": {k: alg_bytes / (statistics.median(v) * 1e-3) / 1e9 for k, v in per_kernel.items()},
     }
 
+    extra = None
+    if not args.no_extra:
+        try:
+            extra = run_extras(torch, dist, ops, _capi, x, rank, world, peak)
+        except Exception as exc:  # never lose the headline line to an optional record
+            extra = [{"error": repr(exc)}]
+
     # ---- e2e: host buffers through the public Grid API -----------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -379,7 +580,7 @@ def run_ours(args):
                        "l2": "each field is 2.59 GB in + 2.59 GB out per launch, >> 126 MB L2: no flush needed",
                        "parallelism": f"time-shards x{world} (one field per rank per step, no collective on the data path)"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks,
+            "clocks": clocks, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

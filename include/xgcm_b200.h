@@ -97,6 +97,10 @@ XG_API const char* xg_last_error(void);
 /* Number of kernels this library has launched in this process (all threads). */
 XG_API long long xg_launch_count(void);
 
+/* Label of the kernel the calling thread launched last ("" before any launch): lets tests and the
+ * bench state WHICH code path served a call (e.g. the TMA-staged transform vs its fallback). */
+XG_API const char* xg_last_launch(void);
+
 /* Device properties the host side needs for planning (SM count, L2 bytes). */
 XG_API int xg_device_info(int device, int* sm_count, int64_t* l2_bytes, int64_t* hbm_bytes);
 

@@ -32,6 +32,7 @@ SIGNATURES = {
     "xg_version": (C.c_int, []),
     "xg_last_error": (C.c_char_p, []),
     "xg_launch_count": (C.c_longlong, []),
+    "xg_last_launch": (C.c_char_p, []),
     "xg_device_info": (C.c_int, [C.c_int, C.POINTER(C.c_int), _i64p, _i64p]),
     "xg_stencil2": (
         C.c_int,
@@ -132,3 +133,8 @@ def dtype_code(np_dtype) -> int:
     if dt == np.float64:
         return XG_F64
     raise TypeError(f"xgcm_b200 kernels support float32/float64 fields, got {dt}")
+
+
+def last_launch() -> str:
+    """Label of the kernel this thread launched last (xg_last_launch)."""
+    return load().xg_last_launch().decode("utf-8", "replace")

@@ -10,6 +10,7 @@
 
 static thread_local std::string g_last_error;
 static std::atomic<long long> g_launches{0};
+static thread_local const char* g_last_launch = "";
 
 void xg_set_error(const std::string& msg) { g_last_error = msg; }
 
@@ -24,8 +25,11 @@ int xg_check_launch(const char* what) {
     return xg_fail(XG_ECUDA, std::string(what) + ": " + cudaGetErrorString(e));
   }
   g_launches.fetch_add(1, std::memory_order_relaxed);
+  g_last_launch = what;  // always a string literal
   return XG_OK;
 }
+
+extern "C" const char* xg_last_launch(void) { return g_last_launch; }
 
 extern "C" long long xg_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 

@@ -28,100 +28,14 @@
 //
 // Roofline: HBM, (n + m) * sizeof(T) bytes per column (shared 1-D theta) or
 // (2n + m) * sizeof(T) (theta field).
-#include "xg_common.cuh"
+#include "xg_vinterp.cuh"
 
 namespace {
+using namespace xgvi;
 
 constexpr int kWarps = 8;
-constexpr int kTile = 32;
-constexpr int LIKELY_IN_CACHE_SIZE = 8;
-constexpr int kPrefetchRows = 6;  // theta-field kernel: phi / theta rows pulled into L1 ahead of the walk
 template <typename T>
 constexpr int kCPLv = 1;  // columns per lane in the shared-theta kernel (2 was measured slower: 3.0 vs 2.7 ms at C5)
-
-template <typename T>
-struct InterpArgs {
-  const T* phi;
-  T* out;
-  int64_t outer, n, inner, m;
-  XgOperand theta;
-  XgOperand target;  // levels: shared 1-D vector or one vector per column (axis_stride = level stride)
-  int mask_edges, bypass_checks, logarithmic;
-  int64_t ntiles;    // column tiles of 32
-  bool small_cols;   // outer * inner < 2^31
-};
-
-template <typename T>
-__device__ __forceinline__ T xg_log(T x);
-template <>
-__device__ __forceinline__ float xg_log<float>(float x) { return logf(x); }
-template <>
-__device__ __forceinline__ double xg_log<double>(double x) { return log(x); }
-
-// numba/np binary_search_with_guess (compiled_base.c), literal port over an accessor X(k)
-template <typename F>
-__device__ __forceinline__ int search_with_guess(double key, F X, int len, int guess) {
-  int imin = 0, imax = len;
-  if (key > X(len - 1)) return len;
-  if (key < X(0)) return -1;
-  if (len <= 4) {
-    int i = 1;
-    while (i < len && key >= X(i)) ++i;
-    return i - 1;
-  }
-  if (guess > len - 3) guess = len - 3;
-  if (guess < 1) guess = 1;
-  if (key < X(guess)) {
-    if (key < X(guess - 1)) {
-      imax = guess - 1;
-      if (guess > LIKELY_IN_CACHE_SIZE && key >= X(guess - LIKELY_IN_CACHE_SIZE))
-        imin = guess - LIKELY_IN_CACHE_SIZE;
-    } else {
-      return guess - 1;
-    }
-  } else {
-    if (key < X(guess + 1)) return guess;
-    if (key < X(guess + 2)) return guess + 1;
-    imin = guess + 2;
-    if (guess < len - LIKELY_IN_CACHE_SIZE - 1 && key < X(guess + LIKELY_IN_CACHE_SIZE))
-      imax = guess + LIKELY_IN_CACHE_SIZE;
-  }
-  while (imin < imax) {
-    const int imid = imin + ((imax - imin) >> 1);
-    if (key >= X(imid)) imin = imid + 1;
-    else imax = imid;
-  }
-  return imin - 1;
-}
-
-// the arithmetic of np.interp for one target given its interval (fp64, no contraction)
-__device__ __forceinline__ double interp_value(double x, double xj, double xj1, double yj, double yj1,
-                                               double slope) {
-  double res = slope * (x - xj) + yj;
-  if (res != res) {
-    res = slope * (x - xj1) + yj1;
-    if (res != res && yj == yj1) res = yj;
-  }
-  return res;
-}
-
-// Correctly rounded a / b from r = RN(1/b) with five fp64 operations instead of the ~30 of the
-// generic division (Markstein's FMA-based sequence: q0 = RN(a r) is within 2 ulp, the first
-// correction makes it faithful, and for a faithful q with r within half an ulp of 1/b the second
-// correction q + RN(a - b q) r rounds to exactly RN(a / b)).  Only valid when no intermediate
-// can leave the normal range; the caller guards the exponents of a and b and falls back to `/`.
-__device__ __forceinline__ double div_with_recip(double a, double b, double r) {
-  const double q0 = a * r;
-  const double e0 = fma(-b, q0, a);
-  const double q1 = fma(e0, r, q0);
-  const double e1 = fma(-b, q1, a);
-  return fma(e1, r, q1);
-}
-__device__ __forceinline__ bool exponent_safe(double v) {
-  // |v| in [2^-400, 2^400]: biased exponent in [623, 1423]; false for 0, subnormals, NaN, inf
-  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
-  return (e - 623u) <= 800u;
-}
 
 // transposed write-out of a 32-column x nt-target tile
 template <typename T>
@@ -606,6 +520,10 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
   const size_t plan_bytes = (size_t)(m + nchunk) * sizeof(Run) + (size_t)(m + 2 * v.n) * sizeof(double) +
                             sizeof(T) * kWarps * kCPLv<T> * kTile * (kTile + 1) +
                             (size_t)(2 * m + nchunk + 1 + 4) * sizeof(int);
+  if (all_bcast(a.theta) && all_bcast(a.target)) {
+    const int r = vinterp_shared_tma<T>(a, st);  // bulk-async staged tiles when the layout allows
+    if (r != 0) return r < 0 ? r : XG_OK;
+  }
   if (all_bcast(a.theta) && all_bcast(a.target) && plan_bytes <= 200 * 1024) {
     cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)plan_bytes);

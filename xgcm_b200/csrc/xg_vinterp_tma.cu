@@ -1,0 +1,552 @@
+// xg_vinterp_linear, shared 1-D theta and target (config C5: `Grid.transform(da, 'Z', levels)` with the
+// depth coordinate as theta) — the bulk-async (TMA) staged kernel.
+//
+// Replaces xgcm/transform.py:15-41 (_interp_1d_linear) + :233-249 (linear_interpolation: the new
+// vertical dim is appended LAST) for the layout (outer, n, inner) -> (outer, inner, m).
+//
+// Data movement (the kernel is a tile mover: n x TC in, TC x m out, TC = 32 * CPL columns):
+//   in : one `cp.async.bulk.shared.global` (1-D TMA, SASS UBLKCP) per level row of the tile,
+//        TC * sizeof(T) bytes each, all rows of a tile completing on ONE mbarrier (expect_tx).
+//        Nobody waits on a global load: the columns read their levels from shared memory.
+//   out: the TC x m results of a tile are contiguous in the (outer, inner, m) output, so the tile is
+//        assembled in shared memory with conflict-free 16-byte stores and leaves as ONE
+//        `cp.async.bulk.global.shared` (bulk_group) of TC * m * sizeof(T) bytes.
+//   A block owns a ring of NB >= W input buffers and W output buffers (W = warps).  Local tile i is
+//   computed by warp i % W from buffer i % NB; the warp that finishes tile i refills its buffer with
+//   tile i + NB (it was the buffer's last reader, so no "empty" barrier is needed), which warp
+//   (i + NB) % W picks up (NB - W tiles of lookahead beyond one-buffer-per-warp).
+//
+// Arithmetic: identical to k_vinterp_shared (fp64, rounded once; numpy's slope * (x - xj) + yj with
+// the NaN retries; a correctly rounded slope per (column, interval)).  The per-block plan is
+// target-major: entry t = {x_t - X[j_t] (fp64, column independent), j_t, kind}; the slope of an
+// interval is computed when a target enters it.  ~1900 warp instructions per 32-column tile instead
+// of ~7100 (profiles/): no run bookkeeping, no address arithmetic per level, no global-load waits.
+#include "xg_vinterp.cuh"
+
+#include <cuda.h>  // CUtensorMap types only; the encoder is fetched through cudaGetDriverEntryPoint
+#include <cstdlib>
+
+namespace xgvi {
+namespace {
+
+enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NAN = 4 };
+
+// target t: tpd[t] = x_t - X[j_t] (fp64), tpj[t] = j_t | kind << 24.  A plain PK_INTERP entry is just its
+// interval index, so `tpj[t] == current` is the whole fast-path test (interval unchanged AND nothing
+// special); every other entry carries kind bits and never equals an interval index.
+constexpr int kKindShift = 24;
+struct __align__(16) IntervalPlan {
+  double dxj;  // X[j+1] - X[j]
+  double rr;   // RN(1 / dxj), or 0 when the reciprocal sequence must not be used
+};
+
+// ---- PTX wrappers -----------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "XG_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra XG_DONE;\n"
+      "bra XG_WAIT;\n"
+      "XG_DONE:\n"
+      "}\n" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+}
+// global -> shared: one box of the (outer, n, inner) field (3-D tiled TMA), completes box bytes on the mbarrier
+__device__ __forceinline__ void tensor_load_3d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                               uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(dst),
+      "l"(map), "r"(c0), "r"(c1), "r"(c2), "r"(bar)
+      : "memory");
+}
+// shared -> global, tracked by the bulk async-group of the issuing thread
+__device__ __forceinline__ void bulk_store(void* dst, uint32_t src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+template <typename T>
+__device__ __forceinline__ bool is_finite(T v);
+template <>
+__device__ __forceinline__ bool is_finite<float>(float v) { return fabsf(v) < INFINITY; }
+template <>
+__device__ __forceinline__ bool is_finite<double>(double v) { return fabs(v) < (double)INFINITY; }
+
+template <typename T>
+struct Vec16;  // 16 bytes of T
+template <>
+struct Vec16<float> {
+  static constexpr int N = 4;
+  typedef float4 type;
+};
+template <>
+struct Vec16<double> {
+  static constexpr int N = 2;
+  typedef double2 type;
+};
+
+// tile geometry shared by host and device
+template <typename T, int CPL>
+struct Geo {
+  static constexpr int TC = 32 * CPL;  // columns per tile
+};
+
+template <typename T>
+struct TmaArgs {
+  InterpArgs<T> a;
+  int64_t tiles_per_o;  // ceil(inner / TC)
+  int64_t ntiles;       // outer * tiles_per_o
+  int nb;               // input buffers in the ring (>= warps per block)
+  int box_rows;         // levels per TMA box (<= 256)
+  int nbox;             // boxes per tile: nbox * box_rows >= n
+  unsigned in_bytes;    // nbox * box_rows * TC * sizeof(T), rounded up to 128
+  unsigned out_bytes;   // TC * m * sizeof(T), rounded up to 128
+  unsigned plan_bytes;  // offset of the first tile buffer
+};
+
+// np.interp's NaN retries (arr_interp): only reached when slope * (x - xj) + yj is NaN
+__device__ __noinline__ double interp_retry(double slope, double x, double xj1, double yj, double yj1) {
+  double res = slope * (x - xj1) + yj1;
+  if (res != res && yj == yj1) res = yj;
+  return res;
+}
+
+// slope of one interval when the reciprocal sequence does not apply
+__device__ __noinline__ double slow_slope(double dy, double dxj) { return dy / dxj; }
+
+template <typename T, int CPL>
+__global__ void __launch_bounds__(512, 1)
+    k_vinterp_shared_tma(const __grid_constant__ CUtensorMap tmap, const TmaArgs<T> p) {
+  constexpr int TC = Geo<T, CPL>::TC;
+  constexpr int VN = Vec16<T>::N;
+  typedef typename Vec16<T>::type V16;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const InterpArgs<T>& a = p.a;
+  const int n = (int)a.n, m = (int)a.m;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int W = blockDim.x >> 5, NB = p.nb;
+
+  // layout: iv[n] | tpd[m] | Xs[n] | xt[m] | full[NB] (8 B each) | tpj[m] tj[m] tk[m] flags[4] | pad | in[NB] | out[W]
+  IntervalPlan* iv = reinterpret_cast<IntervalPlan*>(smem_raw);
+  double* tpd = reinterpret_cast<double*>(iv + n);
+  double* Xs = tpd + m;
+  double* xt = Xs + n;
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(xt + m);
+  int* tpj = reinterpret_cast<int*>(full + NB);
+  int* tj = tpj + m;
+  int* tk = tj + m;
+  int* flags = tk + m;
+  unsigned char* in0 = smem_raw + p.plan_bytes;
+  unsigned char* out0 = in0 + (size_t)NB * p.in_bytes;
+  T* out_tile = reinterpret_cast<T*>(out0 + (size_t)w * p.out_bytes);
+  const uint32_t full_u32 = smem_u32(full);
+
+  // ---- tile geometry -----------------------------------------------------------------------------
+  // local tile i of this block = global tile i * gridDim.x + blockIdx.x (blocks sweep the field side by
+  // side, so concurrently processed tiles are neighbours in memory)
+  const int64_t nloc = (p.ntiles > blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto tile_geom = [&](int64_t i, int64_t& o, int64_t& i0, int& ncol) {
+    const int64_t g = i * gridDim.x + blockIdx.x;
+    o = g / p.tiles_per_o;
+    i0 = (g - o * p.tiles_per_o) * TC;
+    const int64_t left = a.inner - i0;
+    ncol = left < TC ? (int)left : TC;
+  };
+  // one elected lane arms the barrier and issues the tile's box copies (out-of-range rows / columns of a
+  // box are zero-filled by the TMA unit and still count towards the transaction bytes)
+  auto issue_load = [&](int64_t i) {
+    if (lane == 0) {
+      const int b = (int)(i % NB);
+      int64_t o, i0;
+      int ncol;
+      tile_geom(i, o, i0, ncol);
+      const uint32_t bar = full_u32 + 8u * b;
+      const unsigned box_bytes = (unsigned)p.box_rows * TC * sizeof(T);
+      mbar_expect_tx(bar, box_bytes * (unsigned)p.nbox);
+      const uint32_t dst = smem_u32(in0 + (size_t)b * p.in_bytes);
+      for (int k = 0; k < p.nbox; ++k) tensor_load_3d(dst + k * box_bytes, &tmap, (int)i0, k * p.box_rows, (int)o, bar);
+    }
+  };
+
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int b = 0; b < NB; ++b) mbar_init(full_u32 + 8u * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  // prologue loads go out before the plan is built
+  for (int64_t i = w; i < NB && i < nloc; i += W) issue_load(i);
+
+  // ---- plan, once per block (same classification as k_vinterp_shared) ------------------------------
+  const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
+  const T* target = reinterpret_cast<const T*>(a.target.ptr);
+  const int64_t tstride = a.theta.axis_stride;
+  for (int k = tid; k < n; k += blockDim.x) {
+    T v = __ldg(theta + k * tstride);
+    if (a.logarithmic) v = xg_log<T>(v);  // transform.py:82-84, in the field dtype
+    Xs[k] = (double)v;
+  }
+  __syncthreads();
+  __shared__ double s_tmin, s_tmax;
+  if (tid == 0) {
+    int flip = 0;
+    if (!a.bypass_checks) {  // transform.py:27-31
+      int kf = 0, kl = n - 1;
+      while (kf < n && Xs[kf] != Xs[kf]) ++kf;
+      while (kl >= 0 && Xs[kl] != Xs[kl]) --kl;
+      if (kf < n && Xs[kl] < Xs[kf]) flip = 1;
+    }
+    bool any = false, nan = false, sorted = true;
+    double tmin = 0.0, tmax = 0.0, prev = 0.0;
+    for (int k = 0; k < n; ++k) {
+      const double v = Xs[flip ? n - 1 - k : k];
+      if (v != v) { nan = true; continue; }
+      if (!any) { tmin = tmax = v; any = true; }
+      else { tmin = v < tmin ? v : tmin; tmax = v > tmax ? v : tmax; if (v < prev) sorted = false; }
+      prev = v;
+    }
+    if (!any) tmin = tmax = NAN;
+    s_tmin = tmin;
+    s_tmax = tmax;
+    flags[0] = flip;
+    flags[1] = (!nan && sorted) ? 1 : 0;
+  }
+  __syncthreads();
+  const int flip = flags[0];
+  const bool sorted = flags[1] != 0;
+  if (flip) {  // reverse in place
+    for (int k = tid; k < n / 2; k += blockDim.x) {
+      const double t0 = Xs[k];
+      Xs[k] = Xs[n - 1 - k];
+      Xs[n - 1 - k] = t0;
+    }
+    __syncthreads();
+  }
+  for (int j = tid; j < n; j += blockDim.x) {
+    IntervalPlan e;
+    e.dxj = 0.0;
+    e.rr = 0.0;
+    if (j + 1 < n) {
+      e.dxj = Xs[j + 1] - Xs[j];
+      // The reciprocal sequence is only used on sorted NaN-free theta (dxj > 0, targets at or right of
+      // X[j]): there a slope whose zero sign differs (dy == -0) cannot change any result, so dy needs
+      // no zero test in the column loop (see advance()).
+      if (sorted && exponent_safe(e.dxj)) e.rr = 1.0 / e.dxj;
+    }
+    iv[j] = e;
+  }
+  auto X = [&](int k) -> double { return Xs[k]; };
+  auto classify = [&](int t, double x, int j) {
+    int kind, jj = -1;
+    if (a.mask_edges && (x < s_tmin || x > s_tmax)) kind = PK_NAN;  // transform.py:38-41
+    else if (x != x) kind = PK_NAN;                                  // np.interp: a NaN target stays NaN
+    else if (j == -1) kind = PK_FIRST;
+    else if (j >= n - 1) kind = PK_LAST;  // right of the range, or exactly the last node
+    else {
+      jj = j;
+      kind = (Xs[j] == x) ? PK_EXACT : PK_INTERP;
+    }
+    xt[t] = x;
+    tj[t] = jj;
+    tk[t] = kind;
+  };
+  auto load_target = [&](int t) -> double {
+    T v = __ldg(target + t * a.target.axis_stride);
+    if (a.logarithmic) v = xg_log<T>(v);
+    return (double)v;
+  };
+  if (sorted) {
+    // NaN-free sorted theta: binary_search_with_guess returns the largest j with X[j] <= x whatever
+    // the guess, so every target can be searched independently
+    for (int t = tid; t < m; t += blockDim.x) {
+      const double x = load_target(t);
+      int j = 0;
+      if (x == x) {
+        if (x > Xs[n - 1]) j = n;
+        else if (x < Xs[0]) j = -1;
+        else {
+          int lo = 0, hi = n;
+          while (lo < hi) {
+            const int mid = lo + ((hi - lo) >> 1);
+            if (x >= Xs[mid]) lo = mid + 1;
+            else hi = mid;
+          }
+          j = lo - 1;
+        }
+      }
+      classify(t, x, j);
+    }
+  } else if (tid == 0) {  // literal replay (guess carried from target to target)
+    int guess = 0;
+    for (int t = 0; t < m; ++t) {
+      const double x = load_target(t);
+      int j = 0;
+      if (x == x) {
+        j = search_with_guess(x, X, n, guess);
+        guess = j;
+      }
+      classify(t, x, j);
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < m; t += blockDim.x) {
+    const int kind = tk[t], j = tj[t] < 0 ? 0 : tj[t];
+    tpd[t] = xt[t] - Xs[j];
+    tpj[t] = j | (kind << kKindShift);
+  }
+  __syncthreads();
+
+  // ---- tiles -----------------------------------------------------------------------------------------
+  const bool vec_out = (m % VN) == 0;
+  // level j of the (possibly flipped) column sits in tile row row0 + j * rstep
+  const int rstep = flip ? -TC : TC;
+  const int row0 = flip ? (n - 1) * TC : 0;
+  for (int64_t i = w; i < nloc; i += W) {
+    const int b = (int)(i % NB);
+    const T* tile = reinterpret_cast<const T*>(in0 + (size_t)b * p.in_bytes) + lane + row0;
+    mbar_wait(full_u32 + 8u * b, (uint32_t)((i / NB) & 1));
+    // the previous bulk store of this warp must have finished READING the output buffer
+    if (lane == 0) bulk_wait_read0();
+    __syncwarp();
+
+    int cj = -2;   // interval whose nodes / slope the registers hold
+    int cjk = -1;  // == cj while every lane of the warp is `clean` on it, else -1 (forces the careful path)
+    double yj[CPL], yj1[CPL], slope[CPL];
+    T raw_a[CPL], raw_b[CPL];  // nodes j, j + 1 as stored (finiteness tests, re-use as the next node j)
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) {
+      yj[c] = yj1[c] = slope[c] = 0.0;
+      raw_a[c] = raw_b[c] = T(0);
+    }
+    // clean(c): both nodes finite and the interval has a usable reciprocal -> slope * dxt + yj cannot be
+    // NaN, and (fp32 fields: |dy| is 0 or within [2^-149, 2^129]) the reciprocal sequence is exact
+    auto advance = [&](int j) {
+      const bool seq = (j == cj + 1);
+      cj = j;
+      const IntervalPlan e = iv[j];
+      const bool rr_ok = __double2hiint(e.rr) != 0;  // rr is 0.0 or a normal number
+      const T* row = tile + j * rstep;
+      bool all = rr_ok;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        const T rb = row[rstep + c * 32];
+        if (seq) {
+          raw_a[c] = raw_b[c];
+          yj[c] = yj1[c];
+        } else {
+          raw_a[c] = row[c * 32];
+          yj[c] = (double)raw_a[c];
+        }
+        raw_b[c] = rb;
+        yj1[c] = (double)rb;
+        const double dy = yj1[c] - yj[c];
+        const bool clean = rr_ok && is_finite<T>(raw_a[c]) && is_finite<T>(rb);
+        bool fast = clean;
+        if constexpr (sizeof(T) == 8) fast = fast && exponent_safe(dy);
+        slope[c] = fast ? div_with_recip(dy, e.dxj, e.rr) : slow_slope(dy, e.dxj);
+        all = all && clean;
+      }
+      cjk = __all_sync(0xffffffffu, all) ? j : -1;
+    };
+    // everything that is not "same clean interval, plain interpolation"; false = go on with the fast path
+    auto careful = [&](int t, int jk, double dxt, T (&v)[CPL]) -> bool {
+      const int kind = jk >> kKindShift, j = jk & ((1 << kKindShift) - 1);
+      if (kind >= PK_FIRST) {
+        const int r = (kind == PK_FIRST) ? 0 : (n - 1) * rstep;
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) v[c] = (kind == PK_NAN) ? T(NAN) : tile[r + c * 32];
+        return true;
+      }
+      if (j != cj) advance(j);
+      if (kind == PK_EXACT) {
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) v[c] = raw_a[c];
+        return true;
+      }
+      if (cjk == j) return false;
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) {
+        double res = slope[c] * dxt + yj[c];
+        if (res != res) res = interp_retry(slope[c], xt[t], Xs[j + 1], yj[c], yj1[c]);
+        v[c] = (T)res;
+      }
+      return true;
+    };
+    auto one_target = [&](int t, T (&v)[CPL]) {
+      const double dxt = tpd[t];
+      const int jk = tpj[t];
+      if (jk != cjk) {
+        if (careful(t, jk, dxt, v)) return;
+      }
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) v[c] = (T)(slope[c] * dxt + yj[c]);
+    };
+    int t = 0;
+    if (vec_out) {
+#pragma unroll 1
+      for (; t + 4 <= m; t += 4) {
+        T v[4][CPL];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) one_target(t + q, v[q]);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          T* o = out_tile + (size_t)(c * 32 + lane) * m + t;
+          if constexpr (VN == 4) {
+            *reinterpret_cast<V16*>(o) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
+          } else {
+            *reinterpret_cast<V16*>(o) = make_double2(v[0][c], v[1][c]);
+            *reinterpret_cast<V16*>(o + 2) = make_double2(v[2][c], v[3][c]);
+          }
+        }
+      }
+    }
+#pragma unroll 1
+    for (; t < m; ++t) {
+      T v[CPL];
+      one_target(t, v);
+#pragma unroll
+      for (int c = 0; c < CPL; ++c) out_tile[(size_t)(c * 32 + lane) * m + t] = v[c];
+    }
+
+    // ---- tile done: results out as one bulk store, buffer refilled with tile i + NB --------------------
+    fence_async_smem();  // this lane's STS -> visible to the async proxy
+    __syncwarp();        // ... for all lanes; also: every lane is done reading the input buffer
+    if (lane == 0) {
+      int64_t o, i0;
+      int ncol;
+      tile_geom(i, o, i0, ncol);
+      bulk_store(a.out + (o * a.inner + i0) * a.m, smem_u32(out_tile), (unsigned)ncol * (unsigned)m * sizeof(T));
+      bulk_commit();
+    }
+    if (i + NB < nloc) issue_load(i + NB);
+  }
+  if (lane == 0) bulk_wait_read0();
+}
+
+int env_int(const char* name, int dflt) {
+  const char* s = getenv(name);
+  return (s && *s) ? atoi(s) : dflt;
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = []() -> EncodeTiledFn {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q = cudaDriverEntryPointSymbolNotFound;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      return nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+template <typename T, int CPL>
+int launch_shared(const InterpArgs<T>& a, cudaStream_t st, int sms, int smem_max) {
+  constexpr int TC = Geo<T, CPL>::TC;
+  TmaArgs<T> p;
+  p.a = a;
+  const int n = (int)a.n, m = (int)a.m;
+  p.tiles_per_o = xg_ceil_div(a.inner, TC);
+  p.ntiles = a.outer * p.tiles_per_o;
+  p.nbox = (int)xg_ceil_div(n, 256);
+  p.box_rows = (int)xg_ceil_div(n, p.nbox);
+  auto up128 = [](size_t v) { return (unsigned)((v + 127) / 128 * 128); };
+  p.in_bytes = up128((size_t)p.nbox * p.box_rows * TC * sizeof(T));
+  p.out_bytes = up128((size_t)TC * m * sizeof(T));
+  // choose W warps and NB buffers: as many warps as fit with `extra` buffers of lookahead
+  const int want_w = env_int("XG_VINTERP_W", 0), want_extra = env_int("XG_VINTERP_EXTRA", 2);
+  int best_w = 0, best_nb = 0;
+  unsigned best_plan = 0;
+  for (int W = 16; W >= 1 && !best_w; --W) {
+    if (want_w && W != want_w) continue;
+    for (int extra = want_extra; extra >= 0; --extra) {
+      const int NB = W + extra;
+      const size_t plan = (size_t)n * sizeof(IntervalPlan) + (size_t)(n + 2 * m) * sizeof(double) + (size_t)NB * 8 +
+                          (size_t)(3 * m + 4) * sizeof(int);
+      const unsigned plan_b = up128(plan);
+      const size_t total = plan_b + (size_t)NB * p.in_bytes + (size_t)W * p.out_bytes;
+      if (total + 64 <= (size_t)smem_max) {  // + the static s_tmin / s_tmax
+        best_w = W;
+        best_nb = NB;
+        best_plan = plan_b;
+        break;
+      }
+    }
+  }
+  if (!best_w) return 0;
+  p.nb = best_nb;
+  p.plan_bytes = best_plan;
+
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return 0;
+  CUtensorMap map;
+  const cuuint64_t gdim[3] = {(cuuint64_t)a.inner, (cuuint64_t)a.n, (cuuint64_t)a.outer};
+  const cuuint64_t gstr[2] = {(cuuint64_t)a.inner * sizeof(T), (cuuint64_t)a.n * a.inner * sizeof(T)};
+  const cuuint32_t box[3] = {(cuuint32_t)TC, (cuuint32_t)p.box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  const CUresult cr = enc(&map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+                          const_cast<T*>(a.phi), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) return 0;  // e.g. a stride beyond the descriptor's range: plain kernel
+
+  const size_t smem = best_plan + (size_t)best_nb * p.in_bytes + (size_t)best_w * p.out_bytes;
+  cudaError_t e = cudaFuncSetAttribute(k_vinterp_shared_tma<T, CPL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem);
+  if (e != cudaSuccess) return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  int64_t blocks = xg_ceil_div(p.ntiles, best_w);
+  if (blocks > sms) blocks = sms;
+  k_vinterp_shared_tma<T, CPL><<<(unsigned)blocks, best_w * 32, smem, st>>>(map, p);
+  const int rc = xg_check_launch("xg_vinterp_linear(shared, tma)");
+  return rc ? rc : 1;
+}
+
+}  // namespace
+
+template <typename T>
+int vinterp_shared_tma(const InterpArgs<T>& a, cudaStream_t st) {
+  if (env_int("XG_VINTERP_TMA", 1) == 0) return 0;
+  const int n = (int)a.n;
+  if (n < 2) return 0;  // np.interp's single-node rule lives in the fallback kernel
+  // TMA needs 16-byte aligned global strides and base; the bulk store 16-byte aligned tile starts
+  if ((a.inner * sizeof(T)) % 16 != 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(a.phi) | reinterpret_cast<uintptr_t>(a.out)) & 15) return 0;
+  if (a.inner < 32 || a.inner >= (1ll << 31) || a.outer >= (1ll << 31)) return 0;
+  int dev = 0, sms = 148, smem_max = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int cpl = env_int("XG_VINTERP_CPL", 1);
+  if (cpl == 2) return launch_shared<T, 2>(a, st, sms, smem_max);
+  return launch_shared<T, 1>(a, st, sms, smem_max);
+}
+
+template <typename T>
+int vinterp_columns_tma(const InterpArgs<T>&, cudaStream_t) {
+  return 0;
+}
+
+template int vinterp_shared_tma<float>(const InterpArgs<float>&, cudaStream_t);
+template int vinterp_shared_tma<double>(const InterpArgs<double>&, cudaStream_t);
+template int vinterp_columns_tma<float>(const InterpArgs<float>&, cudaStream_t);
+template int vinterp_columns_tma<double>(const InterpArgs<double>&, cudaStream_t);
+
+}  // namespace xgvi
