@@ -25,15 +25,15 @@ x = torch.empty((nz, ny, nx), dtype=torch.float32, device="cuda")
 ops.fill_uniform(x, 0xC0FFEE)
 peak = json.load(open(os.path.join(os.path.dirname(__file__), "..", "MEASURED_PEAKS.json")))["hbm_gbs"]
 nbytes = ny * nx * (nz + m) * 4
-variants = sys.argv[1:] or ["plain", "1:0:2", "1:8:2", "1:9:1", "1:9:2", "1:10:0", "2:4:2", "2:4:1", "2:5:0", "2:3:2"]
+variants = sys.argv[1:] or ["plain", "1:0:2:0", "1:9:2:3", "1:8:2:4", "1:8:2:2", "1:8:2:3", "1:10:0:3", "1:7:2:4", "1:6:2:5", "2:4:2:4", "2:4:2:8", "2:5:0:6"]
 ref = None
 for v in variants:
-    for k in ("XG_VINTERP_TMA", "XG_VINTERP_CPL", "XG_VINTERP_W", "XG_VINTERP_EXTRA"): os.environ.pop(k, None)
+    for k in ("XG_VINTERP_TMA", "XG_VINTERP_CPL", "XG_VINTERP_W", "XG_VINTERP_EXTRA", "XG_VINTERP_WT"): os.environ.pop(k, None)
     if v == "plain":
         os.environ["XG_VINTERP_TMA"] = "0"
     else:
-        cpl, w, extra = v.split(":")
-        os.environ.update(XG_VINTERP_CPL=cpl, XG_VINTERP_W=w, XG_VINTERP_EXTRA=extra)
+        cpl, w, extra, wt = v.split(":")  # columns per lane : teams (0 = auto) : lookahead buffers : warps per team (0 = auto)
+        os.environ.update(XG_VINTERP_CPL=cpl, XG_VINTERP_W=w, XG_VINTERP_EXTRA=extra, XG_VINTERP_WT=wt)
     out = ops.vinterp_linear(x, depth, target, 0, True)
     path = _capi.last_launch()
     chk = out[::97, ::89].double().nan_to_num(nan=-7.0).sum().item()

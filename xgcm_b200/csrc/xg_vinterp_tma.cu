@@ -11,10 +11,13 @@
 //   out: the TC x m results of a tile are contiguous in the (outer, inner, m) output, so the tile is
 //        assembled in shared memory with conflict-free 16-byte stores and leaves as ONE
 //        `cp.async.bulk.global.shared` (bulk_group) of TC * m * sizeof(T) bytes.
-//   A block owns a ring of NB >= W input buffers and W output buffers (W = warps).  Local tile i is
-//   computed by warp i % W from buffer i % NB; the warp that finishes tile i refills its buffer with
-//   tile i + NB (it was the buffer's last reader, so no "empty" barrier is needed), which warp
-//   (i + NB) % W picks up (NB - W tiles of lookahead beyond one-buffer-per-warp).
+//   A block is NT teams of WT warps; it owns a ring of NB >= NT input buffers and NT output buffers.
+//   Local tile i is computed by team i % NT from buffer i % NB, the WT warps of the team splitting the
+//   TARGETS of the tile between them (shared memory, not registers, limits how many columns an SM can
+//   hold — ~300 — so the warps needed to hide the fp64 dependency chains have to come from splitting
+//   each tile's work, profiles/r2_vtma_*).  The team that finishes tile i refills its buffer with tile
+//   i + NB (it was the buffer's last reader, so no "empty" barrier is needed), which team (i + NB) % NT
+//   picks up (NB - NT tiles of lookahead beyond one-buffer-per-team).
 //
 // Arithmetic: identical to k_vinterp_shared (fp64, rounded once; numpy's slope * (x - xj) + yj with
 // the NaN retries; a correctly rounded slope per (column, interval)).  The per-block plan is
@@ -31,10 +34,16 @@ namespace {
 
 enum { PK_INTERP = 0, PK_EXACT = 1, PK_FIRST = 2, PK_LAST = 3, PK_NAN = 4 };
 
-// target t: tpd[t] = x_t - X[j_t] (fp64), tpj[t] = j_t | kind << 24.  A plain PK_INTERP entry is just its
-// interval index, so `tpj[t] == current` is the whole fast-path test (interval unchanged AND nothing
+// target t: {x_t - X[j_t] (fp64), j_t | kind << 24}.  A plain PK_INTERP entry is just its interval index,
+// so `entry.jk == current` is the whole fast-path test (interval unchanged, every lane clean, nothing
 // special); every other entry carries kind bits and never equals an interval index.
 constexpr int kKindShift = 24;
+constexpr int kUnclean = 1 << 23;  // state flag: the current interval needs the careful path in some lane
+struct __align__(16) TargetPlan {
+  double dxt;
+  int jk;
+  int pad;
+};
 struct __align__(16) IntervalPlan {
   double dxj;  // X[j+1] - X[j]
   double rr;   // RN(1 / dxj), or 0 when the reciprocal sequence must not be used
@@ -110,7 +119,9 @@ struct TmaArgs {
   InterpArgs<T> a;
   int64_t tiles_per_o;  // ceil(inner / TC)
   int64_t ntiles;       // outer * tiles_per_o
-  int nb;               // input buffers in the ring (>= warps per block)
+  int nb;               // input buffers in the ring (>= teams per block)
+  int wt;               // warps per team
+  bool small;           // tile indices fit in 32 bits
   int box_rows;         // levels per TMA box (<= 256)
   int nbox;             // boxes per tile: nbox * box_rows >= n
   unsigned in_bytes;    // nbox * box_rows * TC * sizeof(T), rounded up to 128
@@ -129,30 +140,30 @@ __device__ __noinline__ double interp_retry(double slope, double x, double xj1, 
 __device__ __noinline__ double slow_slope(double dy, double dxj) { return dy / dxj; }
 
 template <typename T, int CPL>
-__global__ void __launch_bounds__(512, 1)
+__global__ void __launch_bounds__(1024, 1)
     k_vinterp_shared_tma(const __grid_constant__ CUtensorMap tmap, const TmaArgs<T> p) {
   constexpr int TC = Geo<T, CPL>::TC;
-  constexpr int VN = Vec16<T>::N;
-  typedef typename Vec16<T>::type V16;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const InterpArgs<T>& a = p.a;
   const int n = (int)a.n, m = (int)a.m;
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int W = blockDim.x >> 5, NB = p.nb;
 
-  // layout: iv[n] | tpd[m] | Xs[n] | xt[m] | full[NB] (8 B each) | tpj[m] tj[m] tk[m] flags[4] | pad | in[NB] | out[W]
-  IntervalPlan* iv = reinterpret_cast<IntervalPlan*>(smem_raw);
-  double* tpd = reinterpret_cast<double*>(iv + n);
-  double* Xs = tpd + m;
+  // layout: tp[m] | iv[n] | Xs[n] | xt[m] | full[NB] (8 B each) | tj[m] tk[m] flags[4] wbeg[33] | pad | in[NB] | out[NT]
+  TargetPlan* tp = reinterpret_cast<TargetPlan*>(smem_raw);
+  IntervalPlan* iv = reinterpret_cast<IntervalPlan*>(tp + m);
+  double* Xs = reinterpret_cast<double*>(iv + n);
   double* xt = Xs + n;
   unsigned long long* full = reinterpret_cast<unsigned long long*>(xt + m);
-  int* tpj = reinterpret_cast<int*>(full + NB);
-  int* tj = tpj + m;
+  int* tj = reinterpret_cast<int*>(full + NB);
   int* tk = tj + m;
   int* flags = tk + m;
+  int* wbeg = flags + 4;  // target range of warp q of a team: [wbeg[q], wbeg[q + 1])
+  const int WT = p.wt, NT = W / WT;
+  const int team = w / WT, wq = w - team * WT;  // this warp's team and its rank in the team
   unsigned char* in0 = smem_raw + p.plan_bytes;
   unsigned char* out0 = in0 + (size_t)NB * p.in_bytes;
-  T* out_tile = reinterpret_cast<T*>(out0 + (size_t)w * p.out_bytes);
+  T* out_tile = reinterpret_cast<T*>(out0 + (size_t)team * p.out_bytes);
   const uint32_t full_u32 = smem_u32(full);
 
   // ---- tile geometry -----------------------------------------------------------------------------
@@ -161,25 +172,29 @@ __global__ void __launch_bounds__(512, 1)
   const int64_t nloc = (p.ntiles > blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   auto tile_geom = [&](int64_t i, int64_t& o, int64_t& i0, int& ncol) {
     const int64_t g = i * gridDim.x + blockIdx.x;
-    o = g / p.tiles_per_o;
-    i0 = (g - o * p.tiles_per_o) * TC;
+    if (p.small) {
+      const uint32_t oo = (uint32_t)g / (uint32_t)p.tiles_per_o;
+      o = oo;
+      i0 = (int64_t)((uint32_t)g - oo * (uint32_t)p.tiles_per_o) * TC;
+    } else {
+      o = g / p.tiles_per_o;
+      i0 = (g - o * p.tiles_per_o) * TC;
+    }
     const int64_t left = a.inner - i0;
     ncol = left < TC ? (int)left : TC;
   };
   // one elected lane arms the barrier and issues the tile's box copies (out-of-range rows / columns of a
   // box are zero-filled by the TMA unit and still count towards the transaction bytes)
   auto issue_load = [&](int64_t i) {
-    if (lane == 0) {
-      const int b = (int)(i % NB);
-      int64_t o, i0;
-      int ncol;
-      tile_geom(i, o, i0, ncol);
-      const uint32_t bar = full_u32 + 8u * b;
-      const unsigned box_bytes = (unsigned)p.box_rows * TC * sizeof(T);
-      mbar_expect_tx(bar, box_bytes * (unsigned)p.nbox);
-      const uint32_t dst = smem_u32(in0 + (size_t)b * p.in_bytes);
-      for (int k = 0; k < p.nbox; ++k) tensor_load_3d(dst + k * box_bytes, &tmap, (int)i0, k * p.box_rows, (int)o, bar);
-    }
+    const int b = (int)(i % NB);
+    int64_t o, i0;
+    int ncol;
+    tile_geom(i, o, i0, ncol);
+    const uint32_t bar = full_u32 + 8u * b;
+    const unsigned box_bytes = (unsigned)p.box_rows * TC * sizeof(T);
+    mbar_expect_tx(bar, box_bytes * (unsigned)p.nbox);
+    const uint32_t dst = smem_u32(in0 + (size_t)b * p.in_bytes);
+    for (int k = 0; k < p.nbox; ++k) tensor_load_3d(dst + k * box_bytes, &tmap, (int)i0, k * p.box_rows, (int)o, bar);
   };
 
   if (tid == 0) {
@@ -189,7 +204,8 @@ __global__ void __launch_bounds__(512, 1)
   }
   __syncthreads();
   // prologue loads go out before the plan is built
-  for (int64_t i = w; i < NB && i < nloc; i += W) issue_load(i);
+  if (wq == 0 && lane == 0)
+    for (int64_t i = team; i < NB && i < nloc; i += NT) issue_load(i);
 
   // ---- plan, once per block (same classification as k_vinterp_shared) ------------------------------
   const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
@@ -305,136 +321,151 @@ __global__ void __launch_bounds__(512, 1)
   __syncthreads();
   for (int t = tid; t < m; t += blockDim.x) {
     const int kind = tk[t], j = tj[t] < 0 ? 0 : tj[t];
-    tpd[t] = xt[t] - Xs[j];
-    tpj[t] = j | (kind << kKindShift);
+    TargetPlan e;
+    e.dxt = xt[t] - Xs[j];
+    e.jk = j | (kind << kKindShift);
+    e.pad = 0;
+    tp[t] = e;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    // Split the targets between the WT warps of a team in contiguous runs of equal estimated cost: a plain
+    // target costs ~1, entering a new interval ~4 more (two node loads + conversions + the slope's
+    // reciprocal sequence per column).  Units of 2 targets (one 8 / 16-byte store each) when m is even.
+    const int unit = (m % 2 == 0) ? 2 : 1;
+    int total = 0;
+    for (int t = 0; t < m; ++t) total += 1 + ((t == 0 || tp[t].jk != tp[t - 1].jk) ? 4 : 0);
+    int acc = 0, q = 1;
+    wbeg[0] = 0;
+    for (int t = 0; t < m && q < WT; ++t) {
+      acc += 1 + ((t == 0 || tp[t].jk != tp[t - 1].jk) ? 4 : 0);
+      if ((t + 1) % unit == 0 && (int64_t)acc * WT >= (int64_t)total * q) wbeg[q++] = t + 1;
+    }
+    for (; q <= WT; ++q) wbeg[q] = m;
   }
   __syncthreads();
 
   // ---- tiles -----------------------------------------------------------------------------------------
-  const bool vec_out = (m % VN) == 0;
+  const bool pair_ok = (m % 2) == 0;
+  const int t_begin = wbeg[wq], t_end = wbeg[wq + 1];
+  const uint32_t team_bar = 1 + team;          // named barrier of the team
+  const uint32_t team_threads = 32u * WT;
+  auto team_sync = [&]() {
+    if (WT > 1) asm volatile("bar.sync %0, %1;" ::"r"(team_bar), "r"(team_threads) : "memory");
+    else __syncwarp();
+  };
   // level j of the (possibly flipped) column sits in tile row row0 + j * rstep
   const int rstep = flip ? -TC : TC;
   const int row0 = flip ? (n - 1) * TC : 0;
-  for (int64_t i = w; i < nloc; i += W) {
-    const int b = (int)(i % NB);
+  const int jmask = kUnclean - 1;
+  int b = team % NB;       // ring buffer of the current tile (local tile i lives in buffer i % NB)
+  uint32_t phase = 0;      // parity of that buffer's current use ((i / NB) & 1)
+  for (int64_t i = team; i < nloc; i += NT) {
     const T* tile = reinterpret_cast<const T*>(in0 + (size_t)b * p.in_bytes) + lane + row0;
-    mbar_wait(full_u32 + 8u * b, (uint32_t)((i / NB) & 1));
-    // the previous bulk store of this warp must have finished READING the output buffer
-    if (lane == 0) bulk_wait_read0();
-    __syncwarp();
-
-    int cj = -2;   // interval whose nodes / slope the registers hold
-    int cjk = -1;  // == cj while every lane of the warp is `clean` on it, else -1 (forces the careful path)
-    double yj[CPL], yj1[CPL], slope[CPL];
-    T raw_a[CPL], raw_b[CPL];  // nodes j, j + 1 as stored (finiteness tests, re-use as the next node j)
-#pragma unroll
-    for (int c = 0; c < CPL; ++c) {
-      yj[c] = yj1[c] = slope[c] = 0.0;
-      raw_a[c] = raw_b[c] = T(0);
+    // the team's previous bulk store must have finished READING the output buffer before anyone writes it
+    if (wq == 0 && lane == 0) bulk_wait_read0();
+    mbar_wait(full_u32 + 8u * b, phase);
+    team_sync();
+    b += NT;
+    if (b >= NB) {
+      b -= NB;
+      phase ^= 1u;
     }
+
+    // State: `cur` = j (every lane clean on interval j: plain targets take the fast path), j | kUnclean
+    // (interval loaded, some lane must go the careful way), or -1 (nothing loaded).
+    int cur = -1;
+    double yj[CPL], slope[CPL];
+#pragma unroll
+    for (int c = 0; c < CPL; ++c) yj[c] = slope[c] = 0.0;
     // clean(c): both nodes finite and the interval has a usable reciprocal -> slope * dxt + yj cannot be
     // NaN, and (fp32 fields: |dy| is 0 or within [2^-149, 2^129]) the reciprocal sequence is exact
     auto advance = [&](int j) {
-      const bool seq = (j == cj + 1);
-      cj = j;
       const IntervalPlan e = iv[j];
       const bool rr_ok = __double2hiint(e.rr) != 0;  // rr is 0.0 or a normal number
       const T* row = tile + j * rstep;
       bool all = rr_ok;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
-        const T rb = row[rstep + c * 32];
-        if (seq) {
-          raw_a[c] = raw_b[c];
-          yj[c] = yj1[c];
-        } else {
-          raw_a[c] = row[c * 32];
-          yj[c] = (double)raw_a[c];
-        }
-        raw_b[c] = rb;
-        yj1[c] = (double)rb;
-        const double dy = yj1[c] - yj[c];
-        const bool clean = rr_ok && is_finite<T>(raw_a[c]) && is_finite<T>(rb);
+        const T ra = row[c * 32], rb = row[rstep + c * 32];
+        yj[c] = (double)ra;
+        const double dy = (double)rb - yj[c];
+        const bool clean = rr_ok && is_finite<T>(ra) && is_finite<T>(rb);
         bool fast = clean;
         if constexpr (sizeof(T) == 8) fast = fast && exponent_safe(dy);
         slope[c] = fast ? div_with_recip(dy, e.dxj, e.rr) : slow_slope(dy, e.dxj);
         all = all && clean;
       }
-      cjk = __all_sync(0xffffffffu, all) ? j : -1;
+      cur = __all_sync(0xffffffffu, all) ? j : (j | kUnclean);
     };
     // everything that is not "same clean interval, plain interpolation"; false = go on with the fast path
     auto careful = [&](int t, int jk, double dxt, T (&v)[CPL]) -> bool {
-      const int kind = jk >> kKindShift, j = jk & ((1 << kKindShift) - 1);
+      const int kind = jk >> kKindShift, j = jk & jmask;
       if (kind >= PK_FIRST) {
         const int r = (kind == PK_FIRST) ? 0 : (n - 1) * rstep;
 #pragma unroll
         for (int c = 0; c < CPL; ++c) v[c] = (kind == PK_NAN) ? T(NAN) : tile[r + c * 32];
         return true;
       }
-      if (j != cj) advance(j);
+      if (cur < 0 || j != (cur & jmask)) advance(j);
       if (kind == PK_EXACT) {
 #pragma unroll
-        for (int c = 0; c < CPL; ++c) v[c] = raw_a[c];
+        for (int c = 0; c < CPL; ++c) v[c] = tile[j * rstep + c * 32];
         return true;
       }
-      if (cjk == j) return false;
+      if (cur == j) return false;
 #pragma unroll
       for (int c = 0; c < CPL; ++c) {
         double res = slope[c] * dxt + yj[c];
-        if (res != res) res = interp_retry(slope[c], xt[t], Xs[j + 1], yj[c], yj1[c]);
+        if (res != res) res = interp_retry(slope[c], xt[t], Xs[j + 1], yj[c], (double)tile[(j + 1) * rstep + c * 32]);
         v[c] = (T)res;
       }
       return true;
     };
     auto one_target = [&](int t, T (&v)[CPL]) {
-      const double dxt = tpd[t];
-      const int jk = tpj[t];
-      if (jk != cjk) {
-        if (careful(t, jk, dxt, v)) return;
+      const TargetPlan e = tp[t];
+      if (e.jk != cur) {
+        if (careful(t, e.jk, e.dxt, v)) return;
       }
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) v[c] = (T)(slope[c] * dxt + yj[c]);
+      for (int c = 0; c < CPL; ++c) v[c] = (T)(slope[c] * e.dxt + yj[c]);
     };
-    int t = 0;
-    if (vec_out) {
+    if (pair_ok) {
 #pragma unroll 1
-      for (; t + 4 <= m; t += 4) {
-        T v[4][CPL];
+      for (int t = t_begin; t < t_end; t += 2) {
+        T v[2][CPL];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) one_target(t + q, v[q]);
+        for (int q = 0; q < 2; ++q) one_target(t + q, v[q]);
 #pragma unroll
         for (int c = 0; c < CPL; ++c) {
           T* o = out_tile + (size_t)(c * 32 + lane) * m + t;
-          if constexpr (VN == 4) {
-            *reinterpret_cast<V16*>(o) = make_float4(v[0][c], v[1][c], v[2][c], v[3][c]);
-          } else {
-            *reinterpret_cast<V16*>(o) = make_double2(v[0][c], v[1][c]);
-            *reinterpret_cast<V16*>(o + 2) = make_double2(v[2][c], v[3][c]);
-          }
+          if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(o) = make_float2(v[0][c], v[1][c]);
+          else *reinterpret_cast<double2*>(o) = make_double2(v[0][c], v[1][c]);
         }
       }
-    }
+    } else {
 #pragma unroll 1
-    for (; t < m; ++t) {
-      T v[CPL];
-      one_target(t, v);
+      for (int t = t_begin; t < t_end; ++t) {
+        T v[CPL];
+        one_target(t, v);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) out_tile[(size_t)(c * 32 + lane) * m + t] = v[c];
+        for (int c = 0; c < CPL; ++c) out_tile[(size_t)(c * 32 + lane) * m + t] = v[c];
+      }
     }
 
     // ---- tile done: results out as one bulk store, buffer refilled with tile i + NB --------------------
     fence_async_smem();  // this lane's STS -> visible to the async proxy
-    __syncwarp();        // ... for all lanes; also: every lane is done reading the input buffer
-    if (lane == 0) {
+    team_sync();         // ... for the whole team; also: everybody is done reading the input buffer
+    if (wq == 0 && lane == 0) {
       int64_t o, i0;
       int ncol;
       tile_geom(i, o, i0, ncol);
       bulk_store(a.out + (o * a.inner + i0) * a.m, smem_u32(out_tile), (unsigned)ncol * (unsigned)m * sizeof(T));
       bulk_commit();
+      if (i + NB < nloc) issue_load(i + NB);
     }
-    if (i + NB < nloc) issue_load(i + NB);
   }
-  if (lane == 0) bulk_wait_read0();
+  if (wq == 0 && lane == 0) bulk_wait_read0();
 }
 
 int env_int(const char* name, int dflt) {
@@ -471,20 +502,21 @@ int launch_shared(const InterpArgs<T>& a, cudaStream_t st, int sms, int smem_max
   auto up128 = [](size_t v) { return (unsigned)((v + 127) / 128 * 128); };
   p.in_bytes = up128((size_t)p.nbox * p.box_rows * TC * sizeof(T));
   p.out_bytes = up128((size_t)TC * m * sizeof(T));
-  // choose W warps and NB buffers: as many warps as fit with `extra` buffers of lookahead
-  const int want_w = env_int("XG_VINTERP_W", 0), want_extra = env_int("XG_VINTERP_EXTRA", 2);
+  // choose NT teams (tiles in flight) and NB buffers: as many teams as fit with `extra` buffers of lookahead
+  // (named barriers: at most 15 teams), then WT warps per team up to 16 warps per block
+  const int want_nt = env_int("XG_VINTERP_W", 0), want_extra = env_int("XG_VINTERP_EXTRA", 2);
   int best_w = 0, best_nb = 0;
   unsigned best_plan = 0;
-  for (int W = 16; W >= 1 && !best_w; --W) {
-    if (want_w && W != want_w) continue;
+  for (int NT = 15; NT >= 1 && !best_w; --NT) {
+    if (want_nt && NT != want_nt) continue;
     for (int extra = want_extra; extra >= 0; --extra) {
-      const int NB = W + extra;
-      const size_t plan = (size_t)n * sizeof(IntervalPlan) + (size_t)(n + 2 * m) * sizeof(double) + (size_t)NB * 8 +
-                          (size_t)(3 * m + 4) * sizeof(int);
+      const int NB = NT + extra;
+      const size_t plan = (size_t)m * sizeof(TargetPlan) + (size_t)n * sizeof(IntervalPlan) +
+                          (size_t)(n + m) * sizeof(double) + (size_t)NB * 8 + (size_t)(2 * m + 4 + 33) * sizeof(int);
       const unsigned plan_b = up128(plan);
-      const size_t total = plan_b + (size_t)NB * p.in_bytes + (size_t)W * p.out_bytes;
+      const size_t total = plan_b + (size_t)NB * p.in_bytes + (size_t)NT * p.out_bytes;
       if (total + 64 <= (size_t)smem_max) {  // + the static s_tmin / s_tmax
-        best_w = W;
+        best_w = NT;
         best_nb = NB;
         best_plan = plan_b;
         break;
@@ -492,6 +524,16 @@ int launch_shared(const InterpArgs<T>& a, cudaStream_t st, int sms, int smem_max
     }
   }
   if (!best_w) return 0;
+  int wt = env_int("XG_VINTERP_WT", 0);
+  if (wt <= 0) {
+    wt = 32 / best_w;                     // up to 32 warps per block
+    const int units = (int)(m / 2);       // a warp wants at least 2 pairs of targets
+    while (wt > 1 && units / wt < 2) --wt;
+  }
+  if (wt < 1) wt = 1;
+  while (wt > 1 && best_w * wt > 32) --wt;
+  p.wt = wt;
+  p.small = p.ntiles < (1ll << 31);
   p.nb = best_nb;
   p.plan_bytes = best_plan;
 
@@ -514,7 +556,7 @@ int launch_shared(const InterpArgs<T>& a, cudaStream_t st, int sms, int smem_max
   if (e != cudaSuccess) return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
   int64_t blocks = xg_ceil_div(p.ntiles, best_w);
   if (blocks > sms) blocks = sms;
-  k_vinterp_shared_tma<T, CPL><<<(unsigned)blocks, best_w * 32, smem, st>>>(map, p);
+  k_vinterp_shared_tma<T, CPL><<<(unsigned)blocks, best_w * wt * 32, smem, st>>>(map, p);
   const int rc = xg_check_launch("xg_vinterp_linear(shared, tma)");
   return rc ? rc : 1;
 }
@@ -525,7 +567,7 @@ template <typename T>
 int vinterp_shared_tma(const InterpArgs<T>& a, cudaStream_t st) {
   if (env_int("XG_VINTERP_TMA", 1) == 0) return 0;
   const int n = (int)a.n;
-  if (n < 2) return 0;  // np.interp's single-node rule lives in the fallback kernel
+  if (n < 2 || n >= kUnclean) return 0;  // np.interp's single-node rule lives in the fallback kernel
   // TMA needs 16-byte aligned global strides and base; the bulk store 16-byte aligned tile starts
   if ((a.inner * sizeof(T)) % 16 != 0) return 0;
   if ((reinterpret_cast<uintptr_t>(a.phi) | reinterpret_cast<uintptr_t>(a.out)) & 15) return 0;
@@ -534,8 +576,14 @@ int vinterp_shared_tma(const InterpArgs<T>& a, cudaStream_t st) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  const int cpl = env_int("XG_VINTERP_CPL", 1);
-  if (cpl == 2) return launch_shared<T, 2>(a, st, sms, smem_max);
+  // columns per lane: 2 (64-column tiles) halves the per-column share of the plan reads and loop control, as
+  // long as four or so tiles (n levels in + m targets out each) still fit in shared memory
+  int cpl = env_int("XG_VINTERP_CPL", 0);
+  if (cpl <= 0) cpl = ((size_t)(a.n + a.m) * 64 * sizeof(T) <= 48 * 1024) ? 2 : 1;
+  if (cpl == 2) {
+    const int r = launch_shared<T, 2>(a, st, sms, smem_max);
+    if (r != 0) return r;
+  }
   return launch_shared<T, 1>(a, st, sms, smem_max);
 }
 
