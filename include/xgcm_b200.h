@@ -85,10 +85,12 @@ typedef enum {
 /* grid.py:1326-1383 trim table of cumsum */
 typedef enum { XG_TRIM_NONE = 0, XG_TRIM_DROP_LAST = 1, XG_TRIM_DROP_FIRST = 2 } xg_trim;
 
-typedef enum { XG_REDUCE_SUM = 0, XG_REDUCE_MEAN = 1 } xg_reduce_mode;
+/* WVALID: sum of the weights of the cells the MEAN would keep (its denominator), for multi-axis means. */
+typedef enum { XG_REDUCE_SUM = 0, XG_REDUCE_MEAN = 1, XG_REDUCE_WVALID = 2 } xg_reduce_mode;
 
 typedef enum {
-  XG_BIN_MUL = 0, XG_BIN_DIV = 1, XG_BIN_ADD = 2, XG_BIN_SUB = 3
+  XG_BIN_MUL = 0, XG_BIN_DIV = 1, XG_BIN_ADD = 2, XG_BIN_SUB = 3,
+  XG_BIN_DIVNZ = 4 /* a / b, NaN where b == 0 (a weighted mean over no valid weight) */
 } xg_binop;
 
 XG_API int xg_version(void);
@@ -149,7 +151,8 @@ XG_API int xg_cumscan(int dtype, const void* in, void* out, int ndim,
 
 /*
  * Weighted reduction along one axis: out = sum_j in[j] * w[j]   (XG_REDUCE_SUM)
- * or  sum_j in*w / sum_j w over non-NaN in  (XG_REDUCE_MEAN, needs weight).
+ * or  sum_j in*w / sum_j w over non-NaN in  (XG_REDUCE_MEAN; skipna == 0 keeps NaN cells, so the result is
+ * NaN wherever the line holds one, like da.weighted(w).mean(skipna=False)).
  * weight may be NULL (plain sum / mean).  Output shape = shape without `axis`.
  */
 XG_API int xg_wreduce(int dtype, const void* in, const void* weight,
@@ -226,8 +229,8 @@ XG_API int xg_fill_uniform_host(int dtype, void* out, int64_t count, uint64_t se
 
 /*
  * Host-buffer variant of xg_stencil2: same semantics, HOST pointers.  The field
- * is streamed through the device in slabs of the outermost non-operated
- * dimension with H2D / kernel / D2H overlapped on three streams.  Host buffers
+ * is streamed through the device in slabs of the outermost dimension (one-plane
+ * overlap when that is the operated axis) with H2D / kernel / D2H overlapped on three streams.  Host buffers
  * should be page-locked for full PCIe rate (pageable memory is staged).
  * `device` selects the GPU.  Synchronous: returns when `out` is complete.
  */
@@ -236,6 +239,38 @@ XG_API int xg_stencil2_host(int op, int dtype, const void* in, void* out, int nd
                      double fill_value, const void* pre_metric,
                      const int64_t* pre_strides, const void* post_metric,
                      const int64_t* post_strides, int device);
+
+/*
+ * One HOST field up, `nout` results down: result k = xg_stencil2(op[k], axis[k], lo[k], hi[k], bc[k],
+ * fill_value[k]) of the same input (no metrics), each into its own HOST buffer out[k].  The field crosses
+ * PCIe once instead of once per result (the reference re-reads it per call, xgcm/grid.py:796-832).
+ * Slabs are cut along dim 0; a result operated along dim 0 must keep that extent (lo + hi == 1) and may
+ * not use XG_BC_EXTRAPOLATE (XG_ENOTIMPL otherwise: use xg_stencil2_host for that result).  nout <= 8.
+ */
+XG_API int xg_stencil2_host_multi(int nout, const int* op, int dtype, const void* in, void* const* out,
+                           int ndim, const int64_t* shape, const int* axis, const int* lo,
+                           const int* hi, const int* bc, const double* fill_value, int device);
+
+/*
+ * Host-buffer twins of xg_cumscan / xg_wreduce / xg_vinterp_linear (same semantics, HOST pointers, `device`
+ * instead of a stream; synchronous).  The field is streamed in slabs of the first NON-operated dimension
+ * (strided 2-D copies when that is not dim 0), so every line along the operated axis stays whole: no
+ * halo between slabs, summation order untouched.  Metric / weight / theta / target operands are uploaded
+ * whole.  Replaces the host side of xgcm/grid.py:1316 (cumsum), :1598-1605 (integrate), :1680-1685
+ * (average) and xgcm/transform.py:233-249 for numpy-backed fields.
+ */
+XG_API int xg_cumscan_host(int dtype, const void* in, void* out, int ndim, const int64_t* shape, int axis,
+                    int reverse, int trim, int pad_lo, int pad_hi, int bc, double fill_value,
+                    const void* pre_metric, const int64_t* pre_strides, const void* post_metric,
+                    const int64_t* post_strides, int skipna, int device);
+XG_API int xg_wreduce_host(int dtype, const void* in, const void* weight, const int64_t* w_strides,
+                    void* out, int ndim, const int64_t* shape, int axis, int mode, int skipna,
+                    int device);
+XG_API int xg_vinterp_linear_host(int dtype, const void* phi, const void* theta,
+                           const int64_t* theta_strides, const void* target,
+                           const int64_t* target_strides, int64_t m, void* out, int ndim,
+                           const int64_t* shape, int axis, int mask_edges, int bypass_checks,
+                           int logarithmic, int device);
 
 /* Free the cached device slabs / streams of the *_host entry points. */
 XG_API int xg_host_workspace_release(void);

@@ -170,11 +170,15 @@ def wreduce(a, w, axis, mode="sum", skipna=True):
     if mode == "sum":
         prod = a if w is None else a * w  # grid.py:1599
         return (np.nansum if skipna else np.sum)(prod, axis=axis)
-    # xarray Weighted.mean: sum(da*w over valid) / sum(w over valid), NaN where that is 0
+    # xarray Weighted.mean: sum(da*w over valid) / sum(w over valid), NaN where that is 0; with
+    # skipna=False nothing is masked and a NaN cell makes its line NaN (xgcm/grid.py:1680-1685 forwards
+    # **kwargs to da.weighted(w).mean)
     wb = np.ones_like(a) if w is None else np.broadcast_to(w, a.shape).astype(a.dtype)
-    valid = ~np.isnan(a)
+    valid = ~np.isnan(a) if skipna else np.ones(a.shape, bool)
     num = np.sum(np.where(valid, a, 0) * wb, axis=axis)
     den = np.sum(np.where(valid, wb, 0), axis=axis)
+    if mode == "wvalid":
+        return den.astype(a.dtype)
     with np.errstate(invalid="ignore", divide="ignore"):
         out = num / den
     return np.where(den != 0, out, np.nan).astype(a.dtype)

@@ -74,8 +74,13 @@ def install(monkeypatch):
         return _t(oracle.pad_axis(_np(x), axis, lo, hi, padding, fill_value))
 
     def binary(opname, a, b, shape=None):
-        fn = {"mul": np.multiply, "div": np.true_divide, "add": np.add, "sub": np.subtract}[opname]
-        return _t(np.asarray(fn(_np(a), _np(b))))
+        def divnz(x, y):
+            with np.errstate(invalid="ignore", divide="ignore"):
+                return np.where(y != 0, x / y, np.nan).astype(np.result_type(x, y))
+
+        fn = {"mul": np.multiply, "div": np.true_divide, "add": np.add, "sub": np.subtract, "divnz": divnz}[opname]
+        with np.errstate(invalid="ignore", divide="ignore"):
+            return _t(np.asarray(fn(_np(a), _np(b))))
 
     def cumscan(x, axis, reverse=False, trim="none", pad_lo=0, pad_hi=0, padding=None,
                 fill_value=0.0, pre=None, post=None, skipna=True):
@@ -129,6 +134,24 @@ def install(monkeypatch):
     monkeypatch.setattr(ops, "strided_copy", strided_copy)
     monkeypatch.setattr(ops, "strided_copy_batch", lambda copies: [strided_copy(*c) for c in copies] and None)
 
+    def cumscan_host(x, axis, reverse=False, trim="none", pad_lo=0, pad_hi=0, padding=None, fill_value=0.0,
+                     pre=None, post=None, skipna=True, device=None):
+        return cumscan(x, axis, reverse, trim, pad_lo, pad_hi, padding, fill_value, pre, post, skipna).numpy()
+
+    def wreduce_host(x, axis, weight=None, mode="sum", skipna=True, device=None):
+        return wreduce(x, axis, weight, mode, skipna).numpy()
+
+    def vinterp_linear_host(phi, theta, target, axis, mask_edges=False, bypass_checks=False, logarithmic=False,
+                            device=None):
+        return vinterp_linear(phi, theta, target, axis, mask_edges, bypass_checks, logarithmic).numpy()
+
+    def stencil2_host_multi(x, specs, outs=None, device=None):
+        return [stencil2(x, ax, op, lo, hi, pad_ if (lo or hi) else None, 0.0 if fv is None else fv).numpy()
+                for ax, op, lo, hi, pad_, fv in specs]
+
     for name, fn in dict(stencil2=stencil2, stencil2_host=stencil2_host, pad=pad, binary=binary,
-                         cumscan=cumscan, wreduce=wreduce, vinterp_linear=vinterp_linear).items():
+                         cumscan=cumscan, wreduce=wreduce, vinterp_linear=vinterp_linear,
+                         cumscan_host=cumscan_host, wreduce_host=wreduce_host,
+                         vinterp_linear_host=vinterp_linear_host,
+                         stencil2_host_multi=stencil2_host_multi).items():
         monkeypatch.setattr(ops, name, fn)

@@ -481,3 +481,57 @@ def test_set_metric_and_overwrite_and_errors():
         grid.set_metrics("X", "foo")
     with pytest.raises(KeyError, match="not compatible with grid axes"):
         grid.set_metrics(("U", "V"), "area_n")
+
+
+def test_apply_many_equals_single_calls():
+    """Extension: Grid.apply_many(da, requests) == the single-operator calls (host arrays go through the
+    batched slab pipeline, device arrays loop)."""
+    ds, coords, metrics, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding={"X": "periodic", "Y": "fill"}, autoparse_metadata=False)
+    da = ds["tracer"]
+    reqs = [("diff", "X"), ("interp", "X"), ("diff", "Y"), ("interp", "Y", "right"), ("min", "X"), ("max", "Y")]
+    many = grid.apply_many(da, reqs)
+    assert len(many) == len(reqs)
+    for r, req in zip(many, reqs):
+        f, ax = req[0], req[1]
+        to = req[2] if len(req) > 2 else None
+        want = getattr(grid, f)(da, ax, to=to)
+        assert r.dims == want.dims
+        np.testing.assert_array_equal(r.values, want.values)
+        assert set(r.coords) == set(want.coords)
+    with pytest.raises(ValueError, match="apply_many supports"):
+        grid.apply_many(da, [("cumsum", "X")])
+    with pytest.raises(KeyError):
+        grid.apply_many(da, [("diff", "Q")])
+
+
+def test_average_skipna_false_and_min_count():
+    """grid.py:1680-1685 forwards **kwargs to da.weighted(w).mean: skipna=False lets NaN through;
+    min_count is refused (not silently ignored)."""
+    ds, coords, metrics, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="fill", autoparse_metadata=False)
+    da = ds["tracer"].copy()
+    vals = np.array(da.values, dtype=np.float64, copy=True)
+    vals[1, 2] = np.nan  # all of (time, z) at x = 1, y = 2
+    da = xg.DataArray(vals, dims=da.dims, coords=da.coords)
+    for axes in ("X", ["X", "Y"]):
+        skip = grid.average(da, axes).values
+        keep = grid.average(da, axes, skipna=False).values
+        assert not np.isnan(skip).any()
+        nan_lines = np.isnan(vals).any(axis=0) if axes == "X" else np.isnan(vals).any(axis=(0, 1))
+        np.testing.assert_array_equal(np.isnan(keep), nan_lines)
+    with pytest.raises(NotImplementedError, match="min_count"):
+        grid.integrate(da, "X", min_count=1)
+
+
+def test_cumint_equals_cumsum_of_product():
+    """grid.py:1656-1660: cumint == cumsum(da * metric); the product rides on the scan kernel's pre operand."""
+    ds, coords, metrics, _ = _metric_grid()
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding="fill", autoparse_metadata=False)
+    da = ds["tracer"]
+    for axes in ("X", "Y", ["X", "Y"]):
+        weight = grid.get_metric(da, (axes,) if isinstance(axes, str) else tuple(axes))
+        want = grid.cumsum(da * weight, axes, padding="fill")
+        got = grid.cumint(da, axes, padding="fill")
+        assert got.dims == want.dims
+        np.testing.assert_array_equal(got.values, want.values)

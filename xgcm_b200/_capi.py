@@ -18,14 +18,17 @@ XG_F32, XG_F64 = 0, 1
 OPS = {"diff": 0, "interp": 1, "min": 2, "max": 3}
 BCS = {None: 0, "periodic": 1, "fill": 2, "extend": 3, "extrapolate": 4}
 TRIMS = {"none": 0, "drop_last": 1, "drop_first": 2}
-REDUCE = {"sum": 0, "mean": 1}
-BINOPS = {"mul": 0, "div": 1, "add": 2, "sub": 3}
+REDUCE = {"sum": 0, "mean": 1, "wvalid": 2}
+BINOPS = {"mul": 0, "div": 1, "add": 2, "sub": 3, "divnz": 4}
 XG_MAX_NDIM = 8
 
 _EXC = {-1: ValueError, -2: NotImplementedError, -3: RuntimeError, -4: RuntimeError}
 
 _i64p = C.POINTER(C.c_int64)
+_i32p = C.POINTER(C.c_int)
+_f64p = C.POINTER(C.c_double)
 _vp = C.c_void_p
+_vpp = C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes); mirrors the header declaration by declaration
 SIGNATURES = {
@@ -79,6 +82,24 @@ SIGNATURES = {
         C.c_int,
         [C.c_int, C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int,
          C.c_double, _vp, _i64p, _vp, _i64p, C.c_int],
+    ),
+    "xg_stencil2_host_multi": (
+        C.c_int,
+        [C.c_int, _i32p, C.c_int, _vp, _vpp, C.c_int, _i64p, _i32p, _i32p, _i32p, _i32p, _f64p, C.c_int],
+    ),
+    "xg_cumscan_host": (
+        C.c_int,
+        [C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+         C.c_double, _vp, _i64p, _vp, _i64p, C.c_int, C.c_int],
+    ),
+    "xg_wreduce_host": (
+        C.c_int,
+        [C.c_int, _vp, _vp, _i64p, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int],
+    ),
+    "xg_vinterp_linear_host": (
+        C.c_int,
+        [C.c_int, _vp, _vp, _i64p, _vp, _i64p, C.c_int64, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int,
+         C.c_int, C.c_int],
     ),
     "xg_host_workspace_release": (C.c_int, []),
 }

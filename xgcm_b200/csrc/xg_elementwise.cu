@@ -116,6 +116,7 @@ template <typename T, int OP>
 __device__ __forceinline__ T bin_apply(T x, T y) {
   if constexpr (OP == XG_BIN_MUL) return x * y;
   else if constexpr (OP == XG_BIN_DIV) return x / y;
+  else if constexpr (OP == XG_BIN_DIVNZ) return (y != T(0)) ? x / y : T(NAN);
   else if constexpr (OP == XG_BIN_ADD) return x + y;
   else return x - y;
 }
@@ -161,6 +162,7 @@ int binary_launch(int binop, BinArgs<T>& a, cudaStream_t st) {
     case XG_BIN_DIV: k_binary<T, VEC, XG_BIN_DIV><<<(unsigned)blocks, kThreads, 0, st>>>(a); break;
     case XG_BIN_ADD: k_binary<T, VEC, XG_BIN_ADD><<<(unsigned)blocks, kThreads, 0, st>>>(a); break;
     case XG_BIN_SUB: k_binary<T, VEC, XG_BIN_SUB><<<(unsigned)blocks, kThreads, 0, st>>>(a); break;
+    case XG_BIN_DIVNZ: k_binary<T, VEC, XG_BIN_DIVNZ><<<(unsigned)blocks, kThreads, 0, st>>>(a); break;
     default: return xg_fail(XG_EINVAL, "xg_binary: unknown operator");
   }
   return xg_check_launch("xg_binary");

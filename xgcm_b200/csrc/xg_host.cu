@@ -24,6 +24,7 @@ constexpr int kSlots = 3;
 
 struct Workspace {
   int device = -1;
+  std::mutex mu;  // one host call at a time per device; different devices run concurrently
   size_t slab_in_bytes = 0, slab_out_bytes = 0, metric_bytes[2] = {0, 0}, halo_bytes = 0;
   void* d_in[kSlots] = {nullptr, nullptr, nullptr};
   void* d_out[kSlots] = {nullptr, nullptr, nullptr};
@@ -87,7 +88,10 @@ size_t operand_span(const int64_t* strides, const int64_t* shape, int ndim, size
 
 }  // namespace
 
+void xg_host_pipe_release();  // xg_host_pipe.cu
+
 extern "C" int xg_host_workspace_release(void) {
+  xg_host_pipe_release();
   std::lock_guard<std::mutex> lock(g_ws_mutex);
   for (Workspace* w : g_ws) {
     cudaSetDevice(w->device);
@@ -130,11 +134,15 @@ extern "C" int xg_stencil2_host(int op, int dtype, const void* in, void* out, in
                    "xg_stencil2_host: no boundary condition was specified but the operation "
                    "needs to pad the axis");
   const size_t es = dtype == XG_F32 ? 4 : 8;
-  std::lock_guard<std::mutex> lock(g_ws_mutex);
   XG_CUDA(cudaSetDevice(device));
   Workspace* w = nullptr;
-  int rc = get_workspace(device, &w);
+  int rc;
+  {
+    std::lock_guard<std::mutex> reg(g_ws_mutex);  // registry only
+    rc = get_workspace(device, &w);
+  }
   if (rc) return rc;
+  std::lock_guard<std::mutex> lock(w->mu);
 
   int64_t out_shape[XG_MAX_NDIM];
   for (int d = 0; d < ndim; ++d) out_shape[d] = shape[d];

@@ -572,10 +572,24 @@ int vinterp_shared_tma(const InterpArgs<T>& a, cudaStream_t st) {
   if ((a.inner * sizeof(T)) % 16 != 0) return 0;
   if ((reinterpret_cast<uintptr_t>(a.phi) | reinterpret_cast<uintptr_t>(a.out)) & 15) return 0;
   if (a.inner < 32 || a.inner >= (1ll << 31) || a.outer >= (1ll << 31)) return 0;
-  int dev = 0, sms = 148, smem_max = 0;
+  int dev = 0;
   cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  // init-once device property cache (attribute queries cost microseconds each, the kernel ~1 ms)
+  static int s_sms[64], s_smem[64];
+  static bool s_have[64];
+  int sms = 148, smem_max = 0;
+  if (dev >= 0 && dev < 64 && s_have[dev]) {
+    sms = s_sms[dev];
+    smem_max = s_smem[dev];
+  } else {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    if (dev >= 0 && dev < 64) {
+      s_sms[dev] = sms;
+      s_smem[dev] = smem_max;
+      s_have[dev] = true;
+    }
+  }
   // columns per lane: 2 (64-column tiles) halves the per-column share of the plan reads and loop control, as
   // long as four or so tiles (n levels in + m targets out each) still fit in shared memory
   int cpl = env_int("XG_VINTERP_CPL", 0);

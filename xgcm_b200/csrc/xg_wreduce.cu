@@ -43,7 +43,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
   Pack num, den;
 #pragma unroll
   for (int q = 0; q < VEC; ++q) num.v[q] = den.v[q] = T(0);
-  const bool mean = a.mode == XG_REDUCE_MEAN;
+  const bool mean = a.mode != XG_REDUCE_SUM;  // MEAN and WVALID carry the sum of valid weights
 
   auto step = [&](const Pack& v, const Pack& m) {
 #pragma unroll
@@ -53,7 +53,9 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
         if (a.skipna && xg_isnan(p)) p = T(0);   // .sum(skipna) -> nansum
         num.v[q] = num.v[q] + p;
       } else {
-        const bool valid = !xg_isnan(v.v[q]);
+        // da.weighted(w).mean(skipna): NaN cells drop out together with their weights; with
+        // skipna=False they stay in and the result is NaN (grid.py:1680-1685 forwards the kwarg)
+        const bool valid = !a.skipna || !xg_isnan(v.v[q]);
         const T wq = HASW ? m.v[q] : T(1);
         num.v[q] = num.v[q] + (valid ? v.v[q] * wq : T(0));
         den.v[q] = den.v[q] + (valid ? wq : T(0));
@@ -80,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
 #pragma unroll
   for (int q = 0; q < VEC; ++q) {
     if (!mean) r.v[q] = num.v[q];
+    else if (a.mode == XG_REDUCE_WVALID) r.v[q] = den.v[q];
     else r.v[q] = (den.v[q] != T(0)) ? num.v[q] / den.v[q] : T(NAN);
   }
   xg_st_stream<T, VEC>(a.out + o * a.inner + i, r);
@@ -95,7 +98,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_rows(const ReduceArgs<T> a)
   const T* wp = reinterpret_cast<const T*>(a.w.ptr);
   int64_t w_base = 0;
   if (HASW) w_base = xg_groups_offset(a.w.outer, r);
-  const bool mean = a.mode == XG_REDUCE_MEAN;
+  const bool mean = a.mode != XG_REDUCE_SUM;
   double num = 0.0, den = 0.0;
   for (int64_t x = (int64_t)lane * VEC; x < a.n; x += 32 * VEC) {
     XgPack<T, VEC> v = xg_ld_stream<T, VEC>(row + x);
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_rows(const ReduceArgs<T> a)
         if (a.skipna && xg_isnan(p)) p = T(0);
         num += (double)p;
       } else {
-        const bool valid = !xg_isnan(v.v[q]);
+        const bool valid = !a.skipna || !xg_isnan(v.v[q]);
         num += valid ? (double)(v.v[q] * w) : 0.0;
         den += valid ? (double)w : 0.0;
       }
@@ -120,6 +123,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_rows(const ReduceArgs<T> a)
   }
   if (lane == 0) {
     if (!mean) a.out[r] = (T)num;
+    else if (a.mode == XG_REDUCE_WVALID) a.out[r] = (T)den;
     else a.out[r] = (den != 0.0) ? (T)(num / den) : T(NAN);
   }
 }
@@ -182,7 +186,7 @@ extern "C" int xg_wreduce(int dtype, const void* in, const void* weight, const i
                           void* out, int ndim, const int64_t* shape, int axis, int mode,
                           int skipna, void* stream) {
   if (!in || !out || !shape) return xg_fail(XG_EINVAL, "xg_wreduce: null pointer");
-  if (mode != XG_REDUCE_SUM && mode != XG_REDUCE_MEAN)
+  if (mode != XG_REDUCE_SUM && mode != XG_REDUCE_MEAN && mode != XG_REDUCE_WVALID)
     return xg_fail(XG_EINVAL, "xg_wreduce: unknown mode");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == XG_F32)

@@ -53,3 +53,71 @@ def result_like(t: torch.Tensor, was_host: bool):
         host.copy_(t)
         return host.numpy()
     return t
+
+
+# --------------------------------------------------------------------------- NUMA placement of the host side
+def _parse_cpulist(text: str):
+    cpus = set()
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        if "-" in part:
+            a, b = part.split("-")
+            cpus.update(range(int(a), int(b) + 1))
+        else:
+            cpus.add(int(part))
+    return cpus
+
+
+def gpu_numa_node(index: int | None = None) -> int:
+    """NUMA node the GPU hangs off (sysfs), or -1 when the platform does not say."""
+    idx = torch.cuda.current_device() if index is None else int(index)
+    p = torch.cuda.get_device_properties(idx)
+    try:
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            return int(f.read().strip())
+    except Exception:
+        return -1
+
+
+def bind_to_gpu_numa(index: int | None = None) -> dict:
+    """Pin the calling thread (and the memory it touches from now on) to the NUMA node of GPU ``index``.
+
+    Host-streamed calls are bound by host-memory / root-complex bandwidth once several GPUs share a socket:
+    page-locked buffers should live on the socket their GPU is attached to.  Call this BEFORE allocating
+    pinned buffers (``ops.pinned_empty``) — one process per GPU, as torchrun launches them.  Returns what was
+    done (for logs); never raises."""
+    import ctypes
+    import os
+    import platform
+
+    info = {"gpu": torch.cuda.current_device() if index is None else int(index), "numa_node": -1,
+            "cpus_bound": 0, "mempolicy": None}
+    try:
+        node = gpu_numa_node(index)
+        info["numa_node"] = node
+        if node < 0:
+            info["note"] = "sysfs reports no NUMA node for this GPU"
+            return info
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = _parse_cpulist(f.read())
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use:
+            os.sched_setaffinity(0, use)
+            info["cpus_bound"] = len(use)
+        else:
+            info["note"] = "node cpus not in this process's cpuset"
+        # set_mempolicy(MPOL_PREFERRED, {node}): page-locked allocations after this land on the GPU's socket
+        nr = {"x86_64": 238, "aarch64": 237}.get(platform.machine())
+        if nr is not None:
+            nbits = 1024
+            mask = (ctypes.c_ulong * (nbits // (8 * ctypes.sizeof(ctypes.c_ulong))))()
+            mask[node // (8 * ctypes.sizeof(ctypes.c_ulong))] |= 1 << (node % (8 * ctypes.sizeof(ctypes.c_ulong)))
+            libc = ctypes.CDLL(None, use_errno=True)
+            rc = libc.syscall(nr, 1, ctypes.byref(mask), nbits + 1)  # MPOL_PREFERRED = 1
+            info["mempolicy"] = "preferred" if rc == 0 else f"failed (errno {ctypes.get_errno()})"
+    except Exception as exc:  # placement is an optimisation, never an error
+        info["note"] = repr(exc)
+    return info

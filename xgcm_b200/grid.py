@@ -562,6 +562,82 @@ class Grid:
         res = DataArray(result_like(out, was_host), dims=out_dims, name=array.name, attrs=array.attrs)
         return _reattach_coords([res], self, None, set(rename.values()), [array])[0]
 
+    def apply_many(self, da, requests, padding=None, fill_value=None):
+        """Several single-axis operators of ONE field in one call (an extension; the reference has no
+        counterpart and would re-read the field per call, grid.py:796-832).
+
+        ``requests``: sequence of ``(funcname, axis)`` or ``(funcname, axis, to)`` with funcname in
+        diff / interp / min / max.  Returns a list of DataArrays, one per request, identical to calling
+        ``getattr(grid, funcname)(da, axis, to=to)`` one by one.  For a numpy-backed field the batch goes
+        through ``xg_stencil2_host_multi``: the field crosses PCIe once and every result streams back
+        while later slabs are still being computed.  Device-resident fields just loop."""
+        from . import ops
+
+        da, as_xarray = self._wrap_in(da)
+        reqs = []
+        for r in requests:
+            funcname, ax_name = r[0], r[1]
+            to = r[2] if len(r) > 2 else None
+            if funcname not in ("diff", "interp", "min", "max"):
+                raise ValueError(f"apply_many supports diff / interp / min / max, got {funcname!r}")
+            if ax_name not in self.axes:
+                raise KeyError(f"Did not find axis {ax_name} in grid axes {list(self.axes)}")
+            reqs.append((funcname, ax_name, to))
+        kw = {}
+        if padding is not None:
+            kw["padding"] = padding
+        if fill_value is not None:
+            kw["fill_value"] = fill_value
+
+        def one_by_one():
+            return [self._wrap_out(self._1d_grid_ufunc_dispatch(f, da, a, to=t, **kw), as_xarray)
+                    for f, a, t in reqs]
+
+        host_ok = (not isinstance(da, dict) and not da.is_device and self._face_connections is None
+                   and np.asarray(da.data).dtype in (np.float32, np.float64) and 1 <= len(reqs) <= 8)
+        if not host_ok:
+            return one_by_one()
+        paddings = self._complete_user_kwargs_using_axis_defaults(padding, "padding")
+        fills = self._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
+        specs, renames = [], []
+        for funcname, ax_name, to in reqs:
+            sig = self._create_1d_grid_ufunc_signatures(da, axis=[ax_name], to=self._map_kwargs_over_axes(to))[0]
+            grid_ufunc, _ = _select_grid_ufunc(funcname, sig, module=gridops)
+            dummy = grid_ufunc.signature.in_ax_names[0][0]
+            lo, hi = (grid_ufunc.padding_width or {}).get(dummy, (0, 0))
+            from_pos, to_pos = sig.in_ax_positions[0][0], sig.out_ax_positions[0][0]
+            in_dim = self.axes[ax_name].coords[from_pos]
+            try:
+                out_dim = self.axes[ax_name].coords[to_pos]
+            except KeyError:
+                raise ValueError(f"Axis position ({ax_name}:{to_pos}) does not exist in grid")
+            pad_mode = paddings[ax_name]
+            if (lo or hi) and pad_mode is None:
+                raise ValueError(
+                    f"No boundary condition was specified for axis {ax_name!r}, but the "
+                    f"requested operation needs to pad it. Set a boundary condition, "
+                    f"e.g. ``padding='fill'`` (or 'extend'/'periodic'), on the Grid "
+                    f"(``Grid(..., padding=...)``) or pass ``padding=`` to the "
+                    f"grid method."
+                )
+            if pad_mode not in ("periodic", "fill", "extend", None):
+                return one_by_one()
+            axn = da.get_axis_num(in_dim)
+            if axn == 0 and (lo + hi != 1):
+                return one_by_one()  # outer / inner shift along the slab dimension
+            fv = fills[ax_name] if fills[ax_name] is not None else 0.0
+            specs.append((axn, funcname, lo, hi, pad_mode if (lo or hi) else None, fv))
+            renames.append((in_dim, out_dim, ax_name, (lo, hi)))
+        dev = self._device_for(da)
+        outs = ops.stencil2_host_multi(np.asarray(da.data), specs, device=dev.index)
+        results = []
+        for arr, (in_dim, out_dim, ax_name, width) in zip(outs, renames):
+            out_dims = tuple(out_dim if d == in_dim else d for d in da.dims)
+            res = DataArray(arr, dims=out_dims, name=da.name, attrs=da.attrs)
+            res = _reattach_coords([res], self, {ax_name: width}, {out_dim}, [da])[0]
+            results.append(self._wrap_out(res, as_xarray))
+        return results
+
     def apply_as_grid_ufunc(self, func: Callable, *args, axis=None, signature="", padding_width=None,
                             padding=None, fill_value=None, dask="forbidden", map_overlap=False,
                             **kwargs):
@@ -605,7 +681,7 @@ class Grid:
 
     # ------------------------------------------------------------------ cumsum family
     def cumsum(self, da, axis, to=None, padding=None, fill_value=None, metric_weighted=None,
-               reverse=False, **kwargs):
+               reverse=False, _pre_weight=None, **kwargs):
         """Cumulative sum moving to the intermediate position (grid.py:1183-1418).
 
         Per axis ONE ``xg_cumscan`` launch does metric multiply, (reverse) sequential
@@ -645,9 +721,16 @@ class Grid:
         fills = self._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
 
         host_input = not da.is_device
-        x, _ = as_device_tensor(da.data, self._device_for(da))
-        data = da._replace(data=x)
-        for ax_name in axis:
+        # numpy-backed field, one axis: stream slabs through the GPU (xg_cumscan_host) instead of one
+        # un-overlapped upload + download around the kernel
+        host_stream = (host_input and len(axis) == 1 and self._face_connections is None
+                       and np.asarray(da.data).dtype in (np.float32, np.float64))
+        if host_stream:
+            data = da
+        else:
+            x, _ = as_device_tensor(da.data, self._device_for(da))
+            data = da._replace(data=x)
+        for ax_i, ax_name in enumerate(axis):
             ax = self.axes[ax_name]
             pos, dim = ax._get_position_name(da)
             input_da = data
@@ -676,11 +759,27 @@ class Grid:
             out_dims = tuple(new_dim if d == dim else d for d in data.dims)
             axis_num = data.get_axis_num(dim)
             pre_t = post_t = None
-            if weighted:
-                pre_t = self._metric_tensor(self.get_metric(data, weighted), data.dims, data.data)
-                probe = DataArray.__new__(DataArray)
-                probe._dims = out_dims
-                post_t = self._metric_tensor(self.get_metric(probe, weighted), out_dims, data.data)
+            probe = DataArray.__new__(DataArray)
+            probe._dims = out_dims
+            if host_stream:
+                fdt = np.asarray(data.data).dtype
+                if weighted:
+                    pre_t = self._metric_host(self.get_metric(data, weighted), data.dims, fdt)
+                    post_t = self._metric_host(self.get_metric(probe, weighted), out_dims, fdt)
+                if _pre_weight is not None:  # cumint: the metric product rides on the kernel's pre operand
+                    if pre_t is not None:
+                        raise NotImplementedError("cumint with metric_weighted on a host array: pass a device array")
+                    pre_t = self._metric_host(_pre_weight, data.dims, fdt)
+            else:
+                if weighted:
+                    pre_t = self._metric_tensor(self.get_metric(data, weighted), data.dims, data.data)
+                    post_t = self._metric_tensor(self.get_metric(probe, weighted), out_dims, data.data)
+                if _pre_weight is not None and ax_i == 0:
+                    w_t = self._metric_tensor(_pre_weight, data.dims, data.data)
+                    if pre_t is None:
+                        pre_t = w_t  # (da * w) is formed inside the scan kernel: 8 B/cell instead of 20
+                    else:  # two roundings in the reference, (da * w) * metric: keep them
+                        data = data._replace(data=ops.binary("mul", data.data, w_t))
             fv = fills[ax.name] if fills[ax.name] is not None else 0.0
             if self._face_connections is not None and (pad_lo or pad_hi):
                 # the reference pads the cumsum'd data with ``pad`` (grid.py:1385-1391), which on a
@@ -693,6 +792,12 @@ class Grid:
                         fill_value=fill_value).data
                 if post_t is not None:
                     y = ops.binary("div", y, post_t)
+            elif host_stream:
+                y = ops.cumscan_host(
+                    np.asarray(data.data), axis_num, ax_reverse, trim, pad_lo, pad_hi,
+                    ax_padding if (pad_lo or pad_hi) else None, fv, pre=pre_t, post=post_t, skipna=True,
+                    device=self._device_for(da).index,
+                )
             else:
                 y = ops.cumscan(
                     data.data, axis_num, ax_reverse, trim, pad_lo, pad_hi,
@@ -703,7 +808,7 @@ class Grid:
                 [coordless], grid=self, padding_width={ax.name: (pad_lo, pad_hi)},
                 out_core_dim_names={new_dim}, input_args=[input_da],
             )[0]
-        if host_input:
+        if host_input and not host_stream:
             data = data._replace(data=result_like(data.data, True))
         return self._wrap_out(data, as_xarray)
 
@@ -711,13 +816,8 @@ class Grid:
         """Cumulative integral: ``cumsum(da * get_metric(da, axis), axis)`` (grid.py:1607-1660)."""
         da, as_xarray = self._wrap_in(da)
         weight = self.get_metric(da, axis)
-        host_input = not da.is_device
-        dev = self._device_for(da)
-        dd = da if da.is_device else da.to_device(dev)
-        wd = weight if weight.is_device else weight.to_device(dev)
-        res = self.cumsum(dd * wd, axis, **kwargs)  # product on the device (xg_binary)
-        if host_input:
-            res = res.to_host()
+        # the product da * metric is formed inside the scan kernel (its `pre` operand): one pass
+        res = self.cumsum(da, axis, _pre_weight=weight, **kwargs)
         return self._wrap_out(res, as_xarray)
 
     # ------------------------------------------------------------------ reductions
@@ -727,43 +827,49 @@ class Grid:
 
         da, as_xarray = self._wrap_in(da)
         skipna = kwargs.pop("skipna", None)
+        min_count = kwargs.pop("min_count", None)
         keep_attrs = kwargs.pop("keep_attrs", None)  # accepted, attrs are dropped like xarray's default
         if kwargs:
             raise TypeError(f"unexpected keyword argument(s): {list(kwargs)}")
+        if min_count is not None:
+            # the reference forwards it to DataArray.sum; not fused here: refuse rather than ignore
+            raise NotImplementedError("min_count is not supported by the fused integrate / average")
         if skipna is None:
             skipna = True  # xarray default for float data
         weight = self.get_metric(da, axis)
         dims = self._get_dims_from_axis(da, axis)
         host_input = not da.is_device
+        if (host_input and len(dims) == 1 and np.asarray(da.data).dtype in (np.float32, np.float64)):
+            # numpy-backed field, one axis: slabs stream through the GPU (xg_wreduce_host)
+            arr = np.asarray(da.data)
+            axn = da.get_axis_num(dims[0])
+            w_np = self._metric_host(weight, da.dims, arr.dtype)
+            y = ops.wreduce_host(arr, axn, w_np, mode, bool(skipna), device=self._device_for(da).index)
+            res = DataArray(y, dims=tuple(x_ for x_ in da.dims if x_ != dims[0]), name=da.name)
+            coords = {k: c for k, c in da.coords.items() if all(d in res.dims for d in c.dims)}
+            return self._wrap_out(res.assign_coords(coords), as_xarray)
         x, _ = as_device_tensor(da.data, self._device_for(da))
         cur = da._replace(data=x)
         wt = self._metric_tensor(weight, cur.dims, x)
-        # several axes: reduce the innermost listed dim first with the weights; the weights are
-        # constant along nothing in general, so multi-axis = one weighted pass per dim is only
-        # exact when the metric factorises; otherwise weight once, then plain sums.
+        # several axes: the first pass (innermost listed dim) applies the weights, the others are plain sums
         order = sorted(dims, key=lambda d: cur.get_axis_num(d), reverse=True)
         if mode == "mean" and len(order) > 1:
-            num = cur
-            den_src = None
-            first = True
+            # weighted mean over several dims = sum(x w over valid) / sum(w over valid): numerator and
+            # denominator are reduced side by side (the kernel masks NaN cells itself: no full-size temp)
+            num, den_src, first = cur, None, True
             for d in order:
                 axn = num.get_axis_num(d)
                 if first:
-                    valid_w = ops.wreduce(_nan_mask_weights(cur.data, wt), axn, None, "sum", False)
-                    numer = ops.wreduce(num.data, axn, wt, "sum", True)
+                    den = ops.wreduce(cur.data, axn, wt, "wvalid", bool(skipna))
+                    numer = ops.wreduce(num.data, axn, wt, "sum", bool(skipna))
                     first = False
-                    den = valid_w
                 else:
-                    numer = ops.wreduce(num.data, axn, None, "sum", True)
+                    numer = ops.wreduce(num.data, axn, None, "sum", bool(skipna))
                     den = ops.wreduce(den_src.data, axn, None, "sum", False)
                 keep = tuple(x_ for x_ in num.dims if x_ != d)
                 num = DataArray(numer, dims=keep)
                 den_src = DataArray(den, dims=keep)
-            out_t = ops.binary("div", num.data, den_src.data)
-            import torch
-
-            out_t = torch.where(den_src.data != 0, out_t, torch.full_like(out_t, float("nan")))
-            res = DataArray(out_t, dims=num.dims, name=da.name)
+            res = DataArray(ops.binary("divnz", num.data, den_src.data), dims=num.dims, name=da.name)
         else:
             first = True
             for d in order:
@@ -842,13 +948,6 @@ class Grid:
     def interp_2d_vector(self, vector, **kwargs):
         """Interpolate a 2-D vector to the intermediate grid point (grid.py:1497-1530)."""
         return self._apply_vector_function(self.interp, vector, **kwargs)
-
-
-def _nan_mask_weights(x, w):
-    """weights where the field is valid, 0 where it is NaN (xarray Weighted._sum_of_weights)."""
-    import torch
-
-    return torch.where(torch.isnan(x), torch.zeros((), dtype=x.dtype, device=x.device), w.expand(x.shape))
 
 
 # (from, to) -> (trim, (pad_lo, pad_hi)); transcription of the enumerated shifts of

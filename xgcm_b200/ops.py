@@ -571,3 +571,137 @@ def stencil2_host(
     )
     _capi.check(rc)
     return out
+
+
+# --------------------------------------------------------------------------- host twins (slab pipelines)
+def _host_field(x, what):
+    if not isinstance(x, np.ndarray):
+        raise TypeError(f"{what} must be a numpy array")
+    if not torch.cuda.is_available():
+        raise RuntimeError("xgcm_b200 needs a CUDA device: the stencil engine has no CPU fallback")
+    if x.dtype not in (np.float32, np.float64):
+        x = x.astype(np.float64)
+    if not x.flags.c_contiguous:
+        x = np.ascontiguousarray(x)
+    return x
+
+
+def stencil2_host_multi(x: np.ndarray, specs, outs=None, device: Optional[int] = None):
+    """One host field up, several stencil results down (``xg_stencil2_host_multi``).
+
+    ``specs``: sequence of ``(axis, op, lo, hi, padding, fill_value)``.  Returns a list of page-locked
+    numpy arrays (or fills ``outs``).  Raises NotImplementedError for what the batched pipeline does not
+    cover (outer / inner shifts or extrapolate along dim 0) — callers then use :func:`stencil2_host`."""
+    lib = _capi.load()
+    x = _host_field(x, "field")
+    k = len(specs)
+    shape = list(x.shape)
+    axes, ops_, los, his, bcs, fills, out_shapes = [], [], [], [], [], [], []
+    for axis, op, lo, hi, padding, fill in specs:
+        if op not in _capi.OPS:
+            raise ValueError(f"unknown op {op!r}")
+        if padding not in _capi.BCS:
+            raise ValueError(f"padding must be one of ['periodic', 'fill', 'extend'] or None, but got {padding}")
+        axis = _norm_axis(axis, x.ndim)
+        axes.append(axis)
+        ops_.append(_capi.OPS[op])
+        los.append(int(lo))
+        his.append(int(hi))
+        bcs.append(_capi.BCS[padding] if (lo or hi) else 0)
+        fills.append(float(0.0 if fill is None else fill))
+        osh = list(shape)
+        osh[axis] = shape[axis] + lo + hi - 1
+        out_shapes.append(osh)
+    if outs is None:
+        outs = [pinned_empty(s, x.dtype) for s in out_shapes]
+    for o, s in zip(outs, out_shapes):
+        if list(o.shape) != s or o.dtype != x.dtype or not o.flags.c_contiguous:
+            raise ValueError("out has wrong shape/dtype/layout")
+    import ctypes as C
+
+    out_ptrs = (C.c_void_p * k)(*[o.ctypes.data for o in outs])
+    dev = torch.cuda.current_device() if device is None else int(device)
+    rc = lib.xg_stencil2_host_multi(
+        k, (C.c_int * k)(*ops_), _capi.dtype_code(x.dtype), x.ctypes.data, out_ptrs, x.ndim,
+        _capi.i64_array(shape), (C.c_int * k)(*axes), (C.c_int * k)(*los), (C.c_int * k)(*his),
+        (C.c_int * k)(*bcs), (C.c_double * k)(*fills), dev)
+    _capi.check(rc)
+    return list(outs)
+
+
+def cumscan_host(x: np.ndarray, axis: int, reverse: bool = False, trim: str = "none", pad_lo: int = 0,
+                 pad_hi: int = 0, padding: Optional[str] = None, fill_value: float = 0.0,
+                 pre: Optional[np.ndarray] = None, post: Optional[np.ndarray] = None, skipna: bool = True,
+                 device: Optional[int] = None) -> np.ndarray:
+    """Host twin of :func:`cumscan` (``xg_cumscan_host``): slabs of a non-operated dim stream through the GPU."""
+    lib = _capi.load()
+    x = _host_field(x, "field")
+    if padding not in _capi.BCS:
+        raise ValueError(f"padding must be one of ['periodic', 'fill', 'extend'] or None, but got {padding}")
+    axis = _norm_axis(axis, x.ndim)
+    shape = list(x.shape)
+    kept = shape[axis] - (0 if trim == "none" else 1)
+    if kept < 0:
+        raise ValueError("operated axis too short to trim")
+    out_shape = list(shape)
+    out_shape[axis] = kept + pad_lo + pad_hi
+    out = pinned_empty(out_shape, x.dtype)
+    kp, pre_ptr, pre_st = _host_operand(pre, shape, x.dtype, "pre metric")
+    kq, post_ptr, post_st = _host_operand(post, out_shape, x.dtype, "post metric")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if out.size:
+        rc = lib.xg_cumscan_host(
+            _capi.dtype_code(x.dtype), x.ctypes.data, out.ctypes.data, x.ndim, _capi.i64_array(shape), axis,
+            int(bool(reverse)), _capi.TRIMS[trim], pad_lo, pad_hi, _capi.BCS[padding], float(fill_value),
+            pre_ptr, pre_st, post_ptr, post_st, int(bool(skipna)), dev)
+        _capi.check(rc)
+    return out
+
+
+def wreduce_host(x: np.ndarray, axis: int, weight: Optional[np.ndarray] = None, mode: str = "sum",
+                 skipna: bool = True, device: Optional[int] = None) -> np.ndarray:
+    """Host twin of :func:`wreduce` (``xg_wreduce_host``)."""
+    lib = _capi.load()
+    x = _host_field(x, "field")
+    axis = _norm_axis(axis, x.ndim)
+    shape = list(x.shape)
+    out_shape = [s for d, s in enumerate(shape) if d != axis]
+    out = pinned_empty(out_shape if out_shape else [1], x.dtype)
+    kw, w_ptr, w_st = _host_operand(weight, shape, x.dtype, "weight")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if out.size and x.size:
+        rc = lib.xg_wreduce_host(_capi.dtype_code(x.dtype), x.ctypes.data, w_ptr, w_st, out.ctypes.data, x.ndim,
+                                 _capi.i64_array(shape), axis, _capi.REDUCE[mode], int(bool(skipna)), dev)
+        _capi.check(rc)
+    return out if out_shape else out.reshape(())
+
+
+def vinterp_linear_host(phi: np.ndarray, theta: np.ndarray, target: np.ndarray, axis: int,
+                        mask_edges: bool = False, bypass_checks: bool = False, logarithmic: bool = False,
+                        device: Optional[int] = None) -> np.ndarray:
+    """Host twin of :func:`vinterp_linear` for a shared 1-D ``target`` (``xg_vinterp_linear_host``); ``theta``
+    broadcasts against ``phi`` (the 1-D coordinate or a full field)."""
+    lib = _capi.load()
+    phi = _host_field(phi, "phi")
+    theta = np.asarray(theta)
+    target = np.asarray(target)
+    if target.ndim > 1:
+        raise NotImplementedError("vinterp_linear_host: per-column targets; use the device entry point")
+    if not (phi.dtype == theta.dtype == target.dtype == np.float32):  # numba loop resolution, transform.py:15-22
+        phi, theta, target = phi.astype(np.float64, copy=False), theta.astype(np.float64), target.astype(np.float64)
+    phi = np.ascontiguousarray(phi)
+    axis = _norm_axis(axis, phi.ndim)
+    shape = list(phi.shape)
+    target = np.ascontiguousarray(target.reshape(-1))
+    m = int(target.size)
+    kt, th_ptr, th_st = _host_operand(theta, shape, phi.dtype, "theta")
+    out_shape = [s for d, s in enumerate(shape) if d != axis] + [m]
+    out = pinned_empty(out_shape, phi.dtype)
+    dev = torch.cuda.current_device() if device is None else int(device)
+    if out.size:
+        rc = lib.xg_vinterp_linear_host(
+            _capi.dtype_code(phi.dtype), phi.ctypes.data, th_ptr, th_st, target.ctypes.data, None, m,
+            out.ctypes.data, phi.ndim, _capi.i64_array(shape), axis, int(bool(mask_edges)),
+            int(bool(bypass_checks)), int(bool(logarithmic)), dev)
+        _capi.check(rc)
+    return out

@@ -52,12 +52,42 @@ def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, ta
             f"The specified `target_dim` {target_dim} is not within the dimensions of the target: [{target_theta_levels.dims}]."
         )
     device = grid._device_for(phi) if grid is not None else None
-    x, host = as_device_tensor(phi.data, device)
     # theta dims other than the core dim must already be dims of phi
     extra = [d for d in theta.dims if d not in phi.dims and d != theta_dim]
     if extra:
         raise ValueError(f"target data has dimensions {extra} that the data does not have")
     tgt_other = [d for d in target_theta_levels.dims if d != target_dim]
+    if (not phi.is_device and not tgt_other and not theta.is_device
+            and np.asarray(phi.data).dtype in (np.float32, np.float64)):
+        # numpy-backed field, shared target levels: slabs of a non-operated dim stream through the GPU
+        # (xg_vinterp_linear_host: H2D || kernel || D2H) instead of one upload + one download
+        th_dims = [d if d != theta_dim else phi_dim for d in theta.dims]
+        th = np.asarray(theta.values)
+        present = [d for d in phi.dims if d in th_dims]
+        perm = [th_dims.index(d) for d in present]
+        if perm != list(range(len(perm))):
+            th = np.transpose(th, perm)
+        sizes = dict(zip(th_dims, theta.shape))
+        if sizes[phi_dim] != phi.sizes[phi_dim]:
+            raise ValueError(
+                f"conflicting sizes for dimension {phi_dim!r}: {phi.sizes[phi_dim]} on the data, "
+                f"{sizes[phi_dim]} on the target data"
+            )
+        th = th.reshape([sizes[d] if d in th_dims else 1 for d in phi.dims])
+        out = ops.vinterp_linear_host(np.asarray(phi.data), th, np.asarray(target_theta_levels.values),
+                                      phi.get_axis_num(phi_dim), mask_edges, bypass_checks, logarithmic,
+                                      device=None if device is None else device.index)
+        out_dims = tuple(d for d in phi.dims if d != phi_dim) + (target_dim,)
+        coords = {k: c for k, c in phi.coords.items()
+                  if phi_dim not in c.dims and k != target_dim and all(d in out_dims for d in c.dims)}
+        for k, c in target_theta_levels.coords.items():
+            if all(d in out_dims for d in c.dims):
+                coords[k] = c
+        res = DataArray(out, dims=out_dims, coords=coords)
+        if phi.name:
+            res.name = phi.name + suffix
+        return res
+    x, host = as_device_tensor(phi.data, device)
     new_dims = [d for d in tgt_other if d not in phi.dims]
     for d in tgt_other:
         if d in phi.dims and phi.sizes[d] != target_theta_levels.sizes[d]:
