@@ -388,6 +388,26 @@ def run_extras(torch, dist, ops, _capi, x, rank, world, peak):
     out.append(r5)
     del xs, d5
 
+    # ---- N > 1: the one real exchange step of the path — the operated axis itself sharded across the GPUs -------
+    if world > 1:
+        from xgcm_b200 import parallel
+
+        comm = parallel.Communicator()
+        for ax_name, axn in (("Z", 0), ("X", 2)):
+            plane_bytes = cells // x.shape[axn] * 4
+            f_fused = lambda: comm.stencil2(x, axn, "diff", 1, 0, "periodic")
+            f_torch = lambda: parallel.sharded_stencil2(x, axn, "diff", 1, 0, "periodic")
+            f_local = lambda: ops.stencil2(x, axn, "diff", 1, 0, "periodic")
+            ms_f, ms_t, ms_l = timed(f_fused, 5, reps=4), timed(f_torch, 5, reps=4), timed(f_local, 5, reps=4)
+            r = rec(f"C3 block per GPU, {ax_name} axis sharded x{world} (periodic ring): Grid.diff via xg_stencil2_sharded",
+                    ms_f, cells, 8 * cells, count(f_fused),
+                    "pack kernel + one NCCL group on a side stream while the local block is computed + edge fix-up")
+            r.update({"nvlink_bytes_per_gpu_per_call": 2 * plane_bytes, "ms_same_kernel_unsharded": ms_l,
+                      "ms_torch_distributed_path": ms_t,
+                      "exchange_hidden_frac": None if ms_t <= ms_l else max(0.0, min(1.0, (ms_t - ms_f) / (ms_t - ms_l)))})
+            out.append(r)
+        comm.close()
+
     # ---- C4: >= 32 time steps, each generated on the device, then the six ops of the headline -----------------
     grid, da = make_dataset(tuple(x.shape), x)
     nsteps = 32

@@ -42,6 +42,7 @@
 #ifndef XGCM_B200_H
 #define XGCM_B200_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -219,6 +220,35 @@ XG_API int xg_strided_copy(int dtype, void* dst, const int64_t* dst_strides, con
 XG_API int xg_strided_copy_batch(int dtype, int count, void* const* dst, const void* const* src,
                           int ndim, const int64_t* shapes, const int64_t* dst_strides,
                           const int64_t* src_strides, const int* negate, void* stream);
+
+/*
+ * Sharded operated axis (reference analogue: map_overlap(depth=1), xgcm/grid_ufunc.py:1057-1133).
+ * Every rank holds a contiguous block of the operated axis on its own GPU, rank order = axis order.
+ *
+ * NCCL is loaded at run time (dlopen); xg_nccl_load(path) names the library explicitly, NULL tries the copy
+ * already in the process, then the default soname.  All NCCL failures return XG_ENCCL.
+ *   xg_comm_unique_id   rank 0 fills 128 bytes; the host ships them to the other ranks
+ *   xg_comm_init        collective over the nranks GPUs (the calling thread's current device)
+ *   xg_halo_exchange    one ring step in ONE NCCL group: send_lo (my first plane) goes to rank-1, send_hi (my
+ *                       last plane) to rank+1; recv_lo / recv_hi receive the neighbours' last / first plane.
+ *                       NULL pointers skip that leg; the ring closes only when `periodic`.
+ *   xg_stencil2_sharded xg_stencil2 (lo + hi == 1; periodic / fill / extend) on the local block: boundary
+ *                       planes are packed (x pre-metric) by a kernel and exchanged on a side stream WHILE the
+ *                       local block is computed; the one or two edge planes are then recomputed from the
+ *                       received halos.  pre / post metrics are the LOCAL shards.  workspace: device memory for
+ *                       4 planes of outer * inner elements, each rounded up to 256 bytes.
+ */
+XG_API int xg_nccl_load(const char* path);
+XG_API int xg_comm_unique_id(void* id128);
+XG_API int xg_comm_init(const void* id128, int nranks, int rank, void** comm);
+XG_API int xg_comm_destroy(void* comm);
+XG_API int xg_halo_exchange(void* comm, const void* send_lo, const void* send_hi, void* recv_lo,
+                     void* recv_hi, size_t bytes, int periodic, void* stream);
+XG_API int xg_stencil2_sharded(void* comm, int op, int dtype, const void* in, void* out, int ndim,
+                        const int64_t* shape, int axis, int lo, int hi, int bc, double fill_value,
+                        const void* pre_metric, const int64_t* pre_strides,
+                        const void* post_metric, const int64_t* post_strides, void* workspace,
+                        size_t workspace_bytes, void* stream);
 
 /* Deterministic synthetic field: out[i] = U(0,1) keyed by (seed, offset+i);
  * identical bits on host (xg_fill_uniform_host) and device. */

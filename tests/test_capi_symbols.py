@@ -4,6 +4,8 @@ import ctypes
 import os
 import re
 
+import pytest
+
 from xgcm_b200 import _build, _capi
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -99,3 +101,26 @@ def test_strided_copy_argument_validation_without_gpu():
     src_strides = i64([1, 2, 4, 8, 16, 32])
     rc = lib.xg_strided_copy_batch(0, 1, one, one, 6, shape, dst_strides, src_strides, (C.c_int * 1)(0), None)
     assert rc == -2 and "5" in _capi.last_error()
+
+
+def test_comm_error_paths_without_a_gpu():
+    """XG_ENCCL is reachable: a NCCL library that cannot be loaded, and argument validation of the sharded
+    entry points, without touching a device."""
+    import ctypes as C
+
+    from xgcm_b200 import _capi
+
+    lib = _capi.load()
+    rc = lib.xg_nccl_load(b"/nonexistent/libnccl.so.2")
+    if rc != 0:  # (0 only if an earlier test in this process already loaded a real NCCL)
+        assert rc == -4
+        assert "NCCL" in _capi.last_error()
+        with pytest.raises(RuntimeError):
+            _capi.check(rc)
+    shape = (C.c_int64 * 2)(4, 8)
+    buf = (C.c_float * 32)()
+    out = (C.c_float * 32)()
+    rc = lib.xg_stencil2_sharded(None, 0, 0, buf, out, 2, shape, 0, 1, 0, 2, 0.0, None, None, None, None, None, 0, None)
+    assert rc == -1 and "null communicator" in _capi.last_error()
+    assert lib.xg_halo_exchange(None, None, None, None, None, 0, 0, None) == -1
+    assert lib.xg_comm_init(None, 2, 0, None) == -1

@@ -34,6 +34,7 @@ def _worker(rank, world, port, ret):
         glob = rng.random(shape).astype(np.float32)
         metric = (1 + rng.random(shape)).astype(np.float32)
         ok = True
+        comm = parallel.Communicator()  # the library's own NCCL communicator (xg_comm_init)
         for axis in range(3):
             start, stop = parallel.shard_bounds(shape[axis], world, rank)
             sl = [slice(None)] * 3
@@ -48,6 +49,24 @@ def _worker(rank, world, port, ret):
                 got = parallel.sharded_stencil2(loc, axis, op, lo, hi, bc, 1.5, pre=mloc, post=mloc).cpu().numpy()
                 want = oracle.stencil2(op, glob, axis, lo, hi, bc, 1.5, metric, metric)[tuple(sl)]
                 ok = ok and np.array_equal(got, want)
+                # the fused C-ABI call: pack kernel + one NCCL group on a side stream + edge fix-up
+                got = parallel.sharded_stencil2(loc, axis, op, lo, hi, bc, 1.5, comm=comm).cpu().numpy()
+                want = oracle.stencil2(op, glob, axis, lo, hi, bc, 1.5)[tuple(sl)]
+                ok = ok and np.array_equal(got, want)
+                got = parallel.sharded_stencil2(loc, axis, op, lo, hi, bc, 1.5, pre=mloc, post=mloc, comm=comm).cpu().numpy()
+                want = oracle.stencil2(op, glob, axis, lo, hi, bc, 1.5, metric, metric)[tuple(sl)]
+                ok = ok and np.array_equal(got, want)
+        # the bare ring step (xg_halo_exchange): my first plane down, my last plane up
+        from xgcm_b200 import _capi
+        lib = _capi.load()
+        mine = torch.full((2, 1000), float(rank), device="cuda")
+        got_lo = torch.full((1000,), -1.0, device="cuda")
+        got_hi = torch.full((1000,), -1.0, device="cuda")
+        rc = lib.xg_halo_exchange(comm._handle, mine[0].data_ptr(), mine[1].data_ptr(), got_lo.data_ptr(),
+                                  got_hi.data_ptr(), 4000, 1, torch.cuda.current_stream().cuda_stream)
+        torch.cuda.synchronize()
+        ok = ok and rc == 0 and bool((got_lo == (rank - 1) % world).all()) and bool((got_hi == (rank + 1) % world).all())
+        comm.close()
         ret[rank] = bool(ok)
     finally:
         dist.destroy_process_group()

@@ -102,6 +102,16 @@ SIGNATURES = {
          C.c_int, C.c_int],
     ),
     "xg_host_workspace_release": (C.c_int, []),
+    "xg_nccl_load": (C.c_int, [C.c_char_p]),
+    "xg_comm_unique_id": (C.c_int, [_vp]),
+    "xg_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vpp]),
+    "xg_comm_destroy": (C.c_int, [_vp]),
+    "xg_halo_exchange": (C.c_int, [_vp, _vp, _vp, _vp, _vp, C.c_size_t, C.c_int, _vp]),
+    "xg_stencil2_sharded": (
+        C.c_int,
+        [_vp, C.c_int, C.c_int, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+         _vp, _i64p, _vp, _i64p, _vp, C.c_size_t, _vp],
+    ),
 }
 
 _lib: Optional[C.CDLL] = None

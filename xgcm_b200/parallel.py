@@ -118,6 +118,93 @@ def _scale(plane: torch.Tensor, metric_plane: torch.Tensor) -> torch.Tensor:
     return plane * metric_plane  # CPU tensors only occur in the gloo plumbing tests
 
 
+class Communicator:
+    """The library's own NCCL communicator over the ranks of a torch.distributed group (``xg_comm_init``).
+
+    torch.distributed is only the rendezvous: rank 0 draws the NCCL unique id inside the C library and
+    broadcasts its 128 bytes; every rank then joins.  The exchange itself (``xg_halo_exchange`` /
+    ``xg_stencil2_sharded``) never goes through Python or torch: pack kernel, one NCCL group on a side stream,
+    the local block computed meanwhile, edge planes fixed up from the received halos."""
+
+    def __init__(self, group=None):
+        import ctypes as C
+
+        from . import _capi
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("xgcm_b200.parallel.Communicator needs CUDA devices (NCCL)")
+        self._lib = _capi.load()
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self._ws = None
+        try:  # name the NCCL torch ships, so both users share one copy of the library
+            import nvidia.nccl as _n  # type: ignore
+            import os
+
+            cand = os.path.join(os.path.dirname(_n.__file__), "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                self._lib.xg_nccl_load(cand.encode())
+        except Exception:
+            pass
+        ident = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            _capi.check(self._lib.xg_comm_unique_id(ident))
+        payload = [bytes(ident)]
+        dist.broadcast_object_list(payload, src=_global_rank(0, group), group=group)
+        ident = (C.c_ubyte * 128).from_buffer_copy(payload[0])
+        handle = C.c_void_p()
+        with torch.cuda.device(torch.cuda.current_device()):
+            _capi.check(self._lib.xg_comm_init(ident, self.world, self.rank, C.byref(handle)))
+        self._handle = handle
+
+    def close(self):
+        if getattr(self, "_handle", None):
+            self._lib.xg_comm_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _workspace(self, plane_bytes: int, device) -> torch.Tensor:
+        need = 4 * ((plane_bytes + 255) // 256 * 256)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(max(need, 256), dtype=torch.uint8, device=device)
+        return self._ws
+
+    def stencil2(self, x_local: torch.Tensor, axis: int, op: str, lo: int, hi: int, padding: Optional[str],
+                 fill_value: float = 0.0, pre: Optional[torch.Tensor] = None,
+                 post: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """``xg_stencil2_sharded``: see :func:`sharded_stencil2`."""
+        from . import _capi, ops
+
+        if lo + hi != 1:
+            raise NotImplementedError(
+                "a sharded operated axis supports only length-preserving shifts (center<->left/right), "
+                "like map_overlap in the reference"
+            )
+        if padding not in ("periodic", "fill", "extend"):
+            raise ValueError(f"padding must be one of ['periodic', 'fill', 'extend'], but got {padding}")
+        x = x_local.contiguous()
+        axis = axis % x.dim()
+        shape = list(x.shape)
+        out = torch.empty_like(x)
+        keep_pre, pre_ptr, pre_st = ops._operand(pre, shape, x, "pre metric")
+        keep_post, post_ptr, post_st = ops._operand(post, shape, x, "post metric")
+        plane = x.numel() // max(shape[axis], 1) * x.element_size()
+        ws = self._workspace(plane, x.device)
+        with torch.cuda.device(x.device):
+            rc = self._lib.xg_stencil2_sharded(
+                self._handle, _capi.OPS[op], ops._dtype_code(x), x.data_ptr(), out.data_ptr(), x.dim(),
+                _capi.i64_array(shape), axis, lo, hi, _capi.BCS[padding], float(fill_value), pre_ptr, pre_st,
+                post_ptr, post_st, ws.data_ptr(), ws.numel(), ops._stream_ptr(x))
+        _capi.check(rc)
+        return out
+
+
 def sharded_stencil2(
     x_local: torch.Tensor,
     axis: int,
@@ -129,11 +216,19 @@ def sharded_stencil2(
     pre: Optional[torch.Tensor] = None,
     post: Optional[torch.Tensor] = None,
     group=None,
+    comm: Optional["Communicator"] = None,
 ) -> torch.Tensor:
     """``xg_stencil2`` on a field whose operated ``axis`` is split across the ranks of ``group``
     (contiguous blocks, rank order = axis order).  ``pre`` / ``post`` are the LOCAL shards of the
-    metrics.  One plane per neighbour crosses NVLink; everything else is the single-GPU kernel."""
+    metrics.  One plane per neighbour crosses NVLink; everything else is the single-GPU kernel.
+
+    With ``comm`` (a :class:`Communicator`) the whole step is ONE C call, ``xg_stencil2_sharded``: planes
+    packed by a kernel, exchanged in one NCCL group on a side stream while the local block is computed.
+    Without it the exchange goes through torch.distributed (any backend; the gloo CPU tests use this)."""
     from . import ops
+
+    if comm is not None:
+        return comm.stencil2(x_local, axis, op, lo, hi, padding, fill_value, pre=pre, post=post)
 
     if lo + hi != 1:
         # grid_ufunc.py:1136-1159: shifting to inner/outer would change the chunk length
