@@ -363,6 +363,17 @@ def run_extras(torch, dist, ops, _capi, x, rank, world, peak):
     f_der3 = lambda: g3.derivative(d3, "X")
     out.append(rec("C3-sized Grid.derivative('X'), dx(Y,X) fused", timed(f_der3, 5, reps=4), cells, 8 * cells + 4 * ny * nx,
                    count(f_der3), "the C2 operation at a bandwidth-bound size"))
+    # two-field composite: (diff(u dy, X) + diff(v dx, Y)) / area in one pass (3 array streams, 12 B/cell)
+    v3 = torch.empty_like(x)
+    ops.fill_uniform(v3, SEED + 7)
+    dx_t = torch.from_numpy(dx3).to(dev)
+    area_t = dx_t * dx_t
+    spec_a, spec_b = ("diff", 0, 1, "periodic", 0.0), (1, "diff", 0, 1, "periodic", 0.0)
+    f_div = lambda: ops.stencil_pair(x, v3, spec_a, spec_b, 0, pre_a=dx_t, pre_b=dx_t, post=area_t)
+    out.append(rec("C3-sized divergence (diff(u dy,'X') + diff(v dx,'Y')) / rA, one fused pass (xg_stencil_pair)",
+                   timed(f_div, 5, reps=4), cells, 12 * cells + 3 * 4 * ny * nx, count(f_div),
+                   "the explicit chain moves ~9 array passes; here read u, read v, write out"))
+    del v3
     f_cum = lambda: g3.cumsum(d3, "Z", padding="fill")
     try:
         out.append(rec("C3-sized Grid.cumsum('Z')", timed(f_cum, 5, reps=4), cells, 8 * cells, count(f_cum), ""))

@@ -137,6 +137,22 @@ XG_API int xg_stencil_multi(int dtype, const void* in, void* out, int ndim, cons
                      const int* bc, const double* fill_value, void* stream);
 
 /*
+ * Two-FIELD composite in one pass (divergence, vorticity ...):
+ *   out = ( OPa(pad_a(a * pre_a)) along the INNERMOST dim  (+ | -)  OPb(pad_b(b * pre_b)) along axis_b ) / post
+ * a, b, out and every metric are laid out against the one common `shape` (both stencils are length
+ * preserving: lo + hi == 1).  Rounded operator by operator like the chain of Grid.diff / xarray arithmetic it
+ * replaces (xgcm docs/ufunc_examples.md:105-153, grid.py:796-832): a*pre_a, OPa, b*pre_b, OPb, the sum or
+ * difference (`subtract`: 0 = a + b, 1 = term a - term b, 2 = term b - term a), the division.
+ * Boundaries: periodic, fill, extend.
+ */
+XG_API int xg_stencil_pair(int dtype, const void* a, const void* b, void* out, int ndim,
+                    const int64_t* shape, int op_a, int lo_a, int hi_a, int bc_a, double fill_a,
+                    const void* pre_a, const int64_t* pre_a_strides, int axis_b, int op_b, int lo_b,
+                    int hi_b, int bc_b, double fill_b, const void* pre_b,
+                    const int64_t* pre_b_strides, int subtract, const void* post,
+                    const int64_t* post_strides, void* stream);
+
+/*
  * Cumulative sum along one axis with xgcm's position-shift bookkeeping:
  * c = cumsum(in * pre) (from the high end when reverse), then trim, then pad
  * (pad_lo, pad_hi in {0,1}) with `bc` applied to the cumsum'd data, then / post.

@@ -299,3 +299,16 @@ def vinterp_conservative(phi, theta, target_bins, axis=-1):
         # tests use that is the bin axis.  We reverse the bin axis for any rank.
         out = out[:, ::-1]
     return out.reshape(pm.shape[:-1] + (target_bins.shape[0] - 1,))
+
+
+def stencil_pair(op_a, a, axis_a, lo_a, hi_a, bc_a, fill_a, pre_a, op_b, b, axis_b, lo_b, hi_b, bc_b, fill_b, pre_b,
+                 subtract=False, post=None):
+    """The chain a user writes with the reference (docs/ufunc_examples.md:105-153; xgcm/grid.py:796-832 per term):
+    (op_a(a * pre_a, axis_a) +- op_b(b * pre_b, axis_b)) / post, every step a separate numpy pass."""
+    ta = stencil2(op_a, a, axis_a, lo_a, hi_a, bc_a, fill_a, pre_a, None)
+    tb = stencil2(op_b, b, axis_b, lo_b, hi_b, bc_b, fill_b, pre_b, None)
+    r = ta + tb if not subtract else (ta - tb if int(subtract) == 1 else tb - ta)
+    if post is not None:
+        with np.errstate(invalid="ignore", divide="ignore"):
+            r = r / post
+    return r.astype(np.asarray(a).dtype)

@@ -145,6 +145,16 @@ def install(monkeypatch):
                             device=None):
         return vinterp_linear(phi, theta, target, axis, mask_edges, bypass_checks, logarithmic).numpy()
 
+    def stencil_pair(a, b, spec_a, spec_b, subtract=0, pre_a=None, pre_b=None, post=None):
+        op_a, lo_a, hi_a, pad_a, fill_a = spec_a
+        axis_b, op_b, lo_b, hi_b, pad_b, fill_b = spec_b
+        aa = _np(a)
+        r = oracle.stencil_pair(op_a, aa, aa.ndim - 1, lo_a, hi_a, pad_a, fill_a, _np(pre_a), op_b, _np(b), axis_b, lo_b,
+                                hi_b, pad_b, fill_b, _np(pre_b), subtract, _np(post))
+        return _t(r)
+
+    monkeypatch.setattr(ops, "stencil_pair", stencil_pair)
+
     def stencil2_host_multi(x, specs, outs=None, device=None):
         return [stencil2(x, ax, op, lo, hi, pad_ if (lo or hi) else None, 0.0 if fv is None else fv).numpy()
                 for ax, op, lo, hi, pad_, fv in specs]

@@ -535,3 +535,40 @@ def test_cumint_equals_cumsum_of_product():
         got = grid.cumint(da, axes, padding="fill")
         assert got.dims == want.dims
         np.testing.assert_array_equal(got.values, want.values)
+
+
+@pytest.mark.parametrize("grid_type", ["C"])
+def test_pair_divergence_vorticity_equal_the_explicit_chain(grid_type):
+    """Extension: Grid.pair / divergence / vorticity == the chain of Grid.diff calls and array
+    arithmetic a user writes with the reference (docs/ufunc_examples.md:105-153), bit for bit."""
+    ds, coords, metrics, _ = _metric_grid(grid_type)
+    grid = xg.Grid(ds, coords=coords, metrics=metrics, padding={"X": "periodic", "Y": "periodic", "Z": "fill"},
+                   autoparse_metadata=False)
+    u, v = ds["u"], ds["v"]  # u on (xu, yt), v on (xt, yu): right-shifted C-grid
+    # the innermost dim of the fixtures is z; put x last for one variant so that the fused kernel engages
+    for order in (("time", "zt", None, None), None):
+        if order is None:
+            uu, vv = u, v
+        else:
+            uu = u.transpose("time", "zt", "yt", "xu")
+            vv = v.transpose("time", "zt", "yu", "xt")
+        dy_u = grid.get_metric(uu, ("Y",))
+        dx_v = grid.get_metric(vv, ("X",))
+        want = grid.diff(uu * dy_u, "X") + grid.diff(vv * dx_v, "Y")
+        want = want / grid.get_metric(want, ("X", "Y"))
+        got = grid.divergence(uu, vv)
+        assert got.dims == want.dims
+        np.testing.assert_array_equal(got.values, want.values)
+        dy_v = grid.get_metric(vv, ("Y",))
+        dx_u = grid.get_metric(uu, ("X",))
+        zw = grid.diff(vv * dy_v, "X") - grid.diff(uu * dx_u, "Y")
+        zw = zw / grid.get_metric(zw, ("X", "Y"))
+        got = grid.vorticity(uu, vv)
+        assert got.dims == zw.dims
+        np.testing.assert_array_equal(got.values, zw.values)
+        # plain pair without metrics, interp + diff, sub
+        want = grid.interp(uu, "X", padding="extend") - grid.diff(vv, "Y", padding="extend")
+        got = grid.pair("interp", uu, "X", "diff", vv, "Y", combine="sub", padding="extend")
+        np.testing.assert_array_equal(got.values, want.values)
+    with pytest.raises(ValueError, match="different positions"):
+        grid.pair("diff", u, "X", "diff", u, "Y")

@@ -102,6 +102,11 @@ SIGNATURES = {
          C.c_int, C.c_int],
     ),
     "xg_host_workspace_release": (C.c_int, []),
+    "xg_stencil_pair": (
+        C.c_int,
+        [C.c_int, _vp, _vp, _vp, C.c_int, _i64p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _i64p,
+         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, _vp, _i64p, C.c_int, _vp, _i64p, _vp],
+    ),
     "xg_nccl_load": (C.c_int, [C.c_char_p]),
     "xg_comm_unique_id": (C.c_int, [_vp]),
     "xg_comm_init": (C.c_int, [_vp, C.c_int, C.c_int, _vpp]),

@@ -108,58 +108,72 @@ struct XgComm {
   cudaEvent_t ready = nullptr, done = nullptr;
 };
 
-// ---- plane kernels (plane-sized work: simple scalar threads) ---------------------------------------------
-__device__ __forceinline__ int64_t operand_off(const XgOperand& m, int64_t o, int64_t j, int64_t i) {
-  int64_t off = xg_groups_offset(m.outer, o) + j * m.axis_stride;
-  if (m.inner_mode == XG_IM_CONTIG) off += i;
-  else if (m.inner_mode == XG_IM_GENERIC) off += xg_groups_offset(m.inner, i);
-  return off;
-}
-
+// ---- plane kernels: one thread per 16-byte vector of a plane (scalar when the layout does not allow) -------
 template <typename T>
 struct PlaneArgs {
   const T* in;
   int64_t outer, n, inner;
+  int64_t nvec_inner;  // vectors (or scalars) per row of `inner`
+  bool small;          // outer * nvec_inner < 2^31
   XgOperand pre, post;
 };
 
 // dst[o, i] = in[o, j, i] * pre[o, j, i]   (the halo carries field x metric, like the reference's padded array)
-template <typename T>
+template <typename T, int VEC>
 __global__ void __launch_bounds__(256) k_pack_plane(const PlaneArgs<T> a, int64_t j, T* dst) {
-  const int64_t total = a.outer * a.inner;
-  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (int64_t)gridDim.x * 256) {
-    const int64_t o = g / a.inner, i = g - o * a.inner;
-    T v = a.in[(o * a.n + j) * a.inner + i];
-    if (a.pre.ptr) v = v * reinterpret_cast<const T*>(a.pre.ptr)[operand_off(a.pre, o, j, i)];
-    dst[g] = v;
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (g >= a.outer * a.nvec_inner) return;
+  int64_t o, iv;
+  xg_divmod(g, a.nvec_inner, a.small, o, iv);
+  const int64_t i = iv * VEC;
+  XgPack<T, VEC> v = xg_ld_stream<T, VEC>(a.in + (o * a.n + j) * a.inner + i);
+  if (a.pre.ptr) {
+    const XgOperandView<T, VEC> pv = xg_operand_view<T, VEC>(a.pre, xg_groups_offset(a.pre.outer, o), i);
+    const XgPack<T, VEC> m = xg_ld_view<T, VEC>(pv, j * a.pre.axis_stride);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v.v[k] = v.v[k] * m.v[k];
   }
+  xg_st_stream<T, VEC>(dst + o * a.inner + i, v);
 }
 
 // out[o, j_out, i] = OP(P_lo, P_hi) / post : the plane next to a shard boundary, with the received halo as the
 // missing operand.  low side: P_lo = halo, P_hi = in[., j_src, .] * pre;  high side: the other way round.
-template <typename T, int OP>
+template <typename T, int VEC, int OP>
 __global__ void __launch_bounds__(256) k_edge_fix(const PlaneArgs<T> a, const T* halo, int low_side, int64_t j_src,
                                                   int64_t j_out, int64_t n_out, T* out) {
-  const int64_t total = a.outer * a.inner;
-  for (int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x; g < total; g += (int64_t)gridDim.x * 256) {
-    const int64_t o = g / a.inner, i = g - o * a.inner;
-    T v = a.in[(o * a.n + j_src) * a.inner + i];
-    if (a.pre.ptr) v = v * reinterpret_cast<const T*>(a.pre.ptr)[operand_off(a.pre, o, j_src, i)];
-    const T h = halo[g];
-    T r = low_side ? xg_apply_op<T, OP>(h, v) : xg_apply_op<T, OP>(v, h);
-    if (a.post.ptr) r = r / reinterpret_cast<const T*>(a.post.ptr)[operand_off(a.post, o, j_out, i)];
-    out[(o * n_out + j_out) * a.inner + i] = r;
+  const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (g >= a.outer * a.nvec_inner) return;
+  int64_t o, iv;
+  xg_divmod(g, a.nvec_inner, a.small, o, iv);
+  const int64_t i = iv * VEC;
+  XgPack<T, VEC> v = xg_ld_stream<T, VEC>(a.in + (o * a.n + j_src) * a.inner + i);
+  const XgPack<T, VEC> h = xg_ld_stream<T, VEC>(halo + o * a.inner + i);
+  if (a.pre.ptr) {
+    const XgOperandView<T, VEC> pv = xg_operand_view<T, VEC>(a.pre, xg_groups_offset(a.pre.outer, o), i);
+    const XgPack<T, VEC> m = xg_ld_view<T, VEC>(pv, j_src * a.pre.axis_stride);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) v.v[k] = v.v[k] * m.v[k];
   }
+  XgPack<T, VEC> r;
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) r.v[k] = low_side ? xg_apply_op<T, OP>(h.v[k], v.v[k]) : xg_apply_op<T, OP>(v.v[k], h.v[k]);
+  if (a.post.ptr) {
+    const XgOperandView<T, VEC> qv = xg_operand_view<T, VEC>(a.post, xg_groups_offset(a.post.outer, o), i);
+    const XgPack<T, VEC> m = xg_ld_view<T, VEC>(qv, j_out * a.post.axis_stride);
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / m.v[k];
+  }
+  xg_st_stream<T, VEC>(out + (o * n_out + j_out) * a.inner + i, r);
 }
 
-template <typename T>
-int launch_edge_fix(int op, const PlaneArgs<T>& a, const T* halo, int low_side, int64_t j_src, int64_t j_out,
-                    int64_t n_out, T* out, unsigned blocks, cudaStream_t st) {
+template <typename T, int VEC>
+int launch_edge_fix_v(int op, const PlaneArgs<T>& a, const T* halo, int low_side, int64_t j_src, int64_t j_out,
+                      int64_t n_out, T* out, unsigned blocks, cudaStream_t st) {
   switch (op) {
-    case XG_OP_DIFF: k_edge_fix<T, XG_OP_DIFF><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
-    case XG_OP_INTERP: k_edge_fix<T, XG_OP_INTERP><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
-    case XG_OP_MIN: k_edge_fix<T, XG_OP_MIN><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
-    case XG_OP_MAX: k_edge_fix<T, XG_OP_MAX><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
+    case XG_OP_DIFF: k_edge_fix<T, VEC, XG_OP_DIFF><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
+    case XG_OP_INTERP: k_edge_fix<T, VEC, XG_OP_INTERP><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
+    case XG_OP_MIN: k_edge_fix<T, VEC, XG_OP_MIN><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
+    case XG_OP_MAX: k_edge_fix<T, VEC, XG_OP_MAX><<<blocks, 256, 0, st>>>(a, halo, low_side, j_src, j_out, n_out, out); break;
     default: return xg_fail(XG_EINVAL, "xg_stencil2_sharded: unknown op");
   }
   return xg_check_launch("xg_stencil2_sharded(edge)");
@@ -218,20 +232,38 @@ int sharded_typed(XgComm* c, int op, const void* in, void* out, int ndim, const 
   rc = xg_make_operand(post_metric, post_strides, ndim, out_shape, axis, VEC, sizeof(T), &pa.post,
                        "xg_stencil2_sharded(post)");
   if (rc) return rc;
-  unsigned blocks = (unsigned)(plane > 0 ? (xg_ceil_div(plane, 256) > 148 * 8 ? 148 * 8 : xg_ceil_div(plane, 256)) : 1);
+  constexpr int VECW = XgVecWidth<T>::value;
+  // 16-byte vectors along `inner` when every row start stays aligned (workspace slots are 256-byte aligned)
+  bool vec_ok = v.inner % VECW == 0 && ((uintptr_t)in % 16 == 0) && ((uintptr_t)out % 16 == 0);
+  if (!vec_ok) {
+    pa.pre.vec_ok = 0;
+    pa.post.vec_ok = 0;
+  }
+  pa.nvec_inner = vec_ok ? v.inner / VECW : v.inner;
+  pa.small = v.outer * pa.nvec_inner < (1ll << 31);
+  const int64_t nblk = xg_ceil_div(v.outer * pa.nvec_inner, 256);
+  if (nblk > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2_sharded: plane too large");
+  const unsigned blocks = (unsigned)(nblk > 0 ? nblk : 1);
+  auto pack = [&](int64_t j, T* dst) -> int {
+    if (vec_ok) k_pack_plane<T, VECW><<<blocks, 256, 0, c->side>>>(pa, j, dst);
+    else k_pack_plane<T, 1><<<blocks, 256, 0, c->side>>>(pa, j, dst);
+    return xg_check_launch("xg_stencil2_sharded(pack)");
+  };
+  auto fix = [&](const T* halo, int low_side, int64_t j_src, int64_t j_out, int64_t n_out_) -> int {
+    if (vec_ok) return launch_edge_fix_v<T, VECW>(op, pa, halo, low_side, j_src, j_out, n_out_, static_cast<T*>(out), blocks, st);
+    return launch_edge_fix_v<T, 1>(op, pa, halo, low_side, j_src, j_out, n_out_, static_cast<T*>(out), blocks, st);
+  };
 
   // ---- side stream: pack + exchange, ordered after whatever produced `in` on the caller's stream
   XG_CUDA(cudaEventRecord(c->ready, st));
   XG_CUDA(cudaStreamWaitEvent(c->side, c->ready, 0));
   if (plane > 0) {
     if (give_lo) {
-      k_pack_plane<T><<<blocks, 256, 0, c->side>>>(pa, 0, send_lo);
-      rc = xg_check_launch("xg_stencil2_sharded(pack)");
+      rc = pack(0, send_lo);
       if (rc) return rc;
     }
     if (give_hi) {
-      k_pack_plane<T><<<blocks, 256, 0, c->side>>>(pa, v.n - 1, send_hi);
-      rc = xg_check_launch("xg_stencil2_sharded(pack)");
+      rc = pack(v.n - 1, send_hi);
       if (rc) return rc;
     }
   }
@@ -254,11 +286,11 @@ int sharded_typed(XgComm* c, int op, const void* in, void* out, int ndim, const 
   XG_CUDA(cudaStreamWaitEvent(st, c->done, 0));
   const int64_t n_out = v.n;  // lo + hi == 1
   if (plane > 0 && need_lo) {
-    rc = launch_edge_fix<T>(op, pa, recv_lo, 1, 0, 0, n_out, static_cast<T*>(out), blocks, st);
+    rc = fix(recv_lo, 1, 0, 0, n_out);
     if (rc) return rc;
   }
   if (plane > 0 && need_hi) {
-    rc = launch_edge_fix<T>(op, pa, recv_hi, 0, v.n - 1, n_out - 1, n_out, static_cast<T*>(out), blocks, st);
+    rc = fix(recv_hi, 0, v.n - 1, n_out - 1, n_out);
     if (rc) return rc;
   }
   return XG_OK;

@@ -638,6 +638,117 @@ class Grid:
             results.append(self._wrap_out(res, as_xarray))
         return results
 
+    # ------------------------------------------------------------------ two-field composites (extension)
+    def pair(self, funcname_a, da_a, axis_a, funcname_b, da_b, axis_b, combine="add", metric_a=None,
+             metric_b=None, divide_by=None, to=None, padding=None, fill_value=None):
+        """``(f_a(da_a * metric_a, axis_a)  +|-  f_b(da_b * metric_b, axis_b)) / metric_out`` — what users chain
+        from ``Grid.diff`` / ``Grid.interp`` and xarray arithmetic for divergence-like quantities
+        (docs/ufunc_examples.md:105-153), evaluated in ONE kernel (``xg_stencil_pair``) when both terms are
+        length-preserving stencils along different dims of same-shaped fields; rounding is that of the chain.
+
+        ``metric_a`` / ``metric_b``: axes whose metric (``get_metric`` at the input's position) multiplies the
+        input; ``divide_by``: axes whose metric at the OUTPUT position divides the result; ``combine``: "add" or
+        "sub" (term a minus term b).  Anything the fused kernel does not cover runs as the explicit chain."""
+        from . import ops
+        from .device import as_device_tensor, result_like
+
+        if combine not in ("add", "sub"):
+            raise ValueError(f"combine must be 'add' or 'sub', got {combine!r}")
+        da_a, xr_a = self._wrap_in(da_a)
+        da_b, xr_b = self._wrap_in(da_b)
+        as_xarray = xr_a or xr_b
+        to = self._map_kwargs_over_axes(to)
+        kw = {}
+        if padding is not None:
+            kw["padding"] = padding
+        if fill_value is not None:
+            kw["fill_value"] = fill_value
+
+        def as_tuple(m):
+            return (m,) if isinstance(m, str) else (tuple(m) if m is not None else None)
+
+        metric_a, metric_b, divide_by = as_tuple(metric_a), as_tuple(metric_b), as_tuple(divide_by)
+
+        def chain():
+            xa = da_a * self.get_metric(da_a, metric_a) if metric_a else da_a
+            xb = da_b * self.get_metric(da_b, metric_b) if metric_b else da_b
+            ta = self._1d_grid_ufunc_dispatch(funcname_a, xa, axis_a, to={axis_a: to.get(axis_a)}, **kw)
+            tb = self._1d_grid_ufunc_dispatch(funcname_b, xb, axis_b, to={axis_b: to.get(axis_b)}, **kw)
+            if ta.dims != tb.dims:
+                raise ValueError(f"the two terms land on different positions: {ta.dims} vs {tb.dims}")
+            r = ta + tb if combine == "add" else ta - tb
+            if divide_by:
+                r = r / self.get_metric(r, divide_by)
+            r.name = da_a.name
+            return self._wrap_out(r, as_xarray)
+
+        if (isinstance(da_a, dict) or isinstance(da_b, dict) or self._face_connections is not None
+                or axis_a == axis_b or da_a.shape != da_b.shape or da_a.is_device != da_b.is_device):
+            return chain()
+        paddings = self._complete_user_kwargs_using_axis_defaults(padding, "padding")
+        fills = self._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
+        terms = []
+        for funcname, da, ax_name in ((funcname_a, da_a, axis_a), (funcname_b, da_b, axis_b)):
+            if funcname not in ("diff", "interp", "min", "max") or ax_name not in self.axes:
+                return chain()
+            sig = self._create_1d_grid_ufunc_signatures(da, axis=[ax_name], to={ax_name: to.get(ax_name)})[0]
+            grid_ufunc, _ = _select_grid_ufunc(funcname, sig, module=gridops)
+            dummy = grid_ufunc.signature.in_ax_names[0][0]
+            lo, hi = (grid_ufunc.padding_width or {}).get(dummy, (0, 0))
+            from_pos, to_pos = sig.in_ax_positions[0][0], sig.out_ax_positions[0][0]
+            in_dim = self.axes[ax_name].coords[from_pos]
+            out_dim = self.axes[ax_name].coords.get(to_pos)
+            if out_dim is None or lo + hi != 1 or paddings[ax_name] not in ("periodic", "fill", "extend"):
+                return chain()
+            fv = fills[ax_name] if fills[ax_name] is not None else 0.0
+            terms.append(dict(op=funcname, lo=lo, hi=hi, pad=paddings[ax_name], fill=fv, axn=da.get_axis_num(in_dim),
+                              in_dim=in_dim, out_dim=out_dim, ax=ax_name))
+        ta, tb = terms
+        out_dims_a = tuple(ta["out_dim"] if d == ta["in_dim"] else d for d in da_a.dims)
+        out_dims_b = tuple(tb["out_dim"] if d == tb["in_dim"] else d for d in da_b.dims)
+        # each term leaves the other's operated dim untouched: the sum needs both to land on the same dims
+        if out_dims_a != out_dims_b:
+            raise ValueError(f"the two terms land on different positions: {out_dims_a} vs {out_dims_b}")
+        last = da_a.ndim - 1
+        if ta["axn"] == last and tb["axn"] != last:
+            first, second, fa, fb, ma_ax, mb_ax = ta, tb, da_a, da_b, metric_a, metric_b
+            sub = 0 if combine == "add" else 1
+        elif tb["axn"] == last and ta["axn"] != last:
+            first, second, fa, fb, ma_ax, mb_ax = tb, ta, da_b, da_a, metric_b, metric_a
+            sub = 0 if combine == "add" else 2  # kernel: innermost term first; we want (a - b) = strided - innermost
+        else:
+            return chain()  # neither (or both) terms act on the innermost dim
+        host = not da_a.is_device
+        dev = self._device_for(da_a)
+        xa, _ = as_device_tensor(fa.data, dev)
+        xb, _ = as_device_tensor(fb.data, dev)
+        if xa.dtype != xb.dtype:
+            return chain()
+        pre_a = self._metric_tensor(self.get_metric(fa, ma_ax), fa.dims, xa) if ma_ax else None
+        pre_b = self._metric_tensor(self.get_metric(fb, mb_ax), fb.dims, xb) if mb_ax else None
+        post = None
+        if divide_by:
+            probe = DataArray.__new__(DataArray)
+            probe._dims = out_dims_a
+            post = self._metric_tensor(self.get_metric(probe, divide_by), out_dims_a, xa)
+        y = ops.stencil_pair(xa, xb, (first["op"], first["lo"], first["hi"], first["pad"], first["fill"]),
+                             (second["axn"], second["op"], second["lo"], second["hi"], second["pad"], second["fill"]),
+                             sub, pre_a=pre_a, pre_b=pre_b, post=post)
+        res = DataArray(result_like(y, host), dims=out_dims_a, name=da_a.name)
+        res = _reattach_coords([res], self, None, {ta["out_dim"], tb["out_dim"]}, [da_a, da_b])[0]
+        return self._wrap_out(res, as_xarray)
+
+    def divergence(self, u, v, axis_u="X", axis_v="Y", **kwargs):
+        """Finite-volume horizontal divergence ``(diff(u * dy, X) + diff(v * dx, Y)) / area`` on a C-grid, metrics
+        from ``get_metric`` (u * its Y-metric, v * its X-metric, area at the output position); one fused pass."""
+        return self.pair("diff", u, axis_u, "diff", v, axis_v, combine="add", metric_a=(axis_v,), metric_b=(axis_u,),
+                         divide_by=(axis_u, axis_v), **kwargs)
+
+    def vorticity(self, u, v, axis_u="X", axis_v="Y", **kwargs):
+        """Vertical relative vorticity ``(diff(v * dy, X) - diff(u * dx, Y)) / area`` on a C-grid; one fused pass."""
+        return self.pair("diff", v, axis_u, "diff", u, axis_v, combine="sub", metric_a=(axis_v,), metric_b=(axis_u,),
+                         divide_by=(axis_u, axis_v), **kwargs)
+
     def apply_as_grid_ufunc(self, func: Callable, *args, axis=None, signature="", padding_width=None,
                             padding=None, fill_value=None, dask="forbidden", map_overlap=False,
                             **kwargs):

@@ -573,6 +573,40 @@ def stencil2_host(
     return out
 
 
+def stencil_pair(a: torch.Tensor, b: torch.Tensor, spec_a, spec_b, subtract: int = 0,
+                 pre_a: Optional[torch.Tensor] = None, pre_b: Optional[torch.Tensor] = None,
+                 post: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """``(OPa(a * pre_a) along the innermost dim  +|-  OPb(b * pre_b) along another dim) / post`` in one pass
+    (``xg_stencil_pair``).  ``spec_a = (op, lo, hi, padding, fill)`` acts on the LAST dim, ``spec_b =
+    (axis, op, lo, hi, padding, fill)`` on ``axis`` != last.  All arrays share ``a``'s shape; metrics broadcast."""
+    lib = _capi.load()
+    _require_cuda(a, "field a")
+    _require_cuda(b, "field b")
+    if a.shape != b.shape or a.dtype != b.dtype:
+        raise ValueError("stencil_pair: both fields must have the same shape and dtype")
+    a, b = a.contiguous(), b.contiguous()
+    op_a, lo_a, hi_a, pad_a, fill_a = spec_a
+    axis_b, op_b, lo_b, hi_b, pad_b, fill_b = spec_b
+    axis_b = _norm_axis(axis_b, a.dim())
+    for pad_ in (pad_a, pad_b):
+        if pad_ not in ("periodic", "fill", "extend"):
+            raise ValueError(f"padding must be one of ['periodic', 'fill', 'extend'], but got {pad_}")
+    shape = list(a.shape)
+    out = torch.empty_like(a)
+    k1, pa_ptr, pa_st = _operand(pre_a, shape, a, "pre metric a")
+    k2, pb_ptr, pb_st = _operand(pre_b, shape, a, "pre metric b")
+    k3, po_ptr, po_st = _operand(post, shape, a, "post metric")
+    if out.numel():
+        with torch.cuda.device(a.device):
+            rc = lib.xg_stencil_pair(
+                _dtype_code(a), a.data_ptr(), b.data_ptr(), out.data_ptr(), a.dim(), _capi.i64_array(shape),
+                _capi.OPS[op_a], lo_a, hi_a, _capi.BCS[pad_a], float(0.0 if fill_a is None else fill_a), pa_ptr, pa_st,
+                axis_b, _capi.OPS[op_b], lo_b, hi_b, _capi.BCS[pad_b], float(0.0 if fill_b is None else fill_b),
+                pb_ptr, pb_st, int(subtract), po_ptr, po_st, _stream_ptr(a))
+        _capi.check(rc)
+    return out
+
+
 # --------------------------------------------------------------------------- host twins (slab pipelines)
 def _host_field(x, what):
     if not isinstance(x, np.ndarray):
