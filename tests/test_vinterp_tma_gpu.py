@@ -154,3 +154,83 @@ def test_tma_full_size_c5_samples():
     a = x[:, -1:, -64:].cpu().numpy()
     want = oracle.vinterp_linear(a, depth.reshape(-1, 1, 1) * np.ones((1, 1, 64), np.float32), levels, 0, True)
     np.testing.assert_array_equal(out[-1:, -64:].cpu().numpy(), want)
+
+
+# ----------------------------------------------------------------------------- theta FIELD (columns kernel)
+COLS_TMA = "xg_vinterp_linear(columns, tma)"
+
+
+def _theta_field(shape, axis, dtype, rng, decreasing_frac=0.3, nan_frac=0.0, unsorted_frac=0.0):
+    inc = np.cumsum(0.1 + rng.random(shape), axis=axis).astype(dtype)
+    flip_shape = [s if d != axis else 1 for d, s in enumerate(shape)]
+    th = np.where(rng.random(flip_shape) < decreasing_frac, np.flip(inc, axis=axis), inc).astype(dtype)
+    if unsorted_frac:
+        sw = rng.random(flip_shape) < unsorted_frac
+        a, b = np.take(th, [3], axis=axis), np.take(th, [5], axis=axis)
+        idx3 = [slice(None)] * len(shape)
+        idx5 = [slice(None)] * len(shape)
+        idx3[axis], idx5[axis] = slice(3, 4), slice(5, 6)
+        th[tuple(idx3)] = np.where(sw, b, a)
+        th[tuple(idx5)] = np.where(sw, a, b)
+    if nan_frac:
+        th[rng.random(shape) < nan_frac] = np.nan
+    return th
+
+
+@pytest.mark.parametrize("wt", ["0", "1", "3"])
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,axis", [((20, 64), 0), ((75, 5, 44), 0), ((3, 25, 40), 1), ((2, 31, 5, 36), 1), ((9, 2, 1028), 0)])
+def test_columns_tma_matches_oracle(monkeypatch, wt, dtype, shape, axis):
+    from xgcm_b200 import _capi, ops
+
+    monkeypatch.setenv("XG_VINTERP_WT", wt)
+    rng = np.random.default_rng(17)
+    phi = rng.standard_normal(shape).astype(dtype)
+    phi[rng.random(shape) < 0.02] = np.nan
+    for kind in ("sorted", "nan", "unsorted", "allnan_cols"):
+        theta = _theta_field(shape, axis, dtype, rng, nan_frac=0.04 if kind == "nan" else 0.0,
+                             unsorted_frac=0.3 if kind == "unsorted" else 0.0)
+        if kind == "allnan_cols":
+            col_shape = [s if d != axis else 1 for d, s in enumerate(shape)]
+            theta = np.where(rng.random(col_shape) < 0.2, np.nan, theta).astype(dtype)
+        lo, hi = float(np.nanmin(theta)), float(np.nanmax(theta))
+        for m in (1, 6, 33, 100):
+            target = np.linspace(lo - 0.3, hi + 0.3, m).astype(dtype)
+            if m >= 6:
+                target[2] = np.nan
+                target[3] = theta.reshape(-1)[0] if not np.isnan(theta.reshape(-1)[0]) else target[3]
+            for tg in (target, target[::-1].copy()):
+                for mask, bypass in ((True, False), (False, False), (True, True)):
+                    with np.errstate(invalid="ignore"):
+                        want = oracle.vinterp_linear(phi, theta, tg, axis, mask, bypass)
+                    got = ops.vinterp_linear(_t(phi), _t(theta), _t(tg), axis, mask, bypass).cpu().numpy()
+                    assert _capi.last_launch() == COLS_TMA, _capi.last_launch()
+                    np.testing.assert_array_equal(got, want, err_msg=f"{kind} m={m} mask={mask} bypass={bypass}")
+
+
+def test_columns_tma_log_and_full_size_samples():
+    from xgcm_b200 import _capi, ops
+
+    rng = np.random.default_rng(23)
+    shape = (30, 5, 64)
+    phi = rng.random(shape)
+    theta = np.cumsum(1.0 + rng.random(shape), axis=0)
+    target = np.linspace(0.5, float(theta.max()) + 1, 16)
+    want = oracle.vinterp_linear(phi, theta, target, 0, True, False, True)
+    got = ops.vinterp_linear(_t(phi), _t(theta), _t(target), 0, True, False, True).cpu().numpy()
+    assert _capi.last_launch() == COLS_TMA
+    np.testing.assert_allclose(got, want, rtol=1e-12, atol=1e-12, equal_nan=True)
+    # C5-sized field with a per-column theta
+    nz, ny, nx, m = 75, 2400, 3600, 100
+    x = torch.empty((nz, ny, nx), dtype=torch.float32, device=DEV)
+    ops.fill_uniform(x, 0xC0FFEE)
+    th = torch.cumsum(x + 0.5, 0)
+    levels = torch.linspace(0.0, float(th.max()) + 1, m, device=DEV)
+    out = ops.vinterp_linear(x, th, levels, 0, True)
+    assert _capi.last_launch() == COLS_TMA
+    for _ in range(4):
+        j0, i0 = int(rng.integers(0, ny - 2)), int(rng.integers(0, nx - 40))
+        a = x[:, j0:j0 + 2, i0:i0 + 40].cpu().numpy()
+        t = th[:, j0:j0 + 2, i0:i0 + 40].cpu().numpy()
+        want = oracle.vinterp_linear(a, t, levels.cpu().numpy(), 0, True)
+        np.testing.assert_array_equal(out[j0:j0 + 2, i0:i0 + 40].cpu().numpy(), want)

@@ -15,6 +15,8 @@
 // Work split (as k_stencil_strided): a warp owns 32 x VEC contiguous cells of the innermost dim and marches J
 // cells along axis b keeping B's previous row in registers; the x-neighbour of A comes from a warp shuffle,
 // only the lanes at a warp or row edge do one extra scalar load (or take the boundary value).
+#include <stdlib.h>
+
 #include "xg_common.cuh"
 
 namespace {
@@ -55,7 +57,20 @@ __device__ __forceinline__ int64_t operand_inner_off(const XgOperand& m, int64_t
   return 0;
 }
 
-template <typename T, int VEC, bool MET>
+// OPS >= 0: both operators known at compile time (OPS = op_a * 4 + op_b), the common diff / interp pairs;
+// OPS < 0: operators read from the arguments (min / max combinations)
+template <typename T, int OPS>
+__device__ __forceinline__ T op_first(const int op_rt, T lo_v, T hi_v) {
+  if constexpr (OPS >= 0) return xg_apply_op<T, OPS / 4>(lo_v, hi_v);
+  else return apply_rt<T>(op_rt, lo_v, hi_v);
+}
+template <typename T, int OPS>
+__device__ __forceinline__ T op_second(const int op_rt, T lo_v, T hi_v) {
+  if constexpr (OPS >= 0) return xg_apply_op<T, OPS % 4>(lo_v, hi_v);
+  else return apply_rt<T>(op_rt, lo_v, hi_v);
+}
+
+template <typename T, int VEC, bool MET, int U, int OPS>
 __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> p) {
   typedef XgPack<T, VEC> Pack;
   const unsigned FULL = 0xffffffffu;
@@ -97,13 +112,18 @@ __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> 
                     operand_inner_off(p.ma, ii));
     return v;
   };
-  auto termA = [&](int64_t j) -> Pack {
+  // A x ma, row j (the thread's own vector)
+  auto loadA = [&](int64_t j) -> Pack {
     Pack va = xg_ld_stream<T, VEC>(abase + j * p.inner);
     if (has_ma) {
       const Pack m = xg_ld_view<T, VEC>(ma_v, j * p.ma.axis_stride);
 #pragma unroll
       for (int k = 0; k < VEC; ++k) va.v[k] = va.v[k] * m.v[k];
     }
+    return va;
+  };
+  // the stencil along x on a loaded row: neighbour from the adjacent lane, the warp / row edges on their own
+  auto termA = [&](int64_t j, const Pack& va) -> Pack {
     Pack r;
     if (p.lo_a) {  // out[x] = OP(P[x-1], P[x])
       T left = __shfl_up_sync(FULL, va.v[VEC - 1], 1);
@@ -115,7 +135,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> 
         left = scalarA(j, i - 1);
       }
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) r.v[k] = apply_rt<T>(p.op_a, k == 0 ? left : va.v[k > 0 ? k - 1 : 0], va.v[k]);
+      for (int k = 0; k < VEC; ++k) r.v[k] = op_first<T, OPS>(p.op_a, k == 0 ? left : va.v[k > 0 ? k - 1 : 0], va.v[k]);
     } else {  // out[x] = OP(P[x], P[x+1])
       T right = __shfl_down_sync(FULL, va.v[0], 1);
       if (row_last) {
@@ -127,7 +147,7 @@ __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> 
       }
 #pragma unroll
       for (int k = 0; k < VEC; ++k)
-        r.v[k] = apply_rt<T>(p.op_a, va.v[k], k == VEC - 1 ? right : va.v[k < VEC - 1 ? k + 1 : k]);
+        r.v[k] = op_first<T, OPS>(p.op_a, va.v[k], k == VEC - 1 ? right : va.v[k < VEC - 1 ? k + 1 : k]);
     }
     return r;
   };
@@ -155,15 +175,12 @@ __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> 
     return loadB(s < 0 ? 0 : p.nb - 1);
   };
 
-  Pack prev = padB(j0);
-#pragma unroll 2
-  for (int64_t j = j0; j < j1; ++j) {
-    const Pack cur = padB(j + 1);
-    const Pack ta = termA(j);
+  auto emit = [&](int64_t j, const Pack& prev_b, const Pack& cur_b, const Pack& va) {
+    const Pack ta = termA(j, va);
     Pack r;
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
-      const T tb = apply_rt<T>(p.op_b, prev.v[k], cur.v[k]);
+      const T tb = op_second<T, OPS>(p.op_b, prev_b.v[k], cur_b.v[k]);
       r.v[k] = p.subtract == 0 ? ta.v[k] + tb : (p.subtract == 1 ? ta.v[k] - tb : tb - ta.v[k]);
     }
     if (has_post) {
@@ -172,6 +189,28 @@ __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> 
       for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / m.v[k];
     }
     if (valid) xg_st_stream<T, VEC>(obase + j * p.inner, r);
+  };
+  Pack prev = padB(j0);
+  // rows whose upper B operand is an ordinary source row: U rows of both fields in flight per thread
+  const int64_t jm = (j1 < p.nb + p.lo_b - 1) ? j1 : (p.nb + p.lo_b - 1);
+  int64_t j = j0;
+  for (; j + U <= jm; j += U) {
+    Pack cb[U], va[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      cb[u] = loadB(j + u + 1 - p.lo_b);
+      va[u] = loadA(j + u);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      emit(j + u, prev, cb[u], va[u]);
+      prev = cb[u];
+    }
+  }
+#pragma unroll 1
+  for (; j < j1; ++j) {
+    const Pack cur = padB(j + 1);
+    emit(j, prev, cur, loadA(j));
     prev = cur;
   }
 }
@@ -187,10 +226,25 @@ int launch_pair(PairArgs<T>& p, cudaStream_t st) {
   p.small_inner = p.inner < (1ll << 31);
   const int64_t blocks = xg_ceil_div(p.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil_pair: grid too large");
-  if (p.ma.ptr || p.mb.ptr || p.post.ptr)
-    k_stencil_pair<T, VEC, true><<<(unsigned)blocks, kThreads, 0, st>>>(p);
-  else
-    k_stencil_pair<T, VEC, false><<<(unsigned)blocks, kThreads, 0, st>>>(p);
+  const bool met = p.ma.ptr || p.mb.ptr || p.post.ptr;
+  const bool ct = p.op_a <= XG_OP_INTERP && p.op_b <= XG_OP_INTERP;  // diff / interp pairs: compile-time operators
+  const int ops = ct ? p.op_a * 4 + p.op_b : -1;
+#define XG_PAIR_LAUNCH(MET_, U_, OPS_) k_stencil_pair<T, VEC, MET_, U_, OPS_><<<(unsigned)blocks, kThreads, 0, st>>>(p)
+#define XG_PAIR_OPS(MET_, U_)                                         \
+  switch (ops) {                                                      \
+    case XG_OP_DIFF * 4 + XG_OP_DIFF: XG_PAIR_LAUNCH(MET_, U_, XG_OP_DIFF * 4 + XG_OP_DIFF); break;       \
+    case XG_OP_DIFF * 4 + XG_OP_INTERP: XG_PAIR_LAUNCH(MET_, U_, XG_OP_DIFF * 4 + XG_OP_INTERP); break;   \
+    case XG_OP_INTERP * 4 + XG_OP_DIFF: XG_PAIR_LAUNCH(MET_, U_, XG_OP_INTERP * 4 + XG_OP_DIFF); break;   \
+    case XG_OP_INTERP * 4 + XG_OP_INTERP: XG_PAIR_LAUNCH(MET_, U_, XG_OP_INTERP * 4 + XG_OP_INTERP); break; \
+    default: XG_PAIR_LAUNCH(MET_, U_, -1); break;                     \
+  }
+  if (met) {
+    XG_PAIR_OPS(true, 2)
+  } else {
+    XG_PAIR_OPS(false, 4)
+  }
+#undef XG_PAIR_OPS
+#undef XG_PAIR_LAUNCH
   return xg_check_launch("xg_stencil_pair");
 }
 

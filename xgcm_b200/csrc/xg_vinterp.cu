@@ -485,6 +485,7 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
   a.n = v.n;
   a.inner = v.inner;
   a.m = m;
+  a.theta_full = false;
   a.mask_edges = mask_edges;
   a.bypass_checks = bypass_checks;
   a.logarithmic = logarithmic;
@@ -540,6 +541,20 @@ int vinterp_typed(const void* phi, const void* theta, const int64_t* theta_strid
     if (blocks > (int64_t)sms * per_sm) blocks = (int64_t)sms * per_sm;
     k_vinterp_shared<T><<<(unsigned)blocks, kWarps * 32, plan_bytes, st>>>(a);
     return xg_check_launch("xg_vinterp_linear(shared)");
+  }
+  {
+    // theta a full field laid out like phi, one shared level vector: tiles of phi AND theta staged by TMA
+    bool full = true;
+    int64_t want = 1;
+    for (int d = ndim - 1; d >= 0; --d) {
+      if (shape[d] > 1 && theta_strides[d] != want) full = false;
+      want *= shape[d];
+    }
+    a.theta_full = full;
+    if (full && all_bcast(a.target)) {
+      const int r = vinterp_columns_tma<T>(a, st);
+      if (r != 0) return r < 0 ? r : XG_OK;
+    }
   }
   const int64_t blocks = xg_ceil_div(a.ntiles, kWarpsCol);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_vinterp_linear: grid too large");

@@ -19,6 +19,7 @@ struct InterpArgs {
   int mask_edges, bypass_checks, logarithmic;
   int64_t ntiles;    // column tiles of 32
   bool small_cols;   // outer * inner < 2^31
+  bool theta_full;   // theta is a C-contiguous field of phi's shape (same strides)
 };
 
 template <typename T>

@@ -601,9 +601,372 @@ int vinterp_shared_tma(const InterpArgs<T>& a, cudaStream_t st) {
   return launch_shared<T, 1>(a, st, sms, smem_max);
 }
 
+// =====================================================================================================
+// theta FIELD (one theta column per phi column), shared target levels — `Grid.transform(da, 'Z', levels,
+// target_data=<3-D field>)`, e.g. density coordinates.  Same machinery as above: tiles of 32 columns, phi AND
+// theta levels of a tile staged by two TMA box loads on one mbarrier, the 32 x m results leave as one bulk
+// store, teams of warps split a tile's targets.  What differs is the arithmetic: the interval search runs per
+// column (lane = column, all reads from shared memory — the old kernel's dependent global loads, 0.13 of
+// peak, are gone) and each (column, interval) needs a true fp64 division.
+//
+// np.interp's search is replayed exactly as k_vinterp_columns does: columns whose (possibly flipped) theta is
+// NaN-free and sorted walk forward from the current interval (the guess cannot change the answer there);
+// every other column replays binary_search_with_guess literally, carrying the guess from target 0 on (a warp
+// that starts at target tb > 0 first replays the searches of targets 0 .. tb-1 for those columns).
+namespace {
+
 template <typename T>
-int vinterp_columns_tma(const InterpArgs<T>&, cudaStream_t) {
-  return 0;
+struct ColArgs {
+  InterpArgs<T> a;
+  int64_t tiles_per_o, ntiles;
+  int nb, wt;
+  bool small;
+  int box_rows, nbox;
+  unsigned half_bytes;  // one field's box(es): nbox * box_rows * 32 * sizeof(T), rounded up to 128
+  unsigned out_bytes, plan_bytes;
+};
+
+struct ColPartial {  // per (warp of the team, column): what its chunk of levels says about theta
+  int first_k, last_k;  // first / last non-NaN level in the chunk (-1: none)
+  int flags;            // 1: has NaN, 2: some pair ascends strictly, 4: some pair descends strictly
+  int pad;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+    k_vinterp_columns_tma(const __grid_constant__ CUtensorMap map_phi, const __grid_constant__ CUtensorMap map_theta,
+                          const ColArgs<T> p) {
+  constexpr int TC = 32;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const InterpArgs<T>& a = p.a;
+  const int n = (int)a.n, m = (int)a.m;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int W = blockDim.x >> 5, NB = p.nb, WT = p.wt, NT = W / WT;
+  const int team = w / WT, wq = w - team * WT;
+  // layout: xt[m] (double) | xv[m] (T) | full[NB] | wbeg[33] | parts[NT][WT][32] | pad | in[NB] (phi, theta) | out[NT]
+  double* xt = reinterpret_cast<double*>(smem_raw);
+  T* xv = reinterpret_cast<T*>(xt + m);
+  unsigned long long* full = reinterpret_cast<unsigned long long*>(smem_raw + ((size_t)m * (8 + sizeof(T)) + 7) / 8 * 8);
+  int* wbeg = reinterpret_cast<int*>(full + NB);
+  ColPartial* parts = reinterpret_cast<ColPartial*>(wbeg + 36);
+  unsigned char* in0 = smem_raw + p.plan_bytes;
+  unsigned char* out0 = in0 + (size_t)NB * 2 * p.half_bytes;
+  T* out_tile = reinterpret_cast<T*>(out0 + (size_t)team * p.out_bytes);
+  const uint32_t full_u32 = smem_u32(full);
+
+  const int64_t nloc = (p.ntiles > blockIdx.x) ? (p.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  auto tile_geom = [&](int64_t i, int64_t& o, int64_t& i0, int& ncol) {
+    const int64_t g = i * gridDim.x + blockIdx.x;
+    if (p.small) {
+      const uint32_t oo = (uint32_t)g / (uint32_t)p.tiles_per_o;
+      o = oo;
+      i0 = (int64_t)((uint32_t)g - oo * (uint32_t)p.tiles_per_o) * TC;
+    } else {
+      o = g / p.tiles_per_o;
+      i0 = (g - o * p.tiles_per_o) * TC;
+    }
+    const int64_t left = a.inner - i0;
+    ncol = left < TC ? (int)left : TC;
+  };
+  auto issue_load = [&](int64_t i) {
+    const int b = (int)(i % NB);
+    int64_t o, i0;
+    int ncol;
+    tile_geom(i, o, i0, ncol);
+    const uint32_t bar = full_u32 + 8u * b;
+    const unsigned box_bytes = (unsigned)p.box_rows * TC * sizeof(T);
+    mbar_expect_tx(bar, 2u * box_bytes * (unsigned)p.nbox);
+    const uint32_t dst = smem_u32(in0 + (size_t)b * 2 * p.half_bytes);
+    for (int k = 0; k < p.nbox; ++k) {
+      tensor_load_3d(dst + k * box_bytes, &map_phi, (int)i0, k * p.box_rows, (int)o, bar);
+      tensor_load_3d(dst + p.half_bytes + k * box_bytes, &map_theta, (int)i0, k * p.box_rows, (int)o, bar);
+    }
+  };
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_phi) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_theta) : "memory");
+    for (int b = 0; b < NB; ++b) mbar_init(full_u32 + 8u * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (wq == 0 && lane == 0)
+    for (int64_t i = team; i < NB && i < nloc; i += NT) issue_load(i);
+  // ---- per block: the target levels (log applied in the field dtype, transform.py:82-84) and the split
+  const T* target = reinterpret_cast<const T*>(a.target.ptr);
+  const bool logarithmic = a.logarithmic != 0;
+  for (int t = tid; t < m; t += blockDim.x) {
+    T v = __ldg(target + t * a.target.axis_stride);
+    if (logarithmic) v = xg_log<T>(v);
+    xv[t] = v;
+    xt[t] = (double)v;
+  }
+  if (tid == 0) {
+    const int unit = (m % 2 == 0) ? 2 : 1, units = m / unit;
+    for (int q = 0; q <= WT; ++q) wbeg[q] = (int)((int64_t)units * q / WT) * unit;
+    wbeg[WT] = m;
+  }
+  __syncthreads();
+  const bool pair_ok = (m % 2) == 0;
+  const int t_begin = wbeg[wq], t_end = wbeg[wq + 1];
+  const int k_begin = (int)((int64_t)n * wq / WT), k_end = (int)((int64_t)n * (wq + 1) / WT);
+  const uint32_t team_bar = 1 + team, team_threads = 32u * WT;
+  auto team_sync = [&]() {
+    if (WT > 1) asm volatile("bar.sync %0, %1;" ::"r"(team_bar), "r"(team_threads) : "memory");
+    else __syncwarp();
+  };
+  ColPartial* my_parts = parts + (size_t)team * WT * 32;
+
+  int b = team % NB;
+  uint32_t phase = 0;
+  for (int64_t i = team; i < nloc; i += NT) {
+    T* phi_t = reinterpret_cast<T*>(in0 + (size_t)b * 2 * p.half_bytes) + lane;
+    T* th_t = reinterpret_cast<T*>(in0 + (size_t)b * 2 * p.half_bytes + p.half_bytes) + lane;
+    if (wq == 0 && lane == 0) bulk_wait_read0();
+    mbar_wait(full_u32 + 8u * b, phase);
+    b += NT;
+    if (b >= NB) {
+      b -= NB;
+      phase ^= 1u;
+    }
+    // ---- per-column facts about theta, the levels split between the warps of the team -----------------
+    {
+      if (logarithmic) {  // in place, once per tile: everything below reads log(theta)
+        for (int k = k_begin; k < k_end; ++k) th_t[k * TC] = xg_log<T>(th_t[k * TC]);
+        team_sync();
+      }
+      ColPartial cp;
+      cp.first_k = cp.last_k = -1;
+      cp.flags = 0;
+      cp.pad = 0;
+      T prev = T(0);
+      bool have_prev = false;
+      // the chunk plus the first level of the next one, so that every adjacent pair is looked at once
+      const int k_stop = (k_end < n) ? k_end + 1 : n;
+      for (int k = k_begin; k < k_stop; ++k) {
+        const T v = th_t[k * TC];
+        if (xg_isnan(v)) {
+          if (k < k_end) cp.flags |= 1;
+          have_prev = false;  // a NaN breaks the walk property anyway
+          continue;
+        }
+        if (k < k_end) {
+          if (cp.first_k < 0) cp.first_k = k;
+          cp.last_k = k;
+        }
+        if (have_prev) {
+          if (v > prev) cp.flags |= 2;
+          if (v < prev) cp.flags |= 4;
+        }
+        prev = v;
+        have_prev = true;
+      }
+      my_parts[wq * 32 + lane] = cp;
+    }
+    team_sync();  // partials + (log) transformed theta visible to the whole team
+    bool flip = false, walk = false;
+    T tmin = T(0), tmax = T(0);
+    {
+      int first_k = -1, last_k = -1, flags = 0;
+      for (int q = 0; q < WT; ++q) {
+        const ColPartial cp = my_parts[q * 32 + lane];
+        if (cp.first_k >= 0 && first_k < 0) first_k = cp.first_k;
+        if (cp.last_k >= 0) last_k = cp.last_k;
+        flags |= cp.flags;
+      }
+      const bool any = first_k >= 0;
+      if (!a.bypass_checks && any) flip = th_t[last_k * TC] < th_t[first_k * TC];  // transform.py:27-31
+      const bool nan = (flags & 1) != 0;
+      const bool sorted = flip ? (flags & 2) == 0 : (flags & 4) == 0;
+      walk = !nan && sorted && n > 1;
+      if (walk) {  // sorted: the extremes are the two ends
+        const T e0 = th_t[0], e1 = th_t[(n - 1) * TC];
+        tmin = e0 < e1 ? e0 : e1;
+        tmax = e0 < e1 ? e1 : e0;
+      } else if (a.mask_edges) {  // nanmin / nanmax (transform.py:36-37): rare columns, full scan
+        bool got = false;
+        for (int k = 0; k < n; ++k) {
+          const T v = th_t[k * TC];
+          if (xg_isnan(v)) continue;
+          if (!got) { tmin = tmax = v; got = true; }
+          else { tmin = v < tmin ? v : tmin; tmax = v > tmax ? v : tmax; }
+        }
+        if (!got) tmin = tmax = T(NAN);
+      }
+    }
+    const int rstep = flip ? -TC : TC, row0 = flip ? (n - 1) * TC : 0;
+    auto X = [&](int k) -> double { return (double)th_t[row0 + k * rstep]; };
+    auto Y = [&](int k) -> double { return (double)phi_t[row0 + k * rstep]; };
+    const double x_first = walk ? X(0) : 0.0, x_last = walk ? X(n - 1) : 0.0;
+
+    int guess = 0, cj = -2;
+    double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
+    if (!walk && n > 1) {  // literal replay: the guess after targets 0 .. t_begin-1
+      for (int t = 0; t < t_begin; ++t) {
+        const double x = xt[t];
+        if (x == x) guess = search_with_guess(x, X, n, guess);
+      }
+    }
+    auto one_target = [&](int t) -> T {
+      const double x = xt[t];
+      double res;
+      if (n == 1) {
+        res = Y(0);
+      } else if (x != x) {
+        res = x;
+      } else {
+        int j;
+        if (walk) {
+          if (x > x_last) j = n;
+          else if (x < x_first) j = -1;
+          else if (cj >= 0 && x >= xj) {
+            j = cj;
+            double xn = xj1;
+            while (j + 1 < n && xn <= x) {
+              ++j;
+              if (j + 1 < n) xn = X(j + 1);
+            }
+          } else {
+            int lo = 0, hi = n;
+            while (lo < hi) {
+              const int mid = lo + ((hi - lo) >> 1);
+              if (x >= X(mid)) lo = mid + 1;
+              else hi = mid;
+            }
+            j = lo - 1;
+          }
+        } else {
+          j = search_with_guess(x, X, n, guess);
+          guess = j;
+        }
+        if (j == -1) res = Y(0);
+        else if (j >= n - 1) res = Y(n - 1);
+        else {
+          if (j != cj) {
+            cj = j;
+            xj = X(j);
+            xj1 = X(j + 1);
+            yj = Y(j);
+            yj1 = Y(j + 1);
+            slope = (yj1 - yj) / (xj1 - xj);
+          }
+          res = (xj == x) ? yj : interp_value(x, xj, xj1, yj, yj1, slope);
+        }
+      }
+      if (a.mask_edges && (xv[t] < tmin || xv[t] > tmax)) res = NAN;  // transform.py:38-41
+      return (T)res;
+    };
+    if (pair_ok) {
+#pragma unroll 1
+      for (int t = t_begin; t < t_end; t += 2) {
+        const T v0 = one_target(t), v1 = one_target(t + 1);
+        T* o = out_tile + (size_t)lane * m + t;
+        if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
+        else *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
+      }
+    } else {
+#pragma unroll 1
+      for (int t = t_begin; t < t_end; ++t) out_tile[(size_t)lane * m + t] = one_target(t);
+    }
+    fence_async_smem();
+    team_sync();
+    if (wq == 0 && lane == 0) {
+      int64_t o, i0;
+      int ncol;
+      tile_geom(i, o, i0, ncol);
+      bulk_store(a.out + (o * a.inner + i0) * a.m, smem_u32(out_tile), (unsigned)ncol * (unsigned)m * sizeof(T));
+      bulk_commit();
+      if (i + NB < nloc) issue_load(i + NB);
+    }
+  }
+  if (wq == 0 && lane == 0) bulk_wait_read0();
+}
+
+template <typename T>
+int encode_field_map(EncodeTiledFn enc, CUtensorMap* map, const T* base, int64_t inner, int64_t n, int64_t outer,
+                     int box_cols, int box_rows) {
+  const cuuint64_t gdim[3] = {(cuuint64_t)inner, (cuuint64_t)n, (cuuint64_t)outer};
+  const cuuint64_t gstr[2] = {(cuuint64_t)inner * sizeof(T), (cuuint64_t)n * inner * sizeof(T)};
+  const cuuint32_t box[3] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return enc(map, sizeof(T) == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3,
+             const_cast<T*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+             CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS
+             ? 0
+             : 1;
+}
+
+}  // namespace
+
+template <typename T>
+int vinterp_columns_tma(const InterpArgs<T>& a, cudaStream_t st) {
+  if (env_int("XG_VINTERP_TMA", 1) == 0) return 0;
+  const int n = (int)a.n, m = (int)a.m;
+  if (n < 1 || n >= (1 << 23) || m < 1) return 0;
+  if ((a.inner * sizeof(T)) % 16 != 0) return 0;
+  const T* theta = reinterpret_cast<const T*>(a.theta.ptr);
+  if ((reinterpret_cast<uintptr_t>(a.phi) | reinterpret_cast<uintptr_t>(theta) | reinterpret_cast<uintptr_t>(a.out)) & 15)
+    return 0;
+  if (a.inner < 32 || a.inner >= (1ll << 31) || a.outer >= (1ll << 31)) return 0;
+  int dev = 0, sms = 148, smem_max = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  constexpr int TC = 32;
+  ColArgs<T> p;
+  p.a = a;
+  p.tiles_per_o = xg_ceil_div(a.inner, TC);
+  p.ntiles = a.outer * p.tiles_per_o;
+  p.small = p.ntiles < (1ll << 31);
+  p.nbox = (int)xg_ceil_div(n, 256);
+  p.box_rows = (int)xg_ceil_div(n, p.nbox);
+  auto up128 = [](size_t v) { return (unsigned)((v + 127) / 128 * 128); };
+  p.half_bytes = up128((size_t)p.nbox * p.box_rows * TC * sizeof(T));
+  p.out_bytes = up128((size_t)TC * m * sizeof(T));
+  const int want_nt = env_int("XG_VINTERP_W", 0), want_extra = env_int("XG_VINTERP_EXTRA", 2);
+  int nt = 0, nb = 0;
+  unsigned plan_b = 0;
+  for (int NT = 15; NT >= 1 && !nt; --NT) {
+    if (want_nt && NT != want_nt) continue;
+    for (int extra = want_extra; extra >= 0; --extra) {
+      const int NB = NT + extra;
+      // the partials array is sized for the largest team this NT allows
+      const int wt_max = 32 / NT > 0 ? 32 / NT : 1;
+      const size_t plan = ((size_t)m * (8 + sizeof(T)) + 7) / 8 * 8 + (size_t)NB * 8 + 36 * sizeof(int) +
+                          (size_t)NT * wt_max * 32 * sizeof(ColPartial);
+      const unsigned pb = up128(plan);
+      const size_t total = pb + (size_t)NB * 2 * p.half_bytes + (size_t)NT * p.out_bytes;
+      if (total + 64 <= (size_t)smem_max) {
+        nt = NT;
+        nb = NB;
+        plan_b = pb;
+        break;
+      }
+    }
+  }
+  if (!nt) return 0;
+  int wt = env_int("XG_VINTERP_WT", 0);
+  if (wt <= 0) {
+    wt = 32 / nt;
+    while (wt > 1 && (m / 2) / wt < 2) --wt;
+  }
+  if (wt < 1) wt = 1;
+  while (wt > 1 && nt * wt > 32) --wt;
+  p.wt = wt;
+  p.nb = nb;
+  p.plan_bytes = plan_b;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return 0;
+  CUtensorMap map_phi, map_theta;
+  if (encode_field_map<T>(enc, &map_phi, a.phi, a.inner, a.n, a.outer, TC, p.box_rows)) return 0;
+  if (encode_field_map<T>(enc, &map_theta, theta, a.inner, a.n, a.outer, TC, p.box_rows)) return 0;
+  const size_t smem = plan_b + (size_t)nb * 2 * p.half_bytes + (size_t)nt * p.out_bytes;
+  cudaError_t e = cudaFuncSetAttribute(k_vinterp_columns_tma<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return xg_fail(XG_ECUDA, std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e));
+  int64_t blocks = xg_ceil_div(p.ntiles, nt);
+  if (blocks > sms) blocks = sms;
+  k_vinterp_columns_tma<T><<<(unsigned)blocks, nt * wt * 32, smem, st>>>(map_phi, map_theta, p);
+  const int rc = xg_check_launch("xg_vinterp_linear(columns, tma)");
+  return rc ? rc : 1;
 }
 
 template int vinterp_shared_tma<float>(const InterpArgs<float>&, cudaStream_t);
