@@ -700,14 +700,15 @@ __global__ void __launch_bounds__(1024, 1)
     xv[t] = v;
     xt[t] = (double)v;
   }
+  __syncthreads();
   if (tid == 0) {
-    const int unit = (m % 2 == 0) ? 2 : 1, units = m / unit;
-    for (int q = 0; q <= WT; ++q) wbeg[q] = (int)((int64_t)units * q / WT) * unit;
-    wbeg[WT] = m;
+    int sorted_t = 1;  // non-decreasing and NaN-free target levels: the level-major fast path applies
+    for (int t = 0; t < m; ++t)
+      if (xt[t] != xt[t] || (t > 0 && xt[t] < xt[t - 1])) sorted_t = 0;
+    wbeg[0] = sorted_t;
   }
   __syncthreads();
-  const bool pair_ok = (m % 2) == 0;
-  const int t_begin = wbeg[wq], t_end = wbeg[wq + 1];
+  const bool tsorted = wbeg[0] != 0;
   const int k_begin = (int)((int64_t)n * wq / WT), k_end = (int)((int64_t)n * (wq + 1) / WT);
   const uint32_t team_bar = 1 + team, team_threads = 32u * WT;
   auto team_sync = [&]() {
@@ -796,76 +797,85 @@ __global__ void __launch_bounds__(1024, 1)
     const int rstep = flip ? -TC : TC, row0 = flip ? (n - 1) * TC : 0;
     auto X = [&](int k) -> double { return (double)th_t[row0 + k * rstep]; };
     auto Y = [&](int k) -> double { return (double)phi_t[row0 + k * rstep]; };
-    const double x_first = walk ? X(0) : 0.0, x_last = walk ? X(n - 1) : 0.0;
-
-    int guess = 0, cj = -2;
-    double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
-    if (!walk && n > 1) {  // literal replay: the guess after targets 0 .. t_begin-1
-      for (int t = 0; t < t_begin; ++t) {
+    T* orow = out_tile + (size_t)lane * m;
+    const bool fast = walk && tsorted;
+    if (fast) {
+      // ---- level-major: this warp owns the intervals [k_begin, k_end) of every column; a column's targets
+      // that fall into them are found by position (targets are sorted), so each interval's slope is formed
+      // once, uniformly across the lanes, and every target is written by exactly one warp of the team.
+      // np.interp on sorted NaN-free theta: j = the largest index with X[j] <= x.
+      int t = 0;
+      {  // first target at or right of X[k_begin] (lower bound over the sorted levels)
+        const double xb = X(k_begin);
+        int lo_t = 0, hi_t = m;
+        while (lo_t < hi_t) {
+          const int mid = lo_t + ((hi_t - lo_t) >> 1);
+          if (xt[mid] < xb) lo_t = mid + 1;
+          else hi_t = mid;
+        }
+        t = lo_t;
+      }
+      if (wq == 0) {  // targets left of the first node: np.interp gives Y(0), the edge mask NaN
+        const T y0 = a.mask_edges ? T(NAN) : phi_t[row0];
+        for (int tt = 0; tt < t; ++tt) orow[tt] = y0;
+      }
+      const T* pth = th_t + row0 + k_begin * rstep;
+      const T* pph = phi_t + row0 + k_begin * rstep;
+      double xk = (double)pth[0], yk = (double)pph[0];
+      const int k_last = (k_end < n - 1) ? k_end : n - 1;  // intervals k_begin .. k_last - 1
+#pragma unroll 1
+      for (int k = k_begin; k < k_last; ++k) {
+        pth += rstep;
+        pph += rstep;
+        const double xk1 = (double)pth[0], yk1 = (double)pph[0];
+        const double slope = (yk1 - yk) / (xk1 - xk);
+        while (t < m) {
+          const double x = xt[t];
+          if (!(x < xk1)) break;
+          const double res = (xk == x) ? yk : interp_value(x, xk, xk1, yk, yk1, slope);
+          orow[t] = (T)res;  // inside [X(0), X(n-1)): never masked
+          ++t;
+        }
+        xk = xk1;
+        yk = yk1;
+      }
+      if (wq == WT - 1) {  // at or right of the last node: Y(n-1); strictly right of it the edge mask applies
+        const double xl = (double)th_t[row0 + (n - 1) * rstep];
+        const T yl = phi_t[row0 + (n - 1) * rstep];
+        for (; t < m; ++t) orow[t] = (a.mask_edges && xt[t] > xl) ? T(NAN) : yl;
+      }
+    } else if (lane % WT == wq) {
+      // ---- everything else (theta with NaNs or out of order, unsorted / NaN targets, a single level): the
+      // literal replay of np.interp for the whole column, such columns dealt round-robin to the team's warps
+      int guess = 0, cj = -2;
+      double yj = 0.0, yj1 = 0.0, slope = 0.0, xj = 0.0, xj1 = 0.0;
+      for (int t = 0; t < m; ++t) {
         const double x = xt[t];
-        if (x == x) guess = search_with_guess(x, X, n, guess);
-      }
-    }
-    auto one_target = [&](int t) -> T {
-      const double x = xt[t];
-      double res;
-      if (n == 1) {
-        res = Y(0);
-      } else if (x != x) {
-        res = x;
-      } else {
-        int j;
-        if (walk) {
-          if (x > x_last) j = n;
-          else if (x < x_first) j = -1;
-          else if (cj >= 0 && x >= xj) {
-            j = cj;
-            double xn = xj1;
-            while (j + 1 < n && xn <= x) {
-              ++j;
-              if (j + 1 < n) xn = X(j + 1);
-            }
-          } else {
-            int lo = 0, hi = n;
-            while (lo < hi) {
-              const int mid = lo + ((hi - lo) >> 1);
-              if (x >= X(mid)) lo = mid + 1;
-              else hi = mid;
-            }
-            j = lo - 1;
-          }
+        double res;
+        if (n == 1) {
+          res = Y(0);
+        } else if (x != x) {
+          res = x;
         } else {
-          j = search_with_guess(x, X, n, guess);
+          const int j = search_with_guess(x, X, n, guess);
           guess = j;
-        }
-        if (j == -1) res = Y(0);
-        else if (j >= n - 1) res = Y(n - 1);
-        else {
-          if (j != cj) {
-            cj = j;
-            xj = X(j);
-            xj1 = X(j + 1);
-            yj = Y(j);
-            yj1 = Y(j + 1);
-            slope = (yj1 - yj) / (xj1 - xj);
+          if (j == -1) res = Y(0);
+          else if (j >= n - 1) res = Y(n - 1);
+          else {
+            if (j != cj) {
+              cj = j;
+              xj = X(j);
+              xj1 = X(j + 1);
+              yj = Y(j);
+              yj1 = Y(j + 1);
+              slope = (yj1 - yj) / (xj1 - xj);
+            }
+            res = (xj == x) ? yj : interp_value(x, xj, xj1, yj, yj1, slope);
           }
-          res = (xj == x) ? yj : interp_value(x, xj, xj1, yj, yj1, slope);
         }
+        if (a.mask_edges && (xv[t] < tmin || xv[t] > tmax)) res = NAN;  // transform.py:38-41
+        orow[t] = (T)res;
       }
-      if (a.mask_edges && (xv[t] < tmin || xv[t] > tmax)) res = NAN;  // transform.py:38-41
-      return (T)res;
-    };
-    if (pair_ok) {
-#pragma unroll 1
-      for (int t = t_begin; t < t_end; t += 2) {
-        const T v0 = one_target(t), v1 = one_target(t + 1);
-        T* o = out_tile + (size_t)lane * m + t;
-        if constexpr (sizeof(T) == 4) *reinterpret_cast<float2*>(o) = make_float2(v0, v1);
-        else *reinterpret_cast<double2*>(o) = make_double2(v0, v1);
-      }
-    } else {
-#pragma unroll 1
-      for (int t = t_begin; t < t_end; ++t) out_tile[(size_t)lane * m + t] = one_target(t);
     }
     fence_async_smem();
     team_sync();
