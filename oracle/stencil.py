@@ -312,3 +312,39 @@ def stencil_pair(op_a, a, axis_a, lo_a, hi_a, bc_a, fill_a, pre_a, op_b, b, axis
         with np.errstate(invalid="ignore", divide="ignore"):
             r = r / post
     return r.astype(np.asarray(a).dtype)
+
+
+def log32_port(x):
+    """numpy restatement of the float32 log the device evaluates for `method="log"` (csrc/xg_vinterp.cuh
+    xg_log<float>): numpy's own AVX2 / AVX512F algorithm (a rational minimax approximation after range reduction to
+    (1/sqrt2, sqrt2]), FMAs emulated through float64.  Test infrastructure: pins the port against np.log."""
+    x = np.asarray(x, dtype=np.float32)
+    P = [np.float32(v) for v in (0.0, 9.999999999999998702752e-01, 2.112677543073053063722e+00,
+                                 1.480000633576506585156e+00, 3.808837741388407920751e-01, 2.589979117907922693523e-02)]
+    Q = [np.float32(v) for v in (1.0, 2.612677543073109236779e+00, 2.453006071784736363091e+00,
+                                 9.864942958519418960339e-01, 1.546476374983906719538e-01, 5.875095403124574342950e-03)]
+
+    def fma(a, b, c):
+        return (a.astype(np.float64) * np.float64(b) + np.float64(c)).astype(np.float32) if np.isscalar(b) or b.ndim == 0 \
+            else (a.astype(np.float64) * b.astype(np.float64) + np.asarray(c, np.float64)).astype(np.float32)
+
+    with np.errstate(all="ignore"):
+        m, e = np.frexp(x)
+        m = m.astype(np.float32)
+        e = e.astype(np.float32)
+        low = m <= np.float32(0.70710678118654752440)
+        m = np.where(low, m * np.float32(2), m)
+        e = np.where(low, e - 1, e)
+        t = m - np.float32(1)
+        num = np.full_like(t, P[5])
+        for c in (P[4], P[3], P[2], P[1], P[0]):
+            num = fma(num, t, np.full_like(t, c))
+        den = np.full_like(t, Q[5])
+        for c in (Q[4], Q[3], Q[2], Q[1], Q[0]):
+            den = fma(den, t, np.full_like(t, c))
+        out = fma(e, np.full_like(t, np.float32(0.693147180559945309417232121458176568)), (num / den).astype(np.float32))
+        out = np.where(x == 0, np.float32(-np.inf), out)
+        out = np.where(x < 0, np.float32(np.nan), out)
+        out = np.where(np.isinf(x) & (x > 0), np.float32(np.inf), out)
+        out = np.where(np.isnan(x), np.float32(np.nan), out)
+    return out.astype(np.float32)

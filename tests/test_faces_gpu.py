@@ -192,6 +192,20 @@ def test_diff_interp_connected_grid_x_to_x():
     np.testing.assert_array_equal(diff_x.coords["xl"].values, ds["xl"].values)
 
 
+def test_connected_grid_rejects_unknown_padding_modes():
+    """A typo / unsupported mode must raise on a connected grid exactly as on a simple one, not turn into a
+    periodic halo on the unconnected edges."""
+    ds = _ds()
+    grid = xg.Grid(ds, coords=COORDS, face_connections=X_TO_X, padding="fill")
+    with pytest.raises(ValueError, match="padding must be one of"):
+        grid.diff(ds["data_c"], "X", padding="bogus")
+    with pytest.raises(NotImplementedError, match="extrapolate"):
+        grid.interp(ds["data_c"], "X", padding="extrapolate")
+    # the three supported modes still differ from each other on the unconnected edge (face 0, left)
+    outs = [grid.diff(ds["data_c"], "X", padding=p).values[0, :, 0] for p in ("fill", "extend", "periodic")]
+    assert not np.array_equal(outs[0], outs[1]) and not np.array_equal(outs[1], outs[2])
+
+
 def test_diff_interp_connected_grid_x_to_y():
     """test_faceconnections.py:183-202: a rotated seam."""
     ds = _ds()

@@ -84,3 +84,23 @@ def test_grid_accepts_and_returns_xarray_like_objects(fake_xarray):
     assert isinstance(native, xg.DataArray)
     out = grid.cumsum(da, "X", to="left")
     assert isinstance(out, FakeDataArray) and out.dims == ("y", "xg")
+
+
+def test_vector_dict_and_other_component_convert_xarray_values(fake_xarray):
+    """`{axis: xr.DataArray}` vector inputs and `other_component` dicts holding xarray objects are
+    converted like a bare DataArray (they used to fail the input type check)."""
+    xr = fake_xarray
+    n = 8
+    rng = np.random.default_rng(1)
+    u, v = rng.random((n, n)), rng.random((n, n))
+    ds = xr.Dataset({}, {"xc": np.arange(n) + 0.5, "xg": np.arange(n) + 0.0, "yc": np.arange(n) + 0.5, "yg": np.arange(n) + 0.0})
+    grid = xg.Grid(ds, coords={"X": {"center": "xc", "left": "xg"}, "Y": {"center": "yc", "left": "yg"}}, padding="periodic")
+    ux = xr.DataArray(u, dims=("yc", "xg"), name="u")
+    vx = xr.DataArray(v, dims=("yg", "xc"), name="v")
+    out = grid.interp({"X": ux}, "X", other_component={"Y": vx})
+    assert isinstance(out, FakeDataArray) and out.dims == ("yc", "xc")
+    np.testing.assert_array_equal(out.data, 0.5 * (u + np.roll(u, -1, axis=1)))
+    # extension methods accept xarray objects too
+    div = grid.pair("diff", ux, "X", "diff", vx, "Y")
+    assert isinstance(div, FakeDataArray) and div.dims == ("yc", "xc")
+    np.testing.assert_array_equal(div.data, (np.roll(u, -1, axis=1) - u) + (np.roll(v, -1, axis=0) - v))

@@ -165,3 +165,33 @@ def test_transform_cases_golden():
         np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6, equal_nan=True, err_msg=name)
         checked += 1
     assert checked >= 10
+
+
+def _numpy_simd_log():
+    """np.log(float32) runs numpy's SIMD algorithm only on x86 with AVX2+FMA3 / AVX512F (elsewhere: libm)."""
+    try:
+        from numpy._core._multiarray_umath import __cpu_features__ as f
+    except Exception:
+        return False
+    return bool(f.get("AVX512F") or (f.get("AVX2") and f.get("FMA3")))
+
+
+def test_log32_port_is_numpys():
+    """The float32 log the device uses for method="log" (oracle.log32_port restates it in numpy) is numpy's own:
+    bit-identical on every exponent, denormals, the reduction threshold and the neighbourhood of 1."""
+    if not _numpy_simd_log():
+        pytest.skip("np.log(float32) does not take numpy's SIMD path on this CPU")
+    rng = np.random.default_rng(3)
+    man = np.concatenate([np.arange(0x3504F3 - 64, 0x3504F3 + 64), np.arange(0, 64),
+                          np.arange(0x7FFFFF - 64, 0x7FFFFF + 1)]).astype(np.uint32)
+    exp = np.arange(0, 255, dtype=np.uint32)
+    bits = ((exp[:, None] << 23) | man[None, :]).reshape(-1)
+    bits = np.concatenate([bits[bits != 0], rng.integers(1, 0x7F800000, size=3_000_000, dtype=np.int64).astype(np.uint32)])
+    x = bits.view(np.float32)
+    with np.errstate(all="ignore"):
+        want = np.log(x)
+    got = oracle.log32_port(x)
+    assert np.array_equal(got.view(np.int32), want.view(np.int32))
+    special = np.array([0.0, -0.0, -1.0, np.inf, np.nan], np.float32)
+    with np.errstate(all="ignore"):
+        np.testing.assert_array_equal(oracle.log32_port(special), np.log(special))

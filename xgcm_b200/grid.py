@@ -278,8 +278,14 @@ class Grid:
 
     def _wrap_in(self, obj):
         """Accept real xarray objects when xarray is installed."""
-        if isinstance(obj, (DataArray, dict)) or obj is None:
+        if isinstance(obj, DataArray) or obj is None:
             return obj, False
+        if isinstance(obj, dict):  # vector input {axis: DataArray} / other_component: convert the values
+            out, any_x = {}, False
+            for k, v in obj.items():
+                out[k], was = self._wrap_in(v)
+                any_x = any_x or was
+            return out, any_x
         if type(obj).__name__ == "DataArray" and hasattr(obj, "dims"):
             from . import interop
 
@@ -462,6 +468,8 @@ class Grid:
         if isinstance(axis, str):
             axis = [axis]
         data, as_xarray = self._wrap_in(data)
+        if other_component is not None:
+            other_component, _ = self._wrap_in(other_component)
         data = _check_data_input(data, self)
         unpacked = _maybe_unpack_vector_component(data)
         for ax_name in axis:

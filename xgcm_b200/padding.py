@@ -293,6 +293,21 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
     paddings = grid._complete_user_kwargs_using_axis_defaults(padding, "padding")
     fills = grid._complete_user_kwargs_using_axis_defaults(fill_value, "fill_value")
     ax_padding = paddings[ax_name]
+    # the same validation the simply connected path performs in ops.stencil2 / _apply_fused_stencil: an
+    # unknown string must not silently become a periodic halo on the unconnected edges
+    if isinstance(ax_padding, Mapping):
+        raise NotImplementedError(
+            "fold / per-side padding mappings are not supported on grids with face connections"
+        )
+    if ax_padding not in (None, "periodic", "fill", "extend"):
+        if ax_padding == "extrapolate":
+            raise NotImplementedError(
+                "padding='extrapolate' (an opt-in extension without a reference counterpart) is not available "
+                "for operators on grids with face connections; use fill / extend / periodic"
+            )
+        raise ValueError(
+            f"padding must be one of ['periodic', 'fill', 'extend'] or None, but got {ax_padding!r}"
+        )
     planes, batch = [], []
     for side, w in ((0, lo), (1, hi)):
         if not w:
@@ -321,6 +336,7 @@ def connected_halo_planes(da, grid, ax_name, lo, hi, padding, fill_value, other_
             if mode == "extend":
                 row = (n - 1) if side else 0
             else:
+                assert mode == "periodic"
                 row = 0 if side else (n - 1)
             ops.strided_copy(plane, 0, _contiguous_strides(p_shape), x, row * strides[t], strides, p_shape)
         planes.append(plane)
