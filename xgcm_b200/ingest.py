@@ -1,0 +1,169 @@
+"""Chunked ingest: time chunks on disk -> page-locked ring -> device, overlapped with the kernels.
+
+The reference leaves out-of-core data to xarray + dask (README.rst:28-33: "datasets that don't fit in memory",
+docs/grid_ufuncs.md:341-376: one task per ``time`` chunk).  With the kernels at HBM speed a 946 GB series (C4) is bound
+by storage and PCIe, so the loader's job is to keep three things busy at once:
+
+    reader thread :  file k+2  --readinto-->  pinned slot      (no intermediate copy, the GIL is released in read)
+    copy stream   :  pinned slot k+1  --cudaMemcpyAsync-->  device slot
+    compute stream:  kernels on device slot k
+
+``ChunkStream`` yields device tensors in file order; a chunk stays valid until the iterator is advanced ``depth - 1``
+more times.  Files are NumPy ``.npy`` (C-order, float32 / float64) or raw binary with an explicit shape / dtype.
+"""
+
+from __future__ import annotations
+
+import os
+import queue
+import threading
+from typing import Iterable, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+
+def _npy_payload(path: str):
+    """(offset, shape, dtype) of a C-ordered .npy file."""
+    with open(path, "rb") as f:
+        version = np.lib.format.read_magic(f)
+        if version == (1, 0):
+            shape, fortran, dtype = np.lib.format.read_array_header_1_0(f)
+        else:
+            shape, fortran, dtype = np.lib.format.read_array_header_2_0(f)
+        if fortran:
+            raise ValueError(f"{path}: Fortran-ordered arrays are not supported")
+        return f.tell(), tuple(shape), np.dtype(dtype)
+
+
+class ChunkStream:
+    """Iterate over equally shaped array chunks stored one per file, delivered as device tensors.
+
+    files   : paths in delivery order (``.npy``, or raw binary when ``shape`` and ``dtype`` are given)
+    device  : CUDA device (default: current); ``"cpu"`` keeps everything on the host (logic tests)
+    depth   : ring depth (>= 2): chunks in flight between the reader, the copy stream and the consumer
+    """
+
+    def __init__(self, files: Sequence[str], shape: Optional[Tuple[int, ...]] = None, dtype=None, device=None,
+                 depth: int = 3):
+        self.files = [os.fspath(f) for f in files]
+        if not self.files:
+            raise ValueError("ChunkStream needs at least one file")
+        if depth < 2:
+            raise ValueError("depth must be >= 2 (reader and consumer need a slot each)")
+        self.depth = depth
+        first = self.files[0]
+        if shape is None or dtype is None:
+            if not first.endswith(".npy"):
+                raise ValueError("raw binary chunks need an explicit shape and dtype")
+            _, shape, dtype = _npy_payload(first)
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        if self.dtype not in (np.dtype("float32"), np.dtype("float64")):
+            raise TypeError("chunks must be float32 or float64")
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        self.on_gpu = not (isinstance(device, str) and device == "cpu")
+        if self.on_gpu:
+            if not torch.cuda.is_available():
+                raise RuntimeError("xgcm_b200 needs a CUDA device: the stencil engine has no CPU fallback")
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        else:
+            self.device = torch.device("cpu")
+        tdt = torch.float32 if self.dtype == np.float32 else torch.float64
+        # page-locked staging ring + device ring (plain tensors on the host-only path)
+        self._host = [torch.empty(self.shape, dtype=tdt, pin_memory=self.on_gpu) for _ in range(depth)]
+        self._dev = [torch.empty(self.shape, dtype=tdt, device=self.device) for _ in range(depth)] if self.on_gpu else self._host
+        self._copy_stream = torch.cuda.Stream(self.device) if self.on_gpu else None
+        self.bytes_read = 0
+
+    # ------------------------------------------------------------------ reader thread
+    def _read_into(self, path: str, slot: int):
+        buf = memoryview(self._host[slot].numpy()).cast("B")
+        if path.endswith(".npy"):
+            off, shape, dtype = _npy_payload(path)
+            if tuple(shape) != self.shape or np.dtype(dtype) != self.dtype:
+                raise ValueError(f"{path}: chunk of shape {shape} / {dtype}, expected {self.shape} / {self.dtype}")
+        else:
+            off = 0
+            if os.path.getsize(path) != self.nbytes:
+                raise ValueError(f"{path}: {os.path.getsize(path)} bytes, expected {self.nbytes}")
+        with open(path, "rb", buffering=0) as f:
+            f.seek(off)
+            got = 0
+            while got < self.nbytes:  # readinto may return short counts on some filesystems
+                n = f.readinto(buf[got:])
+                if not n:
+                    raise IOError(f"{path}: unexpected end of file after {got} of {self.nbytes} bytes")
+                got += n
+        self.bytes_read += self.nbytes
+
+    def _reader(self, free: "queue.Queue[int]", filled: "queue.Queue"):
+        try:
+            for k, path in enumerate(self.files):
+                slot = free.get()
+                if slot is None:
+                    return
+                self._read_into(path, slot)
+                filled.put((k, slot, None))
+        except BaseException as exc:  # delivered to the consumer
+            filled.put((-1, -1, exc))
+            return
+        filled.put((len(self.files), -1, None))
+
+    # ------------------------------------------------------------------ consumer
+    def __iter__(self):
+        free: "queue.Queue" = queue.Queue()
+        filled: "queue.Queue" = queue.Queue()
+        for s in range(self.depth):
+            free.put(s)
+        t = threading.Thread(target=self._reader, args=(free, filled), daemon=True)
+        t.start()
+        in_use = []  # (slot, ready event) handed out, oldest first
+        try:
+            while True:
+                k, slot, exc = filled.get()
+                if exc is not None:
+                    raise exc
+                if slot < 0:
+                    break
+                if self.on_gpu:
+                    cur = torch.cuda.current_stream(self.device)
+                    with torch.cuda.stream(self._copy_stream):
+                        # the consumer's kernels on this device slot (depth iterations ago) must be done
+                        self._copy_stream.wait_stream(cur)
+                        self._dev[slot].copy_(self._host[slot], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record(self._copy_stream)
+                    cur.wait_event(ev)
+                    in_use.append((slot, ev))
+                    # the pinned slot may be refilled once its upload has finished; hand back the OLDEST slot whose
+                    # device copy the consumer no longer needs (valid for depth - 1 further iterations)
+                    if len(in_use) >= self.depth - 0:
+                        old_slot, old_ev = in_use.pop(0)
+                        old_ev.synchronize()
+                        free.put(old_slot)
+                else:
+                    in_use.append((slot, None))
+                    if len(in_use) >= self.depth:
+                        free.put(in_use.pop(0)[0])
+                yield k, self._dev[slot]
+        finally:
+            free.put(None)  # unblock the reader if the consumer stopped early
+
+    def __len__(self):
+        return len(self.files)
+
+
+def write_chunks(directory: str, arrays: Iterable[np.ndarray], prefix: str = "chunk", raw: bool = False):
+    """Write arrays as ``<prefix>_%05d.npy`` (or ``.bin``) files; returns the paths (helper for tests / benches)."""
+    os.makedirs(directory, exist_ok=True)
+    paths = []
+    for k, a in enumerate(arrays):
+        a = np.ascontiguousarray(a)
+        path = os.path.join(directory, f"{prefix}_{k:05d}.{'bin' if raw else 'npy'}")
+        if raw:
+            a.tofile(path)
+        else:
+            np.save(path, a)
+        paths.append(path)
+    return paths
