@@ -43,6 +43,24 @@ def test_pad_matches_np_pad(dtype, shape):
             np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+def test_pad_innermost_flat_stream_kernel(dtype):
+    """xg_pad(rows): the output of an innermost-dim pad is written as one flat stream of aligned vectors that may
+    straddle rows — every width / boundary / row length combination against np.pad."""
+    from xgcm_b200 import _capi, ops
+
+    for shape in [(7, 1027), (3, 5, 130), (1, 9), (2, 3, 4, 33), (4099,)]:
+        a = _field(shape, dtype, seed=13)
+        for (lo, hi), (bc, fill) in itertools.product([(1, 0), (0, 1), (1, 1), (3, 2), (0, 0), (5, 7)], BCS):
+            if bc == "periodic" and max(lo, hi) > shape[-1]:
+                continue
+            want = oracle.pad_axis(a, len(shape) - 1, lo, hi, bc, fill)
+            got = ops.pad(_t(a), len(shape) - 1, lo, hi, bc, fill).cpu().numpy()
+            if shape[-1] + lo + hi >= 8:
+                assert _capi.last_launch() == "xg_pad(rows)"
+            np.testing.assert_array_equal(got, want)
+
+
 # ----------------------------------------------------------------------------- binary
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
 def test_binary_broadcast(dtype):

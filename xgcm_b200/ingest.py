@@ -42,10 +42,11 @@ class ChunkStream:
     files   : paths in delivery order (``.npy``, or raw binary when ``shape`` and ``dtype`` are given)
     device  : CUDA device (default: current); ``"cpu"`` keeps everything on the host (logic tests)
     depth   : ring depth (>= 2): chunks in flight between the reader, the copy stream and the consumer
+    readers : threads reading segments of one file concurrently (a single read() stream tops out near 7 GB/s)
     """
 
     def __init__(self, files: Sequence[str], shape: Optional[Tuple[int, ...]] = None, dtype=None, device=None,
-                 depth: int = 3):
+                 depth: int = 3, readers: int = 8):
         self.files = [os.fspath(f) for f in files]
         if not self.files:
             raise ValueError("ChunkStream needs at least one file")
@@ -75,6 +76,10 @@ class ChunkStream:
         self._dev = [torch.empty(self.shape, dtype=tdt, device=self.device) for _ in range(depth)] if self.on_gpu else self._host
         self._copy_stream = torch.cuda.Stream(self.device) if self.on_gpu else None
         self.bytes_read = 0
+        self.readers = max(1, int(readers))
+        from concurrent.futures import ThreadPoolExecutor
+
+        self._pool = ThreadPoolExecutor(max_workers=self.readers) if self.readers > 1 else None
 
     # ------------------------------------------------------------------ reader thread
     def _read_into(self, path: str, slot: int):
@@ -87,14 +92,26 @@ class ChunkStream:
             off = 0
             if os.path.getsize(path) != self.nbytes:
                 raise ValueError(f"{path}: {os.path.getsize(path)} bytes, expected {self.nbytes}")
-        with open(path, "rb", buffering=0) as f:
-            f.seek(off)
-            got = 0
-            while got < self.nbytes:  # readinto may return short counts on some filesystems
-                n = f.readinto(buf[got:])
-                if not n:
-                    raise IOError(f"{path}: unexpected end of file after {got} of {self.nbytes} bytes")
-                got += n
+        fd = os.open(path, os.O_RDONLY)
+        try:
+            def segment(lo, hi):  # preadv releases the GIL: segments of one file are read concurrently
+                pos = lo
+                while pos < hi:  # short counts happen on some filesystems
+                    n = os.preadv(fd, [buf[pos:hi]], off + pos)
+                    if not n:
+                        raise IOError(f"{path}: unexpected end of file after {pos} of {self.nbytes} bytes")
+                    pos += n
+
+            seg = max(32 << 20, -(-self.nbytes // self.readers))
+            bounds = [(lo, min(self.nbytes, lo + seg)) for lo in range(0, self.nbytes, seg)]
+            if len(bounds) == 1 or self._pool is None:
+                for lo, hi in bounds:
+                    segment(lo, hi)
+            else:
+                for fut in [self._pool.submit(segment, lo, hi) for lo, hi in bounds]:
+                    fut.result()
+        finally:
+            os.close(fd)
         self.bytes_read += self.nbytes
 
     def _reader(self, free: "queue.Queue[int]", filled: "queue.Queue"):
