@@ -336,7 +336,7 @@ int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
   // short enough that there are plenty of warps for 148 SMs.
   static const int tune_j = env_int("XG_STRIDED_J", 0);  // tuning knobs (benchmarks only)
   static const int tune_u = env_int("XG_STRIDED_U", 0);
-  // Tuning notes (profiles/r02_tune_strided.txt): in a loop of identical launches short marches
+  // Tuning notes (profiles/r1b_tune_strided.txt): in a loop of identical launches short marches
   // (J = 4) look 8 % faster for Y, but per-launch ncu timings and the mixed sequence of bench.py
   // show no gain, and the fused-metric variants lose 20 % (per-segment operand setup is amortised
   // over fewer rows) — so 32 stays; a plane-strided axis marches as far as possible.

@@ -364,7 +364,7 @@ int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int n
   const int march_dim = axes[march];
   a.march_n_out = out_shape[march_dim];
   a.march_out_stride = out_stride[march_dim];
-  a.J = a.march_n_out <= 16 ? (int)a.march_n_out : 16;  // measured flat optimum (profiles/r02_tune_multi.txt)
+  a.J = a.march_n_out <= 16 ? (int)a.march_n_out : 16;  // measured flat optimum (profiles/r1b_tune_multi.txt)
   if (const char* e = getenv("XG_MULTI_J")) {  // tuning knob (benchmarks only)
     const int tj = atoi(e);
     if (tj > 0) a.J = tj < a.march_n_out ? tj : (int)a.march_n_out;

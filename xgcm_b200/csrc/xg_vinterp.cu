@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(kWarps * 32) k_vinterp_shared(const InterpArgs
               yj1[c] = (double)raw_b[c];
               // The plan knows which interval is entered next: request its nodes now, a whole
               // interval of work before they are converted above (the per-interval wait on this
-              // load was 37 % of all stall samples, profiles/r02_vinterp_stalls.txt).
+              // load was 37 % of all stall samples, profiles/r1b_vinterp_stalls.txt).
               if (nj >= 0) {
                 const T* pn = phi0[c] + (int64_t)nj * step;
                 raw_b[c] = __ldg(pn + step);

@@ -13,6 +13,8 @@ import numpy as np
 import torch
 
 _FLOAT = (np.dtype("float32"), np.dtype("float64"))
+_SMALL_BYTES = 64 * 1024
+_small_cache: dict = {}
 
 
 def default_device() -> torch.device:
@@ -43,6 +45,18 @@ def as_device_tensor(data, device=None) -> Tuple[torch.Tensor, bool]:
     if not arr.flags.writeable:
         arr = arr.copy()
     dev = device if device is not None else default_device()
+    if arr.nbytes <= _SMALL_BYTES:
+        # coordinate vectors, target levels, 1-D metrics: a pageable upload blocks the host until the copy has
+        # drained behind whatever kernel is running — for a 1 ms kernel that serialises consecutive calls.
+        # Identical small operands (by content) are uploaded once and re-used (never written to by the library).
+        key = (arr.dtype.str, arr.shape, str(dev), hash(arr.tobytes()))
+        hit = _small_cache.get(key)
+        if hit is None:
+            if len(_small_cache) >= 256:
+                _small_cache.clear()
+            hit = torch.from_numpy(arr.copy()).to(dev)
+            _small_cache[key] = hit
+        return hit, True
     return torch.from_numpy(arr).to(dev, non_blocking=True), True
 
 
