@@ -330,7 +330,11 @@ extern "C" int xg_comm_init(const void* id128, int nranks, int rank, void** comm
     delete c;
     return nccl_fail("ncclCommInitRank", r);
   }
-  if (cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) != cudaSuccess ||
+  // highest priority: the exchange's few CTAs must get SM resources as soon as blocks of the (much larger)
+  // stencil grid retire, or they would only run once that grid is exhausted — no overlap
+  int prio_lo = 0, prio_hi = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+  if (cudaStreamCreateWithPriority(&c->side, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->ready, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->done, cudaEventDisableTiming) != cudaSuccess) {
     g_nccl.CommDestroy(c->comm);
