@@ -10,6 +10,7 @@ from .grid import Grid  # noqa: F401
 from .grid_ufunc import GridUFunc, apply_as_grid_ufunc, as_grid_ufunc  # noqa: F401
 from .labeled import DataArray, Dataset  # noqa: F401
 from .padding import pad  # noqa: F401
+from . import ingest  # noqa: F401  (chunked ingest: disk -> page-locked ring -> device)
 
 __version__ = "0.1.0"
 __all__ = [
