@@ -339,6 +339,20 @@ def test_stencil2_host_streams_slabs(dtype):
         np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("n0", [3, 4, 5, 9, 10, 13])
+def test_stencil2_host_extrapolate_edge_slabs(n0):
+    """with the opt-in `extrapolate` boundary along the slabbed (outermost) axis the edge slab must
+    hold two source planes; host result == device result for slab heights that used to leave a one-row tail."""
+    from xgcm_b200 import ops
+
+    a = _field((n0, 6, 40), np.float32, seed=28)
+    for (lo, hi) in [(1, 0), (0, 1), (1, 1)]:
+        for op in ("diff", "interp"):
+            got = ops.stencil2_host(a, 0, op, lo, hi, "extrapolate")
+            want = ops.stencil2(_t(a), 0, op, lo, hi, "extrapolate").cpu().numpy()
+            np.testing.assert_array_equal(got, want)
+
+
 def test_stencil2_host_large_pinned():
     """Many slabs, page-locked buffers: identical to the device path."""
     from xgcm_b200 import ops

@@ -167,6 +167,13 @@ extern "C" int xg_stencil2_host(int op, int dtype, const void* in, void* out, in
   if (rows < 1) rows = 1;
   if (rows > (n0_out + 3) / 4) rows = (n0_out + 3) / 4;
   if (rows < 1) rows = 1;
+  if (ax0 && bc == XG_BC_EXTRAPOLATE && (lo || hi)) {
+    // the extrapolated halo is 2 A[edge] - A[next]: the slab that touches an edge of the axis must hold two
+    // source planes, i.e. no one-row slab at either end (a one-row tail is merged by growing the slab height)
+    if (rows < 2) rows = 2;
+    while (rows < n0_out && n0_out % rows == 1) ++rows;
+    if (rows > n0_out) rows = n0_out;
+  }
   const int64_t nslab = xg_ceil_div(n0_out, rows);
   const int64_t in_rows_max = ax0 ? rows + 1 : rows;
 
