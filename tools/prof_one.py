@@ -21,6 +21,8 @@ fns = {
     "interp_z_metric": lambda: ops.stencil2(x, 0, "interp", 1, 0, "extend", pre=dz, post=dz),
     "wreduce_z": lambda: ops.wreduce(x, 0, dz, "sum"),
     "wreduce_x": lambda: ops.wreduce(x, 2, None, "sum"),
+    "multi_xyz": lambda: ops.stencil_multi(x, [(2, "interp", 1, 0, "periodic", 0.0), (1, "interp", 1, 0, "fill", 0.0), (0, "interp", 1, 0, "extend", 0.0)]),
+    "multi_yz": lambda: ops.stencil_multi(x, [(1, "interp", 1, 0, "fill", 0.0), (0, "interp", 1, 0, "extend", 0.0)]),
 }
 for _ in range(3):
     fns[name]()
