@@ -42,6 +42,7 @@ def install(monkeypatch):
         return _t(arr), True
 
     monkeypatch.setattr(device, "as_device_tensor", as_device_tensor)
+    monkeypatch.setattr(device, "as_device_constant", lambda data, dev=None: as_device_tensor(data, dev)[0])
     monkeypatch.setattr(device, "result_like", lambda t, was_host: t.numpy() if was_host else t)
 
     def stencil2(x, axis, op, lo, hi, padding, fill_value=0.0, pre=None, post=None, halo_lo=None,

@@ -528,13 +528,7 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
       a.small_index = a.outer * a.nvec_inner < (1ll << 31);
       const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
       if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
-      // few scan lines (a long axis with a short outer part, e.g. Y of a (75, 2400, 3600) field: 67 500 threads =
-      // 14 warps per SM): occupancy cannot hide the latency, so each thread keeps twice as many loads in flight
-      // (ncu, profiles/r2: long-scoreboard 15.3 per issue at U = 8)
-      if (!MET && a.outer * a.nvec_inner < 148ll * 1024)
-        k_scan_strided<T, VEC, MET, 2 * U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
-      else
-        k_scan_strided<T, VEC, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+      k_scan_strided<T, VEC, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
     } else {
       a.pre.vec_ok = 0;
       a.post.vec_ok = 0;

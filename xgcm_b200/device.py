@@ -45,19 +45,32 @@ def as_device_tensor(data, device=None) -> Tuple[torch.Tensor, bool]:
     if not arr.flags.writeable:
         arr = arr.copy()
     dev = device if device is not None else default_device()
-    if arr.nbytes <= _SMALL_BYTES:
-        # coordinate vectors, target levels, 1-D metrics: a pageable upload blocks the host until the copy has
-        # drained behind whatever kernel is running — for a 1 ms kernel that serialises consecutive calls.
-        # Identical small operands (by content) are uploaded once and re-used (never written to by the library).
-        key = (arr.dtype.str, arr.shape, str(dev), hash(arr.tobytes()))
-        hit = _small_cache.get(key)
-        if hit is None:
-            if len(_small_cache) >= 256:
-                _small_cache.clear()
-            hit = torch.from_numpy(arr.copy()).to(dev)
-            _small_cache[key] = hit
-        return hit, True
     return torch.from_numpy(arr).to(dev, non_blocking=True), True
+
+
+def as_device_constant(data, device=None) -> torch.Tensor:
+    """Device copy of a SMALL read-only host operand (coordinate vector, target levels, 1-D metric), uploaded once
+    per content.  A pageable upload blocks the host until the copy has drained behind whatever kernel is running
+    — for a 1 ms kernel that serialises consecutive calls — so identical small operands are re-used.  The returned
+    tensor is shared: callers must never write to it (fields go through :func:`as_device_tensor`)."""
+    if isinstance(data, torch.Tensor):
+        return as_device_tensor(data, device)[0]
+    arr = np.asarray(data)
+    if arr.dtype not in _FLOAT:
+        arr = arr.astype(np.float64)
+    if not arr.flags.c_contiguous:
+        arr = np.ascontiguousarray(arr)
+    if arr.nbytes > _SMALL_BYTES:
+        return as_device_tensor(arr, device)[0]
+    dev = device if device is not None else default_device()
+    key = (arr.dtype.str, arr.shape, str(dev), hash(arr.tobytes()))
+    hit = _small_cache.get(key)
+    if hit is None:
+        if len(_small_cache) >= 256:
+            _small_cache.clear()
+        hit = torch.from_numpy(arr.copy()).to(dev)
+        _small_cache[key] = hit
+    return hit
 
 
 def result_like(t: torch.Tensor, was_host: bool):

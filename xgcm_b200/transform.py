@@ -43,7 +43,7 @@ def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, ta
     broadcast dims of the output, like ``xr.apply_ufunc`` does.
     """
     from . import ops
-    from .device import as_device_tensor, result_like
+    from .device import as_device_constant, as_device_tensor, result_like
 
     if theta_dim not in theta.dims:
         raise ValueError(f"`target_data` must have the dimension {theta_dim!r} of the transform axis")
@@ -99,7 +99,7 @@ def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, ta
     axis_num = work_dims.index(phi_dim)
     # theta -> tensor broadcastable against the working dims
     th_dims = [d if d != theta_dim else phi_dim for d in theta.dims]
-    th_t, _ = as_device_tensor(theta.data, x.device)
+    th_t = as_device_constant(theta.data, x.device)  # read-only: the 1-D coordinate is uploaded once per content
     present = [d for d in work_dims if d in th_dims]
     perm = [th_dims.index(d) for d in present]
     if perm != list(range(len(perm))):
@@ -113,7 +113,7 @@ def linear_interpolation(phi, theta, target_theta_levels, phi_dim, theta_dim, ta
     th_t = th_t.reshape([sizes[d] if d in th_dims else 1 for d in work_dims])
     # target -> (column dims..., m)
     col_dims = [d for d in work_dims if d != phi_dim]
-    tg_t, _ = as_device_tensor(target_theta_levels.data, x.device)
+    tg_t = as_device_constant(target_theta_levels.data, x.device)
     if tgt_other:
         tdims = list(target_theta_levels.dims)
         order = [d for d in col_dims if d in tdims] + [target_dim]
