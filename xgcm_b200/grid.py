@@ -1093,9 +1093,17 @@ _CUMSUM_REV = {
 }
 
 
+_SELECTED_UFUNCS: Dict[tuple, "GridUFunc"] = {}
+
+
 def _select_grid_ufunc(funcname, signature: _GridUFuncSignature, module, **kwargs):
     """Pick the GridUFunc of ``module`` whose name starts with ``funcname`` and whose
-    signature is equivalent (grid.py:1779-1824)."""
+    signature is equivalent (grid.py:1779-1824).  The scan is memoised per (module, name,
+    signature text): it is pure, and at BASELINE configs[0] sizes it cost more than the kernel."""
+    key = (module.__name__, funcname, str(signature))
+    hit = _SELECTED_UFUNCS.get(key)
+    if hit is not None:
+        return hit, kwargs
     candidates = inspect.getmembers(module, lambda obj: isinstance(obj, GridUFunc))
     by_name = [f for name, f in candidates if name.startswith(funcname)]
     if not by_name:
@@ -1109,4 +1117,5 @@ def _select_grid_ufunc(funcname, signature: _GridUFuncSignature, module, **kwarg
         raise ValueError(
             f"Function {funcname} with signature='{signature}' and kwargs={kwargs} is an ambiguous selection"
         )
+    _SELECTED_UFUNCS[key] = matching[0]
     return matching[0], kwargs

@@ -95,17 +95,28 @@ class _GridUFuncSignature:
         return ",".join(f"({a})" for a in args)
 
     def __str__(self):
-        return (
-            f"{self._side(self.in_ax_names, self.in_ax_positions)}->"
-            f"{self._side(self.out_ax_names, self.out_ax_positions)}"
-        )
+        text = self.__dict__.get("_text")
+        if text is None:
+            text = self._text = (
+                f"{self._side(self.in_ax_names, self.in_ax_positions)}->"
+                f"{self._side(self.out_ax_names, self.out_ax_positions)}"
+            )
+        return text
 
     def __repr__(self):
         return f"_GridUFuncSignature('{self}')"
 
+    _PARSED: Dict[str, "_GridUFuncSignature"] = {}
+
     @classmethod
     def from_string(cls, signature: str) -> "_GridUFuncSignature":
-        return cls(*_parse_signature_from_string(signature))
+        # signatures are never mutated after construction, so the parse is shared
+        hit = cls._PARSED.get(signature) if cls is _GridUFuncSignature else None
+        if hit is None:
+            hit = cls(*_parse_signature_from_string(signature))
+            if cls is _GridUFuncSignature and len(cls._PARSED) < 4096:
+                cls._PARSED[signature] = hit
+        return hit
 
     @classmethod
     def from_type_hints(cls, hints: Dict[str, Any]) -> "_GridUFuncSignature":
