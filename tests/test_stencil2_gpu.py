@@ -107,6 +107,84 @@ def test_metric_weighting_bit_exact(dtype):
                     _check(a, axis, "interp", lo, hi, bc, fill, pre, post)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(7, 5, 256), (5, 3, 132), (2, 2, 128), (9, 1, 260), (3, 2, 4, 136), (6, 520),
+                                   (7, 5, 1000), (5, 9, 452), (3, 2, 3, 676), (6, 904), (2, 3, 1792)])
+def test_metric_shared_divisor_rows_bit_exact(dtype, shape):
+    """The z-batched row kernels (register-staged below 2 tiles per row, TMA-staged above; divisor
+    dx(Y, X) or dx(X) shared by every level, inverted once):
+    same bits as the reference's separate multiply / op / divide passes, every boundary, halo side
+    and pre-metric layout, ragged level counts (Zn % 4 != 0) and ragged last chunks."""
+    rng = np.random.default_rng(50)
+    a = _field(shape, dtype, seed=51, nan_frac=0.01)
+    nd = len(shape)
+    axis = nd - 1
+
+    def metric(dims):
+        shp = [shape[d] if d in dims else 1 for d in range(nd)]
+        return (0.5 + rng.random(shp)).astype(dtype)
+
+    posts = [metric((nd - 2, nd - 1)), metric((nd - 1,))]
+    pres = [None, metric(range(nd)), metric((nd - 2, nd - 1)), metric((0,)), metric((nd - 1,)), metric((nd - 2,))]
+    for (lo, hi) in ((1, 0), (0, 1)):
+        for (bc, fill) in BCS + [("extrapolate", 0.0)]:
+            for post in posts:
+                for pre in pres:
+                    for op in ("diff", "interp"):
+                        _check(a, axis, op, lo, hi, bc, fill, pre, post)
+            _check(a, axis, "max", lo, hi, bc, fill, None, posts[0])
+            _check(a, axis, "min", lo, hi, bc, fill, pres[2], posts[0])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("X,kernel", [(256, "row_zb"), (1024, "row_tma")])
+def test_shared_divisor_division_is_ieee_on_arbitrary_bit_patterns(dtype, X, kernel):
+    """x / b through the shared reciprocal against numpy's division on raw bit patterns: zeros,
+    subnormals, infinities, NaNs, quotients that overflow, underflow or land in the subnormal range.
+    `max` against an -inf fill hands the field value itself to the divide, so numerator and divisor
+    are both fully controlled."""
+    from xgcm_b200 import ops
+
+    rng = np.random.default_rng(52)
+    Z, Y = 16, 256 * (1024 // X)
+    bits = np.uint32 if dtype == np.float32 else np.uint64
+    hi_bit = 32 if dtype == np.float32 else 64
+
+    def patterns(shape):
+        raw = rng.integers(0, 2 ** hi_bit, size=shape, dtype=np.uint64).astype(bits)
+        return raw.view(dtype)
+
+    specials = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, np.finfo(dtype).max, -np.finfo(dtype).max,
+                         np.finfo(dtype).tiny, np.finfo(dtype).smallest_subnormal, 1.0, -1.0, 3.0, 1 / 3],
+                        dtype=dtype)
+    a = patterns((Z, Y, X))
+    a[:, :, :32] = rng.choice(specials, size=(Z, Y, 32))
+    b = patterns((1, Y, X))
+    b[:, :, 16:48] = rng.choice(specials, size=(1, Y, 32))
+    # near-1 quotients: numerator and divisor share the exponent, mantissas random
+    a[:, :, 64:128] = (1.0 + rng.random((Z, Y, 64))).astype(dtype)
+    b[:, :, 64:128] = (1.0 + rng.random((1, Y, 64))).astype(dtype)
+    dev = torch.device("cuda:0")
+    # max(A[x-1], A[x]) on a field whose odd columns repeat the even ones is the field itself there
+    a2 = a.copy()
+    a2[:, :, 1::2] = a2[:, :, 0::2]
+    with np.errstate(all="ignore"):
+        want = (a2 / b)[:, :, 1::2]
+    m = torch.from_numpy(b).to(dev)
+    got = ops.stencil2(torch.from_numpy(a2).to(dev), 2, "max", 1, 0, "fill", -np.inf, post=m).cpu().numpy()
+    assert _capi_last_launch() == f"xg_stencil2({kernel})"
+    got = got[:, :, 1::2]
+    np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
+    ok = ~np.isnan(want)
+    np.testing.assert_array_equal(got.view(bits)[ok], want.view(bits)[ok])  # signed zeros included
+
+
+def _capi_last_launch():
+    from xgcm_b200 import _capi
+
+    return _capi.last_launch()
+
+
 def test_metric_4d_outer_broadcast():
     """(T, Z, Y, X) field with dx(Y, X) along X and dz(Z) along Y: multi-group outer index."""
     shape = (3, 4, 10, 16)

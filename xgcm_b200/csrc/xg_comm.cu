@@ -115,6 +115,7 @@ struct PlaneArgs {
   int64_t outer, n, inner;
   int64_t nvec_inner;  // vectors (or scalars) per row of `inner`
   bool small;          // outer * nvec_inner < 2^31
+  XgFastDiv fd_nvi;    // multiply-high form of nvec_inner (valid with small)
   XgOperand pre, post;
 };
 
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(256) k_pack_plane(const PlaneArgs<T> a, int64_
   const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= a.outer * a.nvec_inner) return;
   int64_t o, iv;
-  xg_divmod(g, a.nvec_inner, a.small, o, iv);
+  xg_divmod(g, a.nvec_inner, a.fd_nvi, a.small, o, iv);
   const int64_t i = iv * VEC;
   XgPack<T, VEC> v = xg_ld_stream<T, VEC>(a.in + (o * a.n + j) * a.inner + i);
   if (a.pre.ptr) {
@@ -144,7 +145,7 @@ __global__ void __launch_bounds__(256) k_edge_fix(const PlaneArgs<T> a, const T*
   const int64_t g = (int64_t)blockIdx.x * 256 + threadIdx.x;
   if (g >= a.outer * a.nvec_inner) return;
   int64_t o, iv;
-  xg_divmod(g, a.nvec_inner, a.small, o, iv);
+  xg_divmod(g, a.nvec_inner, a.fd_nvi, a.small, o, iv);
   const int64_t i = iv * VEC;
   XgPack<T, VEC> v = xg_ld_stream<T, VEC>(a.in + (o * a.n + j_src) * a.inner + i);
   const XgPack<T, VEC> h = xg_ld_stream<T, VEC>(halo + o * a.inner + i);
@@ -241,6 +242,7 @@ int sharded_typed(XgComm* c, int op, const void* in, void* out, int ndim, const 
   }
   pa.nvec_inner = vec_ok ? v.inner / VECW : v.inner;
   pa.small = v.outer * pa.nvec_inner < (1ll << 31);
+  pa.fd_nvi = xg_fastdiv_make(pa.small ? pa.nvec_inner : 1);
   const int64_t nblk = xg_ceil_div(v.outer * pa.nvec_inner, 256);
   if (nblk > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2_sharded: plane too large");
   const unsigned blocks = (unsigned)(nblk > 0 ? nblk : 1);

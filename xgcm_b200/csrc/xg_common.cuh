@@ -23,11 +23,44 @@ int xg_check_launch(const char* what);
 // ---------------------------------------------------------------------------
 // broadcast operand descriptor
 // ---------------------------------------------------------------------------
+// Division by a launch constant d >= 1 of a dividend below 2^31 as multiply-high + shift
+// (Granlund-Montgomery: l = ceil(log2 d), mul = ceil(2^(31+l) / d), q = umulhi(x, mul) >> (l-1);
+// exact for every x < 2^31).  A generic 32-bit division is ~20 SASS instructions and the fused-metric
+// kernels need up to nine per thread; this form is two.
+struct XgFastDiv {
+  uint32_t d;
+  uint32_t mul;  // 0: d == 1 (quotient = dividend)
+  uint32_t sh;
+};
+
+static inline XgFastDiv xg_fastdiv_make(int64_t d) {
+  XgFastDiv f;
+  f.d = (uint32_t)d;
+  f.mul = 0;
+  f.sh = 0;
+  if (d >= 2 && d < (1ll << 31)) {
+    int l = 0;
+    while ((1ll << l) < d) ++l;
+    f.mul = (uint32_t)((((uint64_t)1 << (31 + l)) + (uint64_t)d - 1) / (uint64_t)d);
+    f.sh = (uint32_t)(l - 1);
+  }
+  return f;
+}
+
+__host__ __device__ __forceinline__ uint32_t xg_fastdiv_q(uint32_t x, const XgFastDiv& f) {
+#ifdef __CUDA_ARCH__
+  return f.mul ? (__umulhi(x, f.mul) >> f.sh) : x;
+#else
+  return f.mul ? (uint32_t)(((uint64_t)x * f.mul) >> 32) >> f.sh : x;
+#endif
+}
+
 struct XgGroups {
   int n;
   int small;  // every size and the total extent fit in 31 bits: 32-bit index math
   int64_t size[XG_MAXG];
   int64_t stride[XG_MAXG];
+  XgFastDiv fd[XG_MAXG];  // of size[k]; valid when `small`
 };
 
 enum { XG_IM_BCAST = 0, XG_IM_CONTIG = 1, XG_IM_GENERIC = 2 };
@@ -62,9 +95,8 @@ __host__ __device__ __forceinline__ int64_t xg_groups_offset(const XgGroups& g,
 #pragma unroll
     for (int k = XG_MAXG - 1; k >= 0; --k) {
       if (k < g.n) {
-        const uint32_t sz = (uint32_t)g.size[k];
-        const uint32_t q = f / sz;
-        off += (int64_t)(f - q * sz) * g.stride[k];
+        const uint32_t q = xg_fastdiv_q(f, g.fd[k]);
+        off += (int64_t)(f - q * g.fd[k].d) * g.stride[k];
         f = q;
       }
     }
@@ -87,6 +119,18 @@ __device__ __forceinline__ void xg_divmod(int64_t x, int64_t d, bool small, int6
     const uint32_t qq = (uint32_t)x / (uint32_t)d;
     q = qq;
     r = (uint32_t)x - qq * (uint32_t)d;
+  } else {
+    q = x / d;
+    r = x - q * d;
+  }
+}
+// the same with the divisor's multiply-high form prepared on the host (`small` implies x < 2^31)
+__device__ __forceinline__ void xg_divmod(int64_t x, int64_t d, const XgFastDiv& f, bool small, int64_t& q,
+                                          int64_t& r) {
+  if (small) {
+    const uint32_t qq = xg_fastdiv_q((uint32_t)x, f);
+    q = qq;
+    r = (uint32_t)x - qq * f.d;
   } else {
     q = x / d;
     r = x - q * d;
@@ -255,5 +299,53 @@ __device__ __forceinline__ T xg_apply_op(T a, T b) {
     return (a > b || xg_isnan(a)) ? a : b;
   }
 }
+
+// ---------------------------------------------------------------------------
+// division by a divisor shared between several cells (same metric value for every level)
+// ---------------------------------------------------------------------------
+// Correctly rounded a / b from r = RN(1/b) with five fp64 operations instead of the ~30 of the
+// generic division (Markstein's FMA-based sequence: q0 = RN(a r) is within 2 ulp, the first
+// correction makes it faithful, and for a faithful q with r within half an ulp of 1/b the second
+// correction q + RN(a - b q) r rounds to exactly RN(a / b)).  Only valid when no intermediate
+// can leave the normal range; the caller guards the exponents of a and b and falls back to `/`.
+__device__ __forceinline__ double xg_div_with_recip(double a, double b, double r) {
+  const double q0 = a * r;
+  const double e0 = fma(-b, q0, a);
+  const double q1 = fma(e0, r, q0);
+  const double e1 = fma(-b, q1, a);
+  return fma(e1, r, q1);
+}
+__device__ __forceinline__ bool xg_exponent_safe(double v) {
+  // |v| in [2^-400, 2^400]: biased exponent in [623, 1423]; false for 0, subnormals, NaN, inf
+  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
+  return (e - 623u) <= 800u;
+}
+
+// x / b for many x and one b, bit-identical to the IEEE division.
+//   float : RN32(RN64(x * RN64(1 / b))).  The fp64 product is within 2^-52 (relative) of x / b,
+//           while a quotient of two 24-bit significands is never closer than 2^-49 to a rounding
+//           boundary of binary32 (midpoints have 25-bit significands; subnormal and overflow
+//           boundaries included), so the second rounding lands where the direct one would.
+//           Zeros, infinities and NaNs follow from IEEE arithmetic on the reciprocal; no guard.
+//   double: Markstein's sequence above behind the exponent guards, else the plain division.
+template <typename T>
+struct XgSharedDivisor;
+template <>
+struct XgSharedDivisor<float> {
+  double r;
+  __device__ __forceinline__ void set(float b) { r = __drcp_rn((double)b); }
+  __device__ __forceinline__ float div(float x) const { return (float)((double)x * r); }
+};
+template <>
+struct XgSharedDivisor<double> {
+  double b, r;  // r == 0: no fast path for this divisor
+  __device__ __forceinline__ void set(double b_) {
+    b = b_;
+    r = xg_exponent_safe(b_) ? 1.0 / b_ : 0.0;
+  }
+  __device__ __forceinline__ double div(double x) const {
+    return (r != 0.0 && xg_exponent_safe(x)) ? xg_div_with_recip(x, b, r) : x / b;
+  }
+};
 
 __host__ __device__ static inline int64_t xg_ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }

@@ -113,6 +113,7 @@ static int collapse_groups(const int64_t* shape, const int64_t* strides, int d0,
     extent *= shape[d] > 0 ? shape[d] : 1;
   }
   g->small = small ? 1 : 0;
+  for (int k = 0; k < XG_MAXG; ++k) g->fd[k] = xg_fastdiv_make(small ? g->size[k] : 1);
   return XG_OK;
 }
 

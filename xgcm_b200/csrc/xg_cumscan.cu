@@ -31,6 +31,7 @@ struct ScanArgs {
   XgOperand pre, post;
   int64_t nvec_inner;
   bool small_index;  // outer * nvec_inner < 2^31
+  XgFastDiv fd_nvi;  // multiply-high form of nvec_inner (valid with small_index)
 };
 
 template <typename T>
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kThreads) k_scan_strided(const ScanArgs<T> a) 
   const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (g >= a.outer * a.nvec_inner) return;
   int64_t o, iv;
-  xg_divmod(g, a.nvec_inner, a.small_index, o, iv);
+  xg_divmod(g, a.nvec_inner, a.fd_nvi, a.small_index, o, iv);
   const int64_t i = iv * VEC;
   const T* ibase = a.in + o * a.n * a.inner + i;
   T* obase = a.out + o * a.n_out * a.inner + i;
@@ -526,6 +527,7 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
     if (vec_ok) {
       a.nvec_inner = a.inner / VEC;
       a.small_index = a.outer * a.nvec_inner < (1ll << 31);
+      a.fd_nvi = xg_fastdiv_make(a.small_index ? a.nvec_inner : 1);
       const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
       if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
       k_scan_strided<T, VEC, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
@@ -534,6 +536,7 @@ int scan_launch(ScanArgs<T>& a, cudaStream_t st) {
       a.post.vec_ok = 0;
       a.nvec_inner = a.inner;
       a.small_index = a.outer * a.nvec_inner < (1ll << 31);
+      a.fd_nvi = xg_fastdiv_make(a.small_index ? a.nvec_inner : 1);
       const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
       if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_cumscan: grid too large");
       k_scan_strided<T, 1, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
@@ -591,6 +594,7 @@ int cumscan_typed(const void* in, void* out, int ndim, const int64_t* shape, int
   a.fill = static_cast<T>(fill);
   a.nvec_inner = 0;
   a.small_index = false;
+  a.fd_nvi = xg_fastdiv_make(1);
   if (kept == 0 && (pad_lo || pad_hi) && bc != XG_BC_FILL)
     return xg_fail(XG_EINVAL, "xg_cumscan: cannot wrap/extend an empty axis");
   if (v.outer == 0 || v.inner == 0 || a.n_out == 0) return XG_OK;

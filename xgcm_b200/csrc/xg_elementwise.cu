@@ -23,6 +23,7 @@ struct PadArgs {
   T fill;
   int64_t nvec_inner;  // vectors per row of `inner`
   bool small;          // total output vectors < 2^31: 32-bit index math
+  XgFastDiv fd_nvi, fd_nout;  // multiply-high forms of nvec_inner / n_out (valid with small)
 };
 
 template <typename T, int VEC>
@@ -32,8 +33,8 @@ __global__ void __launch_bounds__(kThreads) k_pad(const PadArgs<T> a) {
   for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < total;
        g += (int64_t)gridDim.x * kThreads) {
     int64_t iv, t, k, o;
-    xg_divmod(g, a.nvec_inner, a.small, t, iv);
-    xg_divmod(t, a.n_out, a.small, o, k);
+    xg_divmod(g, a.nvec_inner, a.fd_nvi, a.small, t, iv);
+    xg_divmod(t, a.n_out, a.fd_nout, a.small, o, k);
     const int64_t i = iv * VEC;
     const T* base = a.in + o * a.n * a.inner + i;
     int64_t s = k - a.lo;
@@ -79,7 +80,7 @@ __global__ void __launch_bounds__(kThreads) k_pad_rows(const PadArgs<T> a, int64
   if (g >= total_vec) return;
   const int64_t e0 = g * VEC;
   int64_t o, k;
-  xg_divmod(e0, a.n_out, a.small, o, k);
+  xg_divmod(e0, a.n_out, a.fd_nout, a.small, o, k);
   Pack v;
 #pragma unroll
   for (int q = 0; q < VEC; ++q) {
@@ -146,6 +147,8 @@ int pad_typed(const void* in, void* out, int ndim, const int64_t* shape, int axi
     const int64_t total_vec = xg_ceil_div(total, VEC);
     a.nvec_inner = 1;
     a.small = total < (1ll << 31);
+    a.fd_nvi = xg_fastdiv_make(1);
+    a.fd_nout = xg_fastdiv_make(a.small ? a.n_out : 1);
     const int64_t blocks = xg_ceil_div(total_vec, kThreads);
     if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_pad: grid too large");
     k_pad_rows<T, VEC><<<(unsigned)blocks, kThreads, 0, st>>>(a, total_vec, total);
@@ -155,6 +158,8 @@ int pad_typed(const void* in, void* out, int ndim, const int64_t* shape, int axi
   a.nvec_inner = vec_ok ? v.inner / VEC : v.inner;
   const int64_t total = a.outer * a.n_out * a.nvec_inner;
   a.small = total < (1ll << 31);
+  a.fd_nvi = xg_fastdiv_make(a.small ? a.nvec_inner : 1);
+  a.fd_nout = xg_fastdiv_make(a.small ? a.n_out : 1);
   int64_t blocks = xg_ceil_div(total, kThreads);
   if (blocks > 148 * 32) blocks = 148 * 32;
   if (vec_ok)
@@ -173,6 +178,7 @@ struct BinArgs {
   XgOperand b;  // outer groups over rows, axis_stride along the last dim
   int b_vec_ok;
   bool small;
+  XgFastDiv fd_nvec;  // multiply-high form of nvec (valid with small)
 };
 
 template <typename T, int OP>
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(kThreads) k_binary(const BinArgs<T> a) {
   for (int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x; g < total;
        g += (int64_t)gridDim.x * kThreads) {
     int64_t r, xq;
-    xg_divmod(g, a.nvec, a.small, r, xq);
+    xg_divmod(g, a.nvec, a.fd_nvec, a.small, r, xq);
     const int64_t x0 = xq * VEC;
     const int64_t boff = xg_groups_offset(a.b.outer, r);
     Pack va = xg_ld_stream<T, VEC>(a.a + r * a.n + x0);
@@ -218,6 +224,7 @@ template <typename T, int VEC>
 int binary_launch(int binop, BinArgs<T>& a, cudaStream_t st) {
   const int64_t total = a.rows * a.nvec;
   a.small = total < (1ll << 31);
+  a.fd_nvec = xg_fastdiv_make(a.small ? a.nvec : 1);
   int64_t blocks = xg_ceil_div(total, kThreads);
   if (blocks > 148 * 32) blocks = 148 * 32;
   switch (binop) {

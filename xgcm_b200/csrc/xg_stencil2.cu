@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "xg_common.cuh"
+#include "xg_tma.cuh"
 
 namespace {
 
@@ -36,6 +37,7 @@ struct StencilArgs {
   int64_t nseg, nwc;   // segments along the axis, warp-columns (or row chunks)
   int64_t nunits;      // total warp-units
   bool small_units;    // nunits < 2^31: 32-bit unit decomposition
+  XgFastDiv fd_nseg, fd_nwc;  // multiply-high forms of nseg / nwc (valid with small_units)
   bool seg_fast;       // unit order: segment index fastest (else warp-column fastest)
   XgOperand pre, post;
   int pre_axis_vec_ok, post_axis_vec_ok;  // row kernels: metric vector loads along x
@@ -49,8 +51,8 @@ constexpr int kWarpsPerBlock = kThreads / 32;
 // ---------------------------------------------------------------------------
 // strided-axis kernel
 // ---------------------------------------------------------------------------
-template <typename T, int VEC, int OP, bool MET, int U>
-__global__ void __launch_bounds__(kThreads, 4)  // <= 64 registers: 4 CTAs (1024 threads) per SM
+template <typename T, int VEC, int OP, bool MET, int U, int MINB = 4>
+__global__ void __launch_bounds__(kThreads, MINB)  // MINB = 4: <= 64 registers, 4 CTAs (1024 threads) per SM
 k_stencil_strided(const StencilArgs<T> a) {
   typedef XgPack<T, VEC> Pack;
   const int64_t unit =
@@ -59,11 +61,11 @@ k_stencil_strided(const StencilArgs<T> a) {
   const int lane = threadIdx.x & 31;
   int64_t wc, t, seg, o;
   if (a.seg_fast) {  // segments of one column group adjacent in launch order
-    xg_divmod(unit, a.nseg, a.small_units, t, seg);
-    xg_divmod(t, a.nwc, a.small_units, o, wc);
+    xg_divmod(unit, a.nseg, a.fd_nseg, a.small_units, t, seg);
+    xg_divmod(t, a.nwc, a.fd_nwc, a.small_units, o, wc);
   } else {
-    xg_divmod(unit, a.nwc, a.small_units, t, wc);
-    xg_divmod(t, a.nseg, a.small_units, o, seg);
+    xg_divmod(unit, a.nwc, a.fd_nwc, a.small_units, t, wc);
+    xg_divmod(t, a.nseg, a.fd_nseg, a.small_units, o, seg);
   }
   const int64_t i = (wc * 32 + lane) * VEC;
   if (i >= a.inner) return;
@@ -97,9 +99,17 @@ k_stencil_strided(const StencilArgs<T> a) {
 #pragma unroll
     for (int k = 0; k < VEC; ++k) r.v[k] = xg_apply_op<T, OP>(lo_v.v[k], hi_v.v[k]);
     if (has_post) {
-      Pack m = xg_ld_view<T, VEC>(post_v, j * a.post.axis_stride);
+      if (sizeof(T) == 4 && post_v.mode == XG_IM_BCAST) {
+        // dz(Z) against a (Z, Y, X) field: one divisor for the whole vector, inverted once
+        XgSharedDivisor<T> d;
+        d.set(__ldg(post_v.p0 + j * a.post.axis_stride));
 #pragma unroll
-      for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / m.v[k];
+        for (int k = 0; k < VEC; ++k) r.v[k] = d.div(r.v[k]);
+      } else {
+        Pack m = xg_ld_view<T, VEC>(post_v, j * a.post.axis_stride);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) r.v[k] = r.v[k] / m.v[k];
+      }
     }
     xg_st_stream<T, VEC>(obase + j * a.inner, r);
   };
@@ -253,7 +263,7 @@ k_stencil_row_vec(const StencilArgs<T> a) {
   if (unit >= a.nunits) return;  // warp-uniform
   const int lane = threadIdx.x & 31;
   int64_t c, r;
-  xg_divmod(unit, a.nwc, a.small_units, r, c);
+  xg_divmod(unit, a.nwc, a.fd_nwc, a.small_units, r, c);
   const int64_t nv = a.n / VEC;
   RowAccess<T, MET> ra(a, r);
   T* orow = a.out + r * a.n;  // n_out == n
@@ -321,6 +331,332 @@ k_stencil_row_vec(const StencilArgs<T> a) {
 }
 
 // ---------------------------------------------------------------------------
+// row kernel, divisor shared between levels ("z-batched")
+// ---------------------------------------------------------------------------
+// derivative('X') on a (Z, Y, X) field divides by dx(Y, X): the same divisor for every level.
+// Here a warp owns one 512-byte chunk of a row at U consecutive LEVELS (rows r, r + P, ...,
+// P = rows per level), so the divisor vector is loaded and inverted once and each of the U x VEC
+// cells costs a multiply instead of an 11-instruction IEEE division (XgSharedDivisor keeps the
+// quotient bit-identical).  Loads in flight per thread: U field vectors + one metric vector, as
+// in k_stencil_row_vec; the unit decomposition is three multiply-high divisions.
+template <typename T>
+struct RowZbArgs {
+  const T* in;
+  T* out;
+  int64_t n;       // row length (n_out == n)
+  int64_t P, Zn;   // row r = z * P + p; the post metric depends on p only
+  int lo, bc;      // hi == 1 - lo
+  T fill;
+  const T* halo_lo;
+  const T* halo_hi;
+  XgOperand pre, post;
+  int pre_vec;     // pre: 16-byte loads along x are aligned
+  int pre_shared;  // pre: also independent of z
+  int64_t nwc, nunits;
+  XgFastDiv fd_nwc, fd_P;
+  bool small_units;
+};
+
+template <typename T, int VEC, int OP, int U>
+__global__ void __launch_bounds__(kThreads) k_stencil_row_zb(const RowZbArgs<T> a) {
+  typedef XgPack<T, VEC> Pack;
+  const unsigned FULL = 0xffffffffu;
+  const int64_t unit = (int64_t)blockIdx.x * kWarpsPerBlock + (threadIdx.x >> 5);
+  if (unit >= a.nunits) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  int64_t c, t, p, zq;
+  xg_divmod(unit, a.nwc, a.fd_nwc, a.small_units, t, c);
+  xg_divmod(t, a.P, a.fd_P, a.small_units, zq, p);
+  const int64_t z0 = zq * U;
+  const int nz = (a.Zn - z0 < U) ? (int)(a.Zn - z0) : U;
+  const int64_t nv = a.n / VEC;
+  const int64_t q = c * 32 + lane;
+  const bool act = q < nv;
+  // spare lanes of the last chunk shadow the row's last vector: they stay in the shuffles and
+  // hold valid addresses, but never store
+  const int64_t x0 = (act ? q : nv - 1) * VEC;
+  const int64_t row0 = z0 * a.P + p;
+  const int64_t zstride = a.P * a.n;
+  const T* ip = a.in + row0 * a.n;
+  T* op = a.out + row0 * a.n + x0;
+  const bool has_pre = a.pre.ptr != nullptr;
+  const T* prep = reinterpret_cast<const T*>(a.pre.ptr);
+
+  Pack v[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u < nz) {
+      v[u] = xg_ld_stream<T, VEC>(ip + u * zstride + x0);
+    } else {
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) v[u].v[k] = T(0);
+    }
+  }
+  const Pack pm = xg_ld_cached<T, VEC>(reinterpret_cast<const T*>(a.post.ptr) +
+                                       xg_groups_offset(a.post.outer, p) + x0);
+  int64_t pre_off[U];
+  if (has_pre) {
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+      pre_off[u] = (u == 0 || !a.pre_shared) ? xg_groups_offset(a.pre.outer, row0 + (u < nz ? u : 0) * a.P)
+                                             : pre_off[0];
+    Pack m;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u < nz) {
+        if (u == 0 || !a.pre_shared) {
+          const T* pp = prep + pre_off[u];
+          if (a.pre.axis_stride == 0) {
+            const T sc = __ldg(pp);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) m.v[k] = sc;
+          } else if (a.pre_vec) {
+            m = xg_ld_cached<T, VEC>(pp + x0);
+          } else {
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) m.v[k] = __ldg(pp + (x0 + k) * a.pre.axis_stride);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) v[u].v[k] = v[u].v[k] * m.v[k];
+      }
+    }
+  }
+  // A[row u, s] = in * pre for the single elements the shuffles cannot provide
+  auto A = [&](int u, int64_t s) -> T {
+    T val = __ldg(ip + u * zstride + s);
+    if (has_pre) val = val * __ldg(prep + pre_off[u] + s * a.pre.axis_stride);
+    return val;
+  };
+
+  XgSharedDivisor<T> dv[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) dv[k].set(pm.v[k]);
+
+#pragma unroll
+  for (int u = 0; u < U; ++u) {
+    if (u >= nz) break;  // warp-uniform
+    Pack res;
+    if (a.lo == 1) {
+      // out[x] = OP(A[x-1], A[x]); lane 0 has no lower lane to ask
+      T nb = __shfl_up_sync(FULL, v[u].v[VEC - 1], 1);
+      if (lane == 0) {
+        if (c != 0) nb = A(u, x0 - 1);
+        else if (a.halo_lo) nb = __ldg(a.halo_lo + row0 + u * a.P);
+        else if (a.bc == XG_BC_FILL) nb = a.fill;
+        else if (a.bc == XG_BC_PERIODIC) nb = A(u, a.n - 1);
+        else if (a.bc == XG_BC_EXTEND) nb = v[u].v[0];
+        else nb = T(2) * v[u].v[0] - v[u].v[1];
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        res.v[k] = xg_apply_op<T, OP>(k == 0 ? nb : v[u].v[k > 0 ? k - 1 : 0], v[u].v[k]);
+    } else {
+      // out[x] = OP(A[x], A[x+1]); the row's last vector takes the upper boundary value
+      T nb = __shfl_down_sync(FULL, v[u].v[0], 1);
+      if (x0 + VEC >= a.n) {
+        if (a.halo_hi) nb = __ldg(a.halo_hi + row0 + u * a.P);
+        else if (a.bc == XG_BC_FILL) nb = a.fill;
+        else if (a.bc == XG_BC_PERIODIC) nb = A(u, 0);
+        else if (a.bc == XG_BC_EXTEND) nb = v[u].v[VEC - 1];
+        else nb = T(2) * v[u].v[VEC - 1] - v[u].v[VEC - 2];
+      } else if (lane == 31) {
+        nb = A(u, x0 + VEC);
+      }
+#pragma unroll
+      for (int k = 0; k < VEC; ++k)
+        res.v[k] = xg_apply_op<T, OP>(v[u].v[k], k == VEC - 1 ? nb : v[u].v[k < VEC - 1 ? k + 1 : k]);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) res.v[k] = dv[k].div(res.v[k]);
+    if (act) xg_st_stream<T, VEC>(op + u * zstride, res);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// row kernel, divisor shared between levels, TMA-staged ("row_tma")
+// ---------------------------------------------------------------------------
+// Same decomposition as k_stencil_row_zb (U levels share one divisor row), but the operands arrive by
+// bulk-async tensor loads: a tile is U levels x TY rows x TXE cells (+ one 16-byte halo vector), one
+// cp.async.bulk.tensor box per operand, all boxes of a tile completing on one mbarrier.  A persistent
+// CTA keeps a ring of NST tiles in flight (shared memory, not registers, holds the bytes in flight:
+// ~100 KB per CTA instead of the ~20 KB the register-staged kernels reach), threads read 16-byte
+// vectors and the neighbour element from the tile, and results leave as streaming 16-byte stores.
+// TXE is a multiple of 128 bytes so stores of neighbouring tiles never share a sector.
+template <typename T>
+struct RowTmaGeo;
+template <>
+struct RowTmaGeo<float> {
+  static constexpr int VEC = 4, TXE = 224, TY = 4;  // 56 vectors per row, 64 thread slots
+};
+template <>
+struct RowTmaGeo<double> {
+  static constexpr int VEC = 2, TXE = 240, TY = 2;  // 120 vectors per row, 128 thread slots
+};
+enum { XG_PRE_NONE = 0, XG_PRE_FULL = 1, XG_PRE_SHARED = 2, XG_PRE_SCALAR = 3 };
+
+template <typename T>
+struct RowTmaArgs {
+  const T* in;
+  T* out;
+  int64_t n, P, Zn;
+  int lo, bc;
+  T fill;
+  const T* halo_lo;
+  const T* halo_hi;
+  XgOperand pre;      // boundary elements and the per-row scalar mode
+  int pre_mode;       // XG_PRE_*
+  int pre_row_zero;   // shared pre without a row dim (dx(X)): always row 0 of its map
+  int post_row_zero;
+  int64_t ntx, npq, ntiles;
+  XgFastDiv fd_ntx, fd_npq;
+  int nst;                    // tiles in flight
+  unsigned field_bytes, pre_bytes, post_bytes, stage_bytes;  // box sizes rounded up to 128
+};
+
+template <typename T, int OP>
+__global__ void __launch_bounds__(kThreads, 2)
+    k_stencil_row_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_pre,
+                      const __grid_constant__ CUtensorMap map_post, const RowTmaArgs<T> a) {
+  typedef RowTmaGeo<T> G;
+  constexpr int VEC = G::VEC, TXE = G::TXE, TY = G::TY, U = 4;
+  constexpr int BOXW = TXE + VEC, LR = kThreads / TY, NVR = TXE / VEC;
+  typedef XgPack<T, VEC> Pack;
+  typedef typename XgVec<T, VEC>::type V;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int tid = threadIdx.x;
+  const uint32_t full_u32 = smem_u32(smem_raw);  // NST mbarriers, then the stages at +128
+  unsigned char* stage0 = smem_raw + 128;
+  const int NST = a.nst;
+  const int64_t nloc = (a.ntiles > blockIdx.x) ? (a.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+  const int xs = a.lo ? VEC : 0;  // the box starts one vector left of the tile when the lower neighbour is needed
+
+  auto tile_geom = [&](int64_t i, int64_t& z0, int64_t& p0, int64_t& x0) {
+    const uint32_t g = (uint32_t)(i * gridDim.x + blockIdx.x);
+    const uint32_t t = xg_fastdiv_q(g, a.fd_ntx);
+    const uint32_t c = g - t * a.fd_ntx.d;
+    const uint32_t zq = xg_fastdiv_q(t, a.fd_npq);
+    const uint32_t pq = t - zq * a.fd_npq.d;
+    z0 = (int64_t)zq * U;
+    p0 = (int64_t)pq * TY;
+    x0 = (int64_t)c * TXE;
+  };
+  auto issue_load = [&](int64_t i) {
+    const int b = (int)(i % NST);
+    int64_t z0, p0, x0;
+    tile_geom(i, z0, p0, x0);
+    const uint32_t bar = full_u32 + 8u * b;
+    const unsigned fb = BOXW * TY * U * sizeof(T), mb = BOXW * TY * sizeof(T);
+    unsigned bytes = fb + mb;
+    if (a.pre_mode == XG_PRE_FULL) bytes += fb;
+    else if (a.pre_mode == XG_PRE_SHARED) bytes += mb;
+    mbar_expect_tx(bar, bytes);
+    const uint32_t dst = smem_u32(stage0 + (size_t)b * a.stage_bytes);
+    const int cx = (int)x0 - xs;
+    tensor_load_3d(dst, &map_in, cx, (int)p0, (int)z0, bar);
+    if (a.pre_mode == XG_PRE_FULL) tensor_load_3d(dst + a.field_bytes, &map_pre, cx, (int)p0, (int)z0, bar);
+    else if (a.pre_mode == XG_PRE_SHARED)
+      tensor_load_2d(dst + a.field_bytes, &map_pre, cx, a.pre_row_zero ? 0 : (int)p0, bar);
+    tensor_load_2d(dst + a.field_bytes + a.pre_bytes, &map_post, cx, a.post_row_zero ? 0 : (int)p0, bar);
+  };
+  if (tid == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&map_post) : "memory");
+    if (a.pre_mode == XG_PRE_FULL || a.pre_mode == XG_PRE_SHARED)
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&map_pre) : "memory");
+    for (int b = 0; b < NST; ++b) mbar_init(full_u32 + 8u * b, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0)
+    for (int64_t i = 0; i < NST && i < nloc; ++i) issue_load(i);
+
+  const int ty = tid / LR, vx = tid - ty * LR;
+  const int sidx = ty * BOXW + vx * VEC + xs;   // element 0 of this thread's vector inside a box level
+  const int nbi = a.lo ? -1 : VEC;              // where its missing neighbour sits relative to that
+  const bool has_pre = a.pre_mode != XG_PRE_NONE;
+  const T* prep = reinterpret_cast<const T*>(a.pre.ptr);
+
+  for (int64_t i = 0; i < nloc; ++i) {
+    const int b = (int)(i % NST);
+    int64_t z0, p0, x0;
+    tile_geom(i, z0, p0, x0);
+    const int64_t x = x0 + (int64_t)vx * VEC, prow = p0 + ty;
+    const bool act = vx < NVR && x < a.n && prow < a.P;
+    const int nz = (a.Zn - z0 < U) ? (int)(a.Zn - z0) : U;
+    mbar_wait(full_u32 + 8u * b, (uint32_t)((i / NST) & 1));
+    if (act) {
+      const T* fs = reinterpret_cast<const T*>(stage0 + (size_t)b * a.stage_bytes) + sidx;
+      // a row-less shared pre (dx(X)) has its only row at the top of its box
+      const T* ps = reinterpret_cast<const T*>(stage0 + (size_t)b * a.stage_bytes + a.field_bytes) +
+                    ((a.pre_mode == XG_PRE_SHARED && a.pre_row_zero) ? sidx - ty * BOXW : sidx);
+      const T* qs = reinterpret_cast<const T*>(stage0 + (size_t)b * a.stage_bytes + a.field_bytes + a.pre_bytes) + sidx;
+      Pack pm;
+      *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(qs);
+      XgSharedDivisor<T> dv[VEC];
+#pragma unroll
+      for (int k = 0; k < VEC; ++k) dv[k].set(pm.v[k]);
+      Pack pv;
+      T pnb = T(1);
+      if (a.pre_mode == XG_PRE_SHARED) {
+        *reinterpret_cast<V*>(pv.v) = *reinterpret_cast<const V*>(ps);
+        pnb = ps[nbi];
+      }
+      const int64_t row0 = z0 * a.P + prow;
+      const bool at_lo = a.lo && x == 0, at_hi = !a.lo && x + VEC >= a.n;
+      T* op = a.out + row0 * a.n + x;
+      const int64_t zstride = a.P * a.n;
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (u >= nz) break;
+        Pack v;
+        *reinterpret_cast<V*>(v.v) = *reinterpret_cast<const V*>(fs + u * (TY * BOXW));
+        T nb = fs[u * (TY * BOXW) + nbi];
+        if (has_pre) {
+          if (a.pre_mode == XG_PRE_FULL) {
+            *reinterpret_cast<V*>(pv.v) = *reinterpret_cast<const V*>(ps + u * (TY * BOXW));
+            pnb = ps[u * (TY * BOXW) + nbi];
+          } else if (a.pre_mode == XG_PRE_SCALAR) {
+            pnb = __ldg(prep + xg_groups_offset(a.pre.outer, row0 + u * a.P));
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) pv.v[k] = pnb;
+          }
+#pragma unroll
+          for (int k = 0; k < VEC; ++k) v.v[k] = v.v[k] * pv.v[k];
+          nb = nb * pnb;
+        }
+        if (at_lo || at_hi) {
+          // A[row, s] = in * pre straight from global memory: the row's other end (periodic) only
+          const int64_t row = row0 + u * a.P;
+          auto A = [&](int64_t s_) -> T {
+            T val = __ldg(a.in + row * a.n + s_);
+            if (has_pre) val = val * __ldg(prep + xg_groups_offset(a.pre.outer, row) + s_ * a.pre.axis_stride);
+            return val;
+          };
+          const T* halo = at_lo ? a.halo_lo : a.halo_hi;
+          if (halo) nb = __ldg(halo + row);
+          else if (a.bc == XG_BC_FILL) nb = a.fill;
+          else if (a.bc == XG_BC_PERIODIC) nb = A(at_lo ? a.n - 1 : 0);
+          else if (a.bc == XG_BC_EXTEND) nb = at_lo ? v.v[0] : v.v[VEC - 1];
+          else nb = at_lo ? T(2) * v.v[0] - v.v[1] : T(2) * v.v[VEC - 1] - v.v[VEC - 2];
+        }
+        Pack res;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) {
+          if (a.lo) res.v[k] = xg_apply_op<T, OP>(k == 0 ? nb : v.v[k > 0 ? k - 1 : 0], v.v[k]);
+          else res.v[k] = xg_apply_op<T, OP>(v.v[k], k == VEC - 1 ? nb : v.v[k < VEC - 1 ? k + 1 : k]);
+        }
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) res.v[k] = dv[k].div(res.v[k]);
+        xg_st_stream<T, VEC>(op + u * zstride, res);
+      }
+    }
+    __syncthreads();  // every reader of stage b is done: refill it with the tile NST ahead
+    if (tid == 0 && i + NST < nloc) issue_load(i + NST);
+  }
+}
+
+// ---------------------------------------------------------------------------
 // host dispatch
 // ---------------------------------------------------------------------------
 static int env_int(const char* name, int dflt) {
@@ -348,14 +684,21 @@ int launch_strided(StencilArgs<T>& a, cudaStream_t st) {
   a.nseg = xg_ceil_div(a.n_out, J);
   a.nunits = a.outer * a.nseg * a.nwc;
   a.small_units = a.nunits < (1ll << 31);
+  a.fd_nseg = xg_fastdiv_make(a.small_units ? a.nseg : 1);
+  a.fd_nwc = xg_fastdiv_make(a.small_units ? a.nwc : 1);
   static const int tune_sf = env_int("XG_STRIDED_SEGFAST", 0);
   a.seg_fast = tune_sf != 0;
   const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2: grid too large");
+  static const int tune_met = env_int("XG_STRIDED_MET", 0);  // 1: U=2; 2: U=4 at 3 CTAs/SM (80 registers)
   if (!MET && tune_u == 8)
     k_stencil_strided<T, VEC, OP, MET, 8><<<(unsigned)blocks, kThreads, 0, st>>>(a);
   else if (!MET && tune_u == 2)
     k_stencil_strided<T, VEC, OP, MET, 2><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  else if (MET && VEC > 1 && tune_met == 1)
+    k_stencil_strided<T, VEC, OP, MET, 2><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  else if (MET && VEC > 1 && tune_met == 2)
+    k_stencil_strided<T, VEC, OP, MET, 4, 3><<<(unsigned)blocks, kThreads, 0, st>>>(a);
   else
     k_stencil_strided<T, VEC, OP, MET, 4><<<(unsigned)blocks, kThreads, 0, st>>>(a);
   return xg_check_launch("xg_stencil2(strided)");
@@ -368,10 +711,154 @@ int launch_row_vec(StencilArgs<T>& a, cudaStream_t st) {
   a.nwc = xg_ceil_div(nv, 32 * U);
   a.nunits = a.outer * a.nwc;
   a.small_units = a.nunits < (1ll << 31);
+  a.fd_nwc = xg_fastdiv_make(a.small_units ? a.nwc : 1);
   const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil2: grid too large");
   k_stencil_row_vec<T, VEC, OP, MET, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
   return xg_check_launch("xg_stencil2(row_vec)");
+}
+
+// The z-batched kernel applies when the divisor is x-contiguous, 16-byte aligned, and its
+// outermost index group is a broadcast one (the level dim of a (Z, Y, X) field against dx(Y, X)).
+template <typename T, int VEC, int OP>
+int launch_row_zb(const StencilArgs<T>& s, cudaStream_t st, bool* launched) {
+  constexpr int U = 4;
+  *launched = false;
+  static const int enabled = env_int("XG_ROW_ZB", 1);
+  const XgOperand& m = s.post;
+  if (!enabled || !m.ptr || m.axis_stride != 1 || !s.post_axis_vec_ok) return XG_OK;
+  RowZbArgs<T> a;
+  if (m.outer.n == 0) a.Zn = s.outer;  // dx(X): one divisor row for the whole field
+  else if (m.outer.stride[0] == 0) a.Zn = m.outer.size[0];
+  else return XG_OK;
+  if (a.Zn < 2 || s.outer % a.Zn != 0) return XG_OK;
+  a.P = s.outer / a.Zn;
+  a.in = s.in;
+  a.out = s.out;
+  a.n = s.n;
+  a.lo = s.lo;
+  a.bc = s.bc;
+  a.fill = s.fill;
+  a.halo_lo = s.halo_lo;
+  a.halo_hi = s.halo_hi;
+  a.pre = s.pre;
+  a.post = s.post;
+  a.pre_vec = s.pre_axis_vec_ok;
+  a.pre_shared = !s.pre.ptr || s.pre.outer.n == 0 ||
+                 (s.pre.outer.stride[0] == 0 && s.pre.outer.size[0] % a.Zn == 0);
+  a.nwc = xg_ceil_div(s.n / VEC, 32);
+  a.nunits = xg_ceil_div(a.Zn, U) * a.P * a.nwc;
+  a.small_units = a.nunits < (1ll << 31) && a.P < (1ll << 31);
+  a.fd_nwc = xg_fastdiv_make(a.small_units ? a.nwc : 1);
+  a.fd_P = xg_fastdiv_make(a.small_units ? a.P : 1);
+  const int64_t blocks = xg_ceil_div(a.nunits, kWarpsPerBlock);
+  if (blocks > 0x7fffffffLL) return XG_OK;
+  k_stencil_row_zb<T, VEC, OP, U><<<(unsigned)blocks, kThreads, 0, st>>>(a);
+  *launched = true;
+  return xg_check_launch("xg_stencil2(row_zb)");
+}
+
+// Eligibility of the TMA-staged kernel: divisor x-contiguous with a broadcast level group (as for row_zb),
+// rows long enough to fill tiles, and a pre-metric that is absent, laid out like the field, shared like
+// the divisor, or one scalar per row.
+template <typename T, int VEC, int OP>
+int launch_row_tma(const StencilArgs<T>& s, cudaStream_t st, bool* launched) {
+  typedef RowTmaGeo<T> G;
+  static_assert(G::VEC == VEC, "vector width");
+  constexpr int U = 4, BOXW = G::TXE + VEC;
+  *launched = false;
+  static const int enabled = env_int("XG_ROW_TMA", 1);
+  const XgOperand& m = s.post;
+  if (!enabled || !m.ptr || m.axis_stride != 1 || !s.post_axis_vec_ok) return XG_OK;
+  if (s.n < 2 * G::TXE || s.n >= (1ll << 31) || s.outer >= (1ll << 31)) return XG_OK;
+  RowTmaArgs<T> a;
+  int64_t post_rs = 0;
+  if (m.outer.n == 0) { a.Zn = s.outer; a.post_row_zero = 1; }
+  else if (m.outer.n == 1 && m.outer.stride[0] == 0) { a.Zn = m.outer.size[0]; a.post_row_zero = 1; }
+  else if (m.outer.n == 2 && m.outer.stride[0] == 0) { a.Zn = m.outer.size[0]; a.post_row_zero = 0; post_rs = m.outer.stride[1]; }
+  else return XG_OK;
+  if (a.Zn < 2 || s.outer % a.Zn != 0) return XG_OK;
+  a.P = s.outer / a.Zn;
+  if (a.post_row_zero && a.P != 1) return XG_OK;
+  if (!a.post_row_zero && m.outer.size[1] != a.P) return XG_OK;
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (!enc) return XG_OK;
+  a.in = s.in;
+  a.out = s.out;
+  a.n = s.n;
+  a.lo = s.lo;
+  a.bc = s.bc;
+  a.fill = s.fill;
+  a.halo_lo = s.halo_lo;
+  a.halo_hi = s.halo_hi;
+  a.pre = s.pre;
+  a.pre_row_zero = 0;
+  int64_t pre_rs = 0;
+  const XgOperand& q = s.pre;
+  if (!q.ptr) a.pre_mode = XG_PRE_NONE;
+  else if (q.axis_stride == 0) a.pre_mode = XG_PRE_SCALAR;
+  else if (q.axis_stride != 1 || !s.pre_axis_vec_ok) return XG_OK;
+  else if (q.outer.n == 1 && q.outer.stride[0] == s.n && q.outer.size[0] == s.outer) a.pre_mode = XG_PRE_FULL;
+  else if (q.outer.n == 0 || (q.outer.n == 1 && q.outer.stride[0] == 0)) { a.pre_mode = XG_PRE_SHARED; a.pre_row_zero = 1; }
+  else if (q.outer.n == 2 && q.outer.stride[0] == 0 && q.outer.size[0] == a.Zn && q.outer.size[1] == a.P) {
+    a.pre_mode = XG_PRE_SHARED;
+    pre_rs = q.outer.stride[1];
+  } else return XG_OK;
+  if (s.outer == 1 && a.pre_mode == XG_PRE_FULL) return XG_OK;
+
+  auto up128 = [](size_t v) { return (unsigned)((v + 127) / 128 * 128); };
+  a.field_bytes = up128((size_t)BOXW * G::TY * U * sizeof(T));
+  const unsigned metric_bytes = up128((size_t)BOXW * G::TY * sizeof(T));
+  a.pre_bytes = a.pre_mode == XG_PRE_FULL ? a.field_bytes : (a.pre_mode == XG_PRE_SHARED ? metric_bytes : 0);
+  a.post_bytes = metric_bytes;
+  a.stage_bytes = a.field_bytes + a.pre_bytes + a.post_bytes;
+  int dev = 0, sms = 148, smem_max = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  static const int tune_nst = env_int("XG_ROW_TMA_NST", 0);
+  const int per_cta = smem_max / 2 - 2048;  // two CTAs per SM
+  int nst = (per_cta - 128) / (int)a.stage_bytes;
+  if (nst > 6) nst = 6;
+  if (tune_nst > 0 && tune_nst < nst) nst = tune_nst;
+  if (nst < 2) return XG_OK;
+  a.nst = nst;
+  a.ntx = xg_ceil_div(s.n, G::TXE);
+  a.npq = xg_ceil_div(a.P, G::TY);
+  a.ntiles = xg_ceil_div(a.Zn, U) * a.npq * a.ntx;
+  if (a.ntiles >= (1ll << 31)) return XG_OK;
+  a.fd_ntx = xg_fastdiv_make(a.ntx);
+  a.fd_npq = xg_fastdiv_make(a.npq);
+
+  CUtensorMap map_in, map_pre, map_post;
+  const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)a.P, (cuuint64_t)a.Zn};
+  const cuuint64_t s3[2] = {(cuuint64_t)s.n * sizeof(T), (cuuint64_t)a.P * s.n * sizeof(T)};
+  const cuuint32_t b3[3] = {(cuuint32_t)BOXW, (cuuint32_t)G::TY, (cuuint32_t)U};
+  if (xg_encode_map<T>(enc, &map_in, s.in, 3, d3, s3, b3)) return XG_OK;
+  auto encode_rows = [&](CUtensorMap* map, const void* ptr, bool row_zero, int64_t rs) -> int {
+    // a row-less operand is a (n, 1) map read at row 0; its box still spans TY rows (the rest is zero fill)
+    const cuuint64_t d2[2] = {(cuuint64_t)s.n, (cuuint64_t)(row_zero ? 1 : a.P)};
+    const cuuint64_t s2[1] = {(cuuint64_t)(row_zero ? s.n : rs) * sizeof(T)};
+    const cuuint32_t b2[2] = {(cuuint32_t)BOXW, (cuuint32_t)G::TY};
+    return xg_encode_map<T>(enc, map, static_cast<const T*>(ptr), 2, d2, s2, b2);
+  };
+  if (encode_rows(&map_post, m.ptr, a.post_row_zero != 0, post_rs)) return XG_OK;
+  map_pre = map_post;
+  if (a.pre_mode == XG_PRE_FULL) {
+    if (xg_encode_map<T>(enc, &map_pre, static_cast<const T*>(q.ptr), 3, d3, s3, b3)) return XG_OK;
+  } else if (a.pre_mode == XG_PRE_SHARED) {
+    if (encode_rows(&map_pre, q.ptr, a.pre_row_zero != 0, pre_rs)) return XG_OK;
+  }
+  const size_t smem = 128 + (size_t)nst * a.stage_bytes;
+  if (cudaFuncSetAttribute(k_stencil_row_tma<T, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return XG_OK;
+  }
+  int64_t grid = 2ll * sms;
+  if (grid > a.ntiles) grid = a.ntiles;
+  k_stencil_row_tma<T, OP><<<(unsigned)grid, kThreads, smem, st>>>(map_in, map_pre, map_post, a);
+  *launched = true;
+  return xg_check_launch("xg_stencil2(row_tma)");
 }
 
 template <typename T, int OP, bool MET>
@@ -395,8 +882,16 @@ int dispatch_layout(StencilArgs<T>& a, cudaStream_t st) {
     a.post.vec_ok = 0;
     return launch_strided<T, 1, OP, MET>(a, st);
   }
-  if (ptr_ok && a.n_out == a.n && a.n % VEC == 0 && a.n / VEC >= 32)
+  if (ptr_ok && a.n_out == a.n && a.n % VEC == 0 && a.n / VEC >= 32) {
+    if constexpr (MET) {
+      bool launched = false;
+      int rc = launch_row_tma<T, VEC, OP>(a, st, &launched);
+      if (rc || launched) return rc;
+      rc = launch_row_zb<T, VEC, OP>(a, st, &launched);
+      if (rc || launched) return rc;
+    }
     return launch_row_vec<T, VEC, OP, MET>(a, st);
+  }
   return launch_row_scalar<T, OP, MET>(a, st);
 }
 

@@ -38,6 +38,7 @@ struct PairArgs {
   int J;
   int64_t nseg, nwc, nunits;
   bool small_units, small_inner;
+  XgFastDiv fd_nseg, fd_nwc, fd_nx;  // multiply-high forms (valid with the small_* flags)
 };
 
 template <typename T>
@@ -78,13 +79,13 @@ __global__ void __launch_bounds__(kThreads, 3) k_stencil_pair(const PairArgs<T> 
   if (unit >= p.nunits) return;  // warp-uniform
   const int lane = threadIdx.x & 31;
   int64_t wc, t, seg, o;
-  xg_divmod(unit, p.nwc, p.small_units, t, wc);
-  xg_divmod(t, p.nseg, p.small_units, o, seg);
+  xg_divmod(unit, p.nwc, p.fd_nwc, p.small_units, t, wc);
+  xg_divmod(t, p.nseg, p.fd_nseg, p.small_units, o, seg);
   int64_t i = (wc * 32 + lane) * VEC;
   const bool valid = i < p.inner;
   if (!valid) i = p.inner - VEC;  // spare lanes shadow the last vector: all 32 lanes stay in the shuffles
   int64_t row_i, x0;
-  xg_divmod(i, p.nx, p.small_inner, row_i, x0);
+  xg_divmod(i, p.nx, p.fd_nx, p.small_inner, row_i, x0);
   const bool row_first = x0 == 0, row_last = x0 + VEC == p.nx;
 
   const int64_t j0 = seg * p.J;
@@ -224,6 +225,9 @@ int launch_pair(PairArgs<T>& p, cudaStream_t st) {
   p.nunits = p.outer * p.nseg * p.nwc;
   p.small_units = p.nunits < (1ll << 31);
   p.small_inner = p.inner < (1ll << 31);
+  p.fd_nseg = xg_fastdiv_make(p.small_units ? p.nseg : 1);
+  p.fd_nwc = xg_fastdiv_make(p.small_units ? p.nwc : 1);
+  p.fd_nx = xg_fastdiv_make(p.small_inner ? p.nx : 1);
   const int64_t blocks = xg_ceil_div(p.nunits, kWarpsPerBlock);
   if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_stencil_pair: grid too large");
   const bool met = p.ma.ptr || p.mb.ptr || p.post.ptr;

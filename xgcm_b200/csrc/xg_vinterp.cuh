@@ -109,24 +109,11 @@ __device__ __forceinline__ double interp_value(double x, double xj, double xj1, 
   return res;
 }
 
-// Correctly rounded a / b from r = RN(1/b) with five fp64 operations instead of the ~30 of the
-// generic division (Markstein's FMA-based sequence: q0 = RN(a r) is within 2 ulp, the first
-// correction makes it faithful, and for a faithful q with r within half an ulp of 1/b the second
-// correction q + RN(a - b q) r rounds to exactly RN(a / b)).  Only valid when no intermediate
-// can leave the normal range; the caller guards the exponents of a and b and falls back to `/`.
+// correctly rounded division from a shared reciprocal: see xg_common.cuh
 __device__ __forceinline__ double div_with_recip(double a, double b, double r) {
-  const double q0 = a * r;
-  const double e0 = fma(-b, q0, a);
-  const double q1 = fma(e0, r, q0);
-  const double e1 = fma(-b, q1, a);
-  return fma(e1, r, q1);
+  return xg_div_with_recip(a, b, r);
 }
-__device__ __forceinline__ bool exponent_safe(double v) {
-  // |v| in [2^-400, 2^400]: biased exponent in [623, 1423]; false for 0, subnormals, NaN, inf
-  const unsigned e = ((unsigned)__double2hiint(v) >> 20) & 0x7ffu;
-  return (e - 623u) <= 800u;
-}
-
+__device__ __forceinline__ bool exponent_safe(double v) { return xg_exponent_safe(v); }
 
 // TMA-staged shared-theta kernel (xg_vinterp_tma.cu).  Returns 1 when the launch was made, 0 when the
 // layout does not qualify (caller falls back to k_vinterp_shared), < 0 on error.

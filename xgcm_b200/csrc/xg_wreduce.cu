@@ -27,6 +27,7 @@ struct ReduceArgs {
   XgOperand w;
   int64_t nvec_inner;
   bool small_index;
+  XgFastDiv fd_nvi;  // multiply-high form of nvec_inner (valid with small_index)
 };
 
 template <typename T, int VEC, bool HASW, int U>
@@ -35,7 +36,7 @@ __global__ void __launch_bounds__(kThreads) k_reduce_strided(const ReduceArgs<T>
   const int64_t g = (int64_t)blockIdx.x * kThreads + threadIdx.x;
   if (g >= a.outer * a.nvec_inner) return;
   int64_t o, iv;
-  xg_divmod(g, a.nvec_inner, a.small_index, o, iv);
+  xg_divmod(g, a.nvec_inner, a.fd_nvi, a.small_index, o, iv);
   const int64_t i = iv * VEC;
   const T* ibase = a.in + o * a.n * a.inner + i;
   XgOperandView<T, VEC> w_v;
@@ -138,6 +139,7 @@ int reduce_launch(ReduceArgs<T>& a, cudaStream_t st) {
     a.nvec_inner = vec_ok ? a.inner / VEC : a.inner;
     if (!vec_ok) a.w.vec_ok = 0;
     a.small_index = a.outer * a.nvec_inner < (1ll << 31);
+    a.fd_nvi = xg_fastdiv_make(a.small_index ? a.nvec_inner : 1);
     const int64_t blocks = xg_ceil_div(a.outer * a.nvec_inner, kThreads);
     if (blocks > 0x7fffffffLL) return xg_fail(XG_EINVAL, "xg_wreduce: grid too large");
     if (vec_ok)
@@ -172,6 +174,7 @@ int wreduce_typed(const void* in, const void* weight, const int64_t* w_strides, 
   a.skipna = skipna ? 1 : 0;
   a.nvec_inner = 0;
   a.small_index = false;
+  a.fd_nvi = xg_fastdiv_make(1);
   rc = xg_make_operand(weight, w_strides, ndim, shape, axis, VEC, sizeof(T), &a.w,
                        "xg_wreduce(weight)");
   if (rc) return rc;
