@@ -141,7 +141,7 @@ def test_metric_shared_divisor_rows_bit_exact(dtype, shape):
 def test_shared_divisor_division_is_ieee_on_arbitrary_bit_patterns(dtype, X, kernel):
     """x / b through the shared reciprocal against numpy's division on raw bit patterns: zeros,
     subnormals, infinities, NaNs, quotients that overflow, underflow or land in the subnormal range.
-    `max` against an -inf fill hands the field value itself to the divide, so numerator and divisor
+    The numerator handed to the divide is the field value itself (see below), so numerator and divisor
     are both fully controlled."""
     from xgcm_b200 import ops
 
@@ -165,13 +165,14 @@ def test_shared_divisor_division_is_ieee_on_arbitrary_bit_patterns(dtype, X, ker
     a[:, :, 64:128] = (1.0 + rng.random((Z, Y, 64))).astype(dtype)
     b[:, :, 64:128] = (1.0 + rng.random((1, Y, 64))).astype(dtype)
     dev = torch.device("cuda:0")
-    # max(A[x-1], A[x]) on a field whose odd columns repeat the even ones is the field itself there
+    # diff = A[x] - A[x-1] on a field whose even columns are +0 is the field itself at the odd ones
+    # (x - (+0) == x for every x, -0 and NaN included)
     a2 = a.copy()
-    a2[:, :, 1::2] = a2[:, :, 0::2]
+    a2[:, :, 0::2] = 0.0
     with np.errstate(all="ignore"):
         want = (a2 / b)[:, :, 1::2]
     m = torch.from_numpy(b).to(dev)
-    got = ops.stencil2(torch.from_numpy(a2).to(dev), 2, "max", 1, 0, "fill", -np.inf, post=m).cpu().numpy()
+    got = ops.stencil2(torch.from_numpy(a2).to(dev), 2, "diff", 1, 0, "fill", 0.0, post=m).cpu().numpy()
     assert _capi_last_launch() == f"xg_stencil2({kernel})"
     got = got[:, :, 1::2]
     np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
@@ -183,6 +184,45 @@ def _capi_last_launch():
     from xgcm_b200 import _capi
 
     return _capi.last_launch()
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(5, 9, 452), (3, 6, 904), (2, 3, 5, 676), (7, 2, 1000), (2, 1, 448)])
+def test_metric_tile_kernel_second_to_last_axis(dtype, shape):
+    """Metric-fused stencils along the dim next to x with level-shared metrics (derivative('Y') on a
+    (Z, Y, X) field): the TMA-staged tile kernel against the reference's separate passes, every shift
+    (n_out = n - 1, n, n + 1), boundary incl. extrapolate, metric layout and operator; ragged tiles."""
+    from xgcm_b200 import _capi
+
+    rng = np.random.default_rng(60)
+    a = _field(shape, dtype, seed=61, nan_frac=0.01)
+    nd = len(shape)
+    axis = nd - 2
+
+    def metric(dims, n_axis):
+        shp = [shape[d] if d in dims else 1 for d in range(nd)]
+        if axis in dims:
+            shp[axis] = n_axis
+        return (0.5 + rng.random(shp)).astype(dtype)
+
+    for (lo, hi) in SHIFTS:
+        n_out = shape[axis] + lo + hi - 1
+        if n_out <= 0:
+            continue
+        posts = [metric((nd - 2, nd - 1), n_out), metric((nd - 1,), n_out), metric((nd - 2,), n_out), metric((0,), n_out)]
+        pres = [None, metric(range(nd), shape[axis]), metric((nd - 2, nd - 1), shape[axis]), metric((0,), shape[axis]),
+                metric((nd - 1,), shape[axis]), metric((nd - 2,), shape[axis])]
+        for (bc, fill) in BCS + [("extrapolate", 0.0)]:
+            for post in posts:
+                for pre in pres:
+                    _check(a, axis, "diff", lo, hi, bc, fill, pre, post)
+                _check(a, axis, "interp", lo, hi, bc, fill, pres[2], post)
+            _check(a, axis, "max", lo, hi, bc, fill, pres[1], posts[0])
+            if shape[-1] >= (448 if dtype == np.float32 else 480):  # two tiles per row
+                assert _capi.last_launch() == "xg_stencil2(tile_tma)"
+            _check(a, axis, "min", lo, hi, bc, fill, None, posts[0])
+            # a full (Z, Y, X) divisor with a shared pre-metric still stages the pre tile once per level batch
+            _check(a, axis, "diff", lo, hi, bc, fill, pres[2], metric(range(nd), n_out))
 
 
 def test_metric_4d_outer_broadcast():

@@ -52,6 +52,47 @@ def test_pair_matches_chain(dtype, shape):
                 np.testing.assert_array_equal(got, want)
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(5, 9, 452), (3, 6, 904), (2, 3, 5, 676), (6, 2, 1000)])
+def test_pair_tile_kernel_matches_chain(dtype, shape):
+    """Rows long enough for the TMA-staged tile kernel (axis b next to x, metrics shared between levels):
+    every boundary / shift / sign combination and every metric layout it stages (2-D shared, full 3-D,
+    x-only, per-row and per-level scalars), ragged tiles in x, rows and levels."""
+    from xgcm_b200 import _capi, ops
+
+    rng = np.random.default_rng(33)
+    a = rng.standard_normal(shape).astype(dtype)
+    b = rng.standard_normal(shape).astype(dtype)
+    a[rng.random(shape) < 0.01] = np.nan
+    nd = len(shape)
+    axis_b = nd - 2
+
+    def metric(dims):
+        return (0.5 + rng.random([shape[d] if d in dims else 1 for d in range(nd)])).astype(dtype)
+
+    m2, mfull, mz, mx, my = metric((nd - 2, nd - 1)), metric(range(nd)), metric((0,)), metric((nd - 1,)), metric((nd - 2,))
+    bcs = [("periodic", 0.0), ("fill", 1.5), ("extend", 0.0)]
+    for (op_a, op_b), (lo_a, lo_b), ((bc_a, fa), (bc_b, fb)), sub in itertools.product(
+            [("diff", "diff"), ("interp", "diff"), ("min", "max")], [(1, 0), (0, 1), (1, 1), (0, 0)],
+            [(bcs[0], bcs[1]), (bcs[1], bcs[2]), (bcs[2], bcs[0])], [0, 1, 2]):
+        hi_a, hi_b = 1 - lo_a, 1 - lo_b
+        want = oracle.stencil_pair(op_a, a, nd - 1, lo_a, hi_a, bc_a, fa, m2, op_b, b, axis_b, lo_b, hi_b, bc_b, fb, m2, sub, m2)
+        got = ops.stencil_pair(_t(a), _t(b), (op_a, lo_a, hi_a, bc_a, fa), (axis_b, op_b, lo_b, hi_b, bc_b, fb), sub,
+                               pre_a=_t(m2), pre_b=_t(m2), post=_t(m2)).cpu().numpy()
+        if shape[-1] >= (448 if dtype == np.float32 else 480):  # two tiles per row
+            assert _capi.last_launch() == "xg_stencil_pair(tile_tma)"
+        np.testing.assert_array_equal(got, want, err_msg=f"{op_a}/{op_b} lo=({lo_a},{lo_b}) {bc_a}/{bc_b} sub={sub}")
+    combos = [(mfull, m2, m2), (mz, mfull, m2), (None, m2, None), (m2, None, m2), (mx, my, m2), (my, mx, mx), (None, None, m2),
+              (m2, m2, mz), (m2, m2, my), (mfull, mfull, mfull), (m2, mfull, mfull)]
+    for pre_a, pre_b, post in combos:
+        for (lo_a, lo_b), sub, (bc, f) in itertools.product([(0, 1), (1, 0)], (0, 1), bcs):
+            want = oracle.stencil_pair("diff", a, nd - 1, lo_a, 1 - lo_a, bc, f, pre_a, "interp", b, axis_b, lo_b, 1 - lo_b,
+                                       bc, f, pre_b, sub, post)
+            got = ops.stencil_pair(_t(a), _t(b), ("diff", lo_a, 1 - lo_a, bc, f), (axis_b, "interp", lo_b, 1 - lo_b, bc, f),
+                                   sub, pre_a=_t(pre_a), pre_b=_t(pre_b), post=_t(post)).cpu().numpy()
+            np.testing.assert_array_equal(got, want)
+
+
 def test_pair_argument_validation():
     from xgcm_b200 import ops
 

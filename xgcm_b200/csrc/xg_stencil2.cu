@@ -22,6 +22,7 @@
 #include <stdlib.h>
 
 #include "xg_common.cuh"
+#include "xg_stencil_tile.cuh"
 #include "xg_tma.cuh"
 
 namespace {
@@ -479,10 +480,13 @@ __global__ void __launch_bounds__(kThreads) k_stencil_row_zb(const RowZbArgs<T> 
 // Same decomposition as k_stencil_row_zb (U levels share one divisor row), but the operands arrive by
 // bulk-async tensor loads: a tile is U levels x TY rows x TXE cells (+ one 16-byte halo vector), one
 // cp.async.bulk.tensor box per operand, all boxes of a tile completing on one mbarrier.  A persistent
-// CTA keeps a ring of NST tiles in flight (shared memory, not registers, holds the bytes in flight:
-// ~100 KB per CTA instead of the ~20 KB the register-staged kernels reach), threads read 16-byte
-// vectors and the neighbour element from the tile, and results leave as streaming 16-byte stores.
-// TXE is a multiple of 128 bytes so stores of neighbouring tiles never share a sector.
+// CTA = 8 consumer warps + 1 producer warp around a ring of NST tiles (full / empty mbarriers, no
+// block-wide barrier in the loop): shared memory, not registers, holds the bytes in flight.  Threads
+// read 16-byte vectors from the tile, the neighbour element comes from a warp shuffle (the warp's
+// edge lane reads it from the tile), results leave as streaming 16-byte stores.  TXE is a multiple of
+// 128 bytes so stores of neighbouring tiles never share a sector.
+// Tile order: row blocks of ~128 rows outermost, then the level batches, so the divisor rows of a
+// block (~2 MB) are re-read from L2, not from DRAM, by each of the Zn / U level batches.
 template <typename T>
 struct RowTmaGeo;
 template <>
@@ -494,13 +498,14 @@ struct RowTmaGeo<double> {
   static constexpr int VEC = 2, TXE = 240, TY = 2;  // 120 vectors per row, 128 thread slots
 };
 enum { XG_PRE_NONE = 0, XG_PRE_FULL = 1, XG_PRE_SHARED = 2, XG_PRE_SCALAR = 3 };
+constexpr int kTmaConsumers = kThreads;  // + one producer warp
 
 template <typename T>
 struct RowTmaArgs {
   const T* in;
   T* out;
   int64_t n, P, Zn;
-  int lo, bc;
+  int bc;
   T fill;
   const T* halo_lo;
   const T* halo_hi;
@@ -508,151 +513,190 @@ struct RowTmaArgs {
   int pre_mode;       // XG_PRE_*
   int pre_row_zero;   // shared pre without a row dim (dx(X)): always row 0 of its map
   int post_row_zero;
-  int64_t ntx, npq, ntiles;
-  XgFastDiv fd_ntx, fd_npq;
+  int64_t npq;        // tile rows
+  int64_t ntiles;     // virtual tiles: nrb * nzq * rbq * ntx (tile rows past npq are skipped)
+  XgFastDiv fd_ntx, fd_rbq, fd_nzq;
   int nst;                    // tiles in flight
+  int l2_hints;               // evict-first fields, evict-last metric tiles
   unsigned field_bytes, pre_bytes, post_bytes, stage_bytes;  // box sizes rounded up to 128
 };
 
-template <typename T, int OP>
-__global__ void __launch_bounds__(kThreads, 2)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// PRE: XG_PRE_NONE, XG_PRE_FULL, or XG_PRE_SHARED standing for both runtime modes shared / scalar
+template <typename T, int OP, int PRE, bool LO, int U>
+__global__ void __launch_bounds__(kTmaConsumers + 32, 3)
     k_stencil_row_tma(const __grid_constant__ CUtensorMap map_in, const __grid_constant__ CUtensorMap map_pre,
                       const __grid_constant__ CUtensorMap map_post, const RowTmaArgs<T> a) {
   typedef RowTmaGeo<T> G;
-  constexpr int VEC = G::VEC, TXE = G::TXE, TY = G::TY, U = 4;
-  constexpr int BOXW = TXE + VEC, LR = kThreads / TY, NVR = TXE / VEC;
+  constexpr int VEC = G::VEC, TXE = G::TXE, TY = G::TY;
+  constexpr int BOXW = TXE + VEC, LR = kTmaConsumers / TY, NVR = TXE / VEC, LS = TY * BOXW;
+  constexpr int XS = LO ? VEC : 0;  // the box starts one vector left of the tile when the lower neighbour is needed
+  constexpr int NBI = LO ? -1 : VEC;
   typedef XgPack<T, VEC> Pack;
   typedef typename XgVec<T, VEC>::type V;
+  const unsigned FULL = 0xffffffffu;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   const int tid = threadIdx.x;
-  const uint32_t full_u32 = smem_u32(smem_raw);  // NST mbarriers, then the stages at +128
-  unsigned char* stage0 = smem_raw + 128;
   const int NST = a.nst;
+  const uint32_t full_u32 = smem_u32(smem_raw);  // full[NST], empty[NST]; the stages start at +128
+  const uint32_t empty_u32 = full_u32 + 8u * NST;
+  unsigned char* stage0 = smem_raw + 128;
   const int64_t nloc = (a.ntiles > blockIdx.x) ? (a.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-  const int xs = a.lo ? VEC : 0;  // the box starts one vector left of the tile when the lower neighbour is needed
 
-  auto tile_geom = [&](int64_t i, int64_t& z0, int64_t& p0, int64_t& x0) {
+  // virtual tile -> (level batch, tile row, x tile); false for the padding rows of the last row block
+  auto tile_geom = [&](int64_t i, int& z0, int& p0, int& x0) -> bool {
     const uint32_t g = (uint32_t)(i * gridDim.x + blockIdx.x);
     const uint32_t t = xg_fastdiv_q(g, a.fd_ntx);
     const uint32_t c = g - t * a.fd_ntx.d;
-    const uint32_t zq = xg_fastdiv_q(t, a.fd_npq);
-    const uint32_t pq = t - zq * a.fd_npq.d;
-    z0 = (int64_t)zq * U;
-    p0 = (int64_t)pq * TY;
-    x0 = (int64_t)c * TXE;
+    const uint32_t t2 = xg_fastdiv_q(t, a.fd_rbq);
+    const uint32_t pql = t - t2 * a.fd_rbq.d;
+    const uint32_t rb = xg_fastdiv_q(t2, a.fd_nzq);
+    const uint32_t zq = t2 - rb * a.fd_nzq.d;
+    const uint32_t pq = rb * a.fd_rbq.d + pql;
+    z0 = (int)(zq * U);
+    p0 = (int)(pq * TY);
+    x0 = (int)(c * TXE);
+    return pq < (uint32_t)a.npq;
   };
-  auto issue_load = [&](int64_t i) {
-    const int b = (int)(i % NST);
-    int64_t z0, p0, x0;
-    tile_geom(i, z0, p0, x0);
-    const uint32_t bar = full_u32 + 8u * b;
-    const unsigned fb = BOXW * TY * U * sizeof(T), mb = BOXW * TY * sizeof(T);
-    unsigned bytes = fb + mb;
-    if (a.pre_mode == XG_PRE_FULL) bytes += fb;
-    else if (a.pre_mode == XG_PRE_SHARED) bytes += mb;
-    mbar_expect_tx(bar, bytes);
-    const uint32_t dst = smem_u32(stage0 + (size_t)b * a.stage_bytes);
-    const int cx = (int)x0 - xs;
-    tensor_load_3d(dst, &map_in, cx, (int)p0, (int)z0, bar);
-    if (a.pre_mode == XG_PRE_FULL) tensor_load_3d(dst + a.field_bytes, &map_pre, cx, (int)p0, (int)z0, bar);
-    else if (a.pre_mode == XG_PRE_SHARED)
-      tensor_load_2d(dst + a.field_bytes, &map_pre, cx, a.pre_row_zero ? 0 : (int)p0, bar);
-    tensor_load_2d(dst + a.field_bytes + a.pre_bytes, &map_post, cx, a.post_row_zero ? 0 : (int)p0, bar);
-  };
+
   if (tid == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_in) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&map_post) : "memory");
-    if (a.pre_mode == XG_PRE_FULL || a.pre_mode == XG_PRE_SHARED)
+    if (PRE != XG_PRE_NONE && a.pre_mode != XG_PRE_SCALAR)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&map_pre) : "memory");
-    for (int b = 0; b < NST; ++b) mbar_init(full_u32 + 8u * b, 1);
+    for (int b = 0; b < NST; ++b) {
+      mbar_init(full_u32 + 8u * b, 1);
+      mbar_init(empty_u32 + 8u * b, kTmaConsumers / 32);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
-  if (tid == 0)
-    for (int64_t i = 0; i < NST && i < nloc; ++i) issue_load(i);
 
-  const int ty = tid / LR, vx = tid - ty * LR;
-  const int sidx = ty * BOXW + vx * VEC + xs;   // element 0 of this thread's vector inside a box level
-  const int nbi = a.lo ? -1 : VEC;              // where its missing neighbour sits relative to that
-  const bool has_pre = a.pre_mode != XG_PRE_NONE;
-  const T* prep = reinterpret_cast<const T*>(a.pre.ptr);
-
-  for (int64_t i = 0; i < nloc; ++i) {
-    const int b = (int)(i % NST);
-    int64_t z0, p0, x0;
-    tile_geom(i, z0, p0, x0);
-    const int64_t x = x0 + (int64_t)vx * VEC, prow = p0 + ty;
-    const bool act = vx < NVR && x < a.n && prow < a.P;
-    const int nz = (a.Zn - z0 < U) ? (int)(a.Zn - z0) : U;
-    mbar_wait(full_u32 + 8u * b, (uint32_t)((i / NST) & 1));
-    if (act) {
-      const T* fs = reinterpret_cast<const T*>(stage0 + (size_t)b * a.stage_bytes) + sidx;
-      // a row-less shared pre (dx(X)) has its only row at the top of its box
-      const T* ps = reinterpret_cast<const T*>(stage0 + (size_t)b * a.stage_bytes + a.field_bytes) +
-                    ((a.pre_mode == XG_PRE_SHARED && a.pre_row_zero) ? sidx - ty * BOXW : sidx);
-      const T* qs = reinterpret_cast<const T*>(stage0 + (size_t)b * a.stage_bytes + a.field_bytes + a.pre_bytes) + sidx;
-      Pack pm;
-      *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(qs);
-      XgSharedDivisor<T> dv[VEC];
-#pragma unroll
-      for (int k = 0; k < VEC; ++k) dv[k].set(pm.v[k]);
-      Pack pv;
-      T pnb = T(1);
-      if (a.pre_mode == XG_PRE_SHARED) {
-        *reinterpret_cast<V*>(pv.v) = *reinterpret_cast<const V*>(ps);
-        pnb = ps[nbi];
-      }
-      const int64_t row0 = z0 * a.P + prow;
-      const bool at_lo = a.lo && x == 0, at_hi = !a.lo && x + VEC >= a.n;
-      T* op = a.out + row0 * a.n + x;
-      const int64_t zstride = a.P * a.n;
-#pragma unroll
-      for (int u = 0; u < U; ++u) {
-        if (u >= nz) break;
-        Pack v;
-        *reinterpret_cast<V*>(v.v) = *reinterpret_cast<const V*>(fs + u * (TY * BOXW));
-        T nb = fs[u * (TY * BOXW) + nbi];
-        if (has_pre) {
-          if (a.pre_mode == XG_PRE_FULL) {
-            *reinterpret_cast<V*>(pv.v) = *reinterpret_cast<const V*>(ps + u * (TY * BOXW));
-            pnb = ps[u * (TY * BOXW) + nbi];
-          } else if (a.pre_mode == XG_PRE_SCALAR) {
-            pnb = __ldg(prep + xg_groups_offset(a.pre.outer, row0 + u * a.P));
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) pv.v[k] = pnb;
-          }
-#pragma unroll
-          for (int k = 0; k < VEC; ++k) v.v[k] = v.v[k] * pv.v[k];
-          nb = nb * pnb;
+  if (tid >= kTmaConsumers) {
+    // ---- producer warp: one lane keeps the ring full
+    if (tid == kTmaConsumers) {
+      const unsigned fb = BOXW * TY * U * sizeof(T), mb = BOXW * TY * sizeof(T);
+      const bool pre_box = PRE == XG_PRE_FULL || (PRE == XG_PRE_SHARED && a.pre_mode == XG_PRE_SHARED);
+      const unsigned bytes = fb + mb + (PRE == XG_PRE_FULL ? fb : (pre_box ? mb : 0));
+      const uint64_t once = l2_policy_evict_first(), keep = l2_policy_evict_last();
+      int64_t k = 0;
+      for (int64_t i = 0; i < nloc; ++i) {
+        int z0, p0, x0;
+        if (!tile_geom(i, z0, p0, x0)) continue;
+        const int b = (int)(k % NST);
+        if (k >= NST) mbar_wait(empty_u32 + 8u * b, (uint32_t)(((k / NST) - 1) & 1));
+        const uint32_t bar = full_u32 + 8u * b;
+        mbar_expect_tx(bar, bytes);
+        const uint32_t dst = smem_u32(stage0 + (size_t)b * a.stage_bytes);
+        const int cx = x0 - XS;
+        if (a.l2_hints) {
+          tensor_load_3d_hint(dst, &map_in, cx, p0, z0, bar, once);
+          if (PRE == XG_PRE_FULL) tensor_load_3d_hint(dst + a.field_bytes, &map_pre, cx, p0, z0, bar, once);
+          else if (pre_box) tensor_load_2d_hint(dst + a.field_bytes, &map_pre, cx, a.pre_row_zero ? 0 : p0, bar, keep);
+          tensor_load_2d_hint(dst + a.field_bytes + a.pre_bytes, &map_post, cx, a.post_row_zero ? 0 : p0, bar, keep);
+        } else {
+          tensor_load_3d(dst, &map_in, cx, p0, z0, bar);
+          if (PRE == XG_PRE_FULL) tensor_load_3d(dst + a.field_bytes, &map_pre, cx, p0, z0, bar);
+          else if (pre_box) tensor_load_2d(dst + a.field_bytes, &map_pre, cx, a.pre_row_zero ? 0 : p0, bar);
+          tensor_load_2d(dst + a.field_bytes + a.pre_bytes, &map_post, cx, a.post_row_zero ? 0 : p0, bar);
         }
-        if (at_lo || at_hi) {
-          // A[row, s] = in * pre straight from global memory: the row's other end (periodic) only
-          const int64_t row = row0 + u * a.P;
-          auto A = [&](int64_t s_) -> T {
-            T val = __ldg(a.in + row * a.n + s_);
-            if (has_pre) val = val * __ldg(prep + xg_groups_offset(a.pre.outer, row) + s_ * a.pre.axis_stride);
-            return val;
-          };
-          const T* halo = at_lo ? a.halo_lo : a.halo_hi;
-          if (halo) nb = __ldg(halo + row);
-          else if (a.bc == XG_BC_FILL) nb = a.fill;
-          else if (a.bc == XG_BC_PERIODIC) nb = A(at_lo ? a.n - 1 : 0);
-          else if (a.bc == XG_BC_EXTEND) nb = at_lo ? v.v[0] : v.v[VEC - 1];
-          else nb = at_lo ? T(2) * v.v[0] - v.v[1] : T(2) * v.v[VEC - 1] - v.v[VEC - 2];
-        }
-        Pack res;
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) {
-          if (a.lo) res.v[k] = xg_apply_op<T, OP>(k == 0 ? nb : v.v[k > 0 ? k - 1 : 0], v.v[k]);
-          else res.v[k] = xg_apply_op<T, OP>(v.v[k], k == VEC - 1 ? nb : v.v[k < VEC - 1 ? k + 1 : k]);
-        }
-#pragma unroll
-        for (int k = 0; k < VEC; ++k) res.v[k] = dv[k].div(res.v[k]);
-        xg_st_stream<T, VEC>(op + u * zstride, res);
+        ++k;
       }
     }
-    __syncthreads();  // every reader of stage b is done: refill it with the tile NST ahead
-    if (tid == 0 && i + NST < nloc) issue_load(i + NST);
+    return;
+  }
+
+  // ---- consumers
+  const int lane = tid & 31;
+  const int ty = tid / LR, vx = tid - ty * LR;
+  const int vxs = vx < NVR ? vx : NVR - 1;  // spare slots shadow the last vector: valid addresses, in the shuffles, no store
+  const int sidx = ty * BOXW + vxs * VEC + XS;  // element 0 of this thread's vector inside a box level
+  const int pidx = (PRE == XG_PRE_SHARED && a.pre_row_zero) ? sidx - ty * BOXW : sidx;  // a row-less pre sits in row 0
+  const bool edge_lane = LO ? (lane == 0) : (lane == 31 || vx >= NVR - 1);  // no neighbouring lane holds the element
+  const bool pre_scalar = PRE == XG_PRE_SHARED && a.pre_mode == XG_PRE_SCALAR;
+  const T* prep = reinterpret_cast<const T*>(a.pre.ptr);
+  const int64_t zstride = a.P * a.n;
+
+  int64_t k = 0;
+  for (int64_t i = 0; i < nloc; ++i) {
+    int z0, p0, x0;
+    if (!tile_geom(i, z0, p0, x0)) continue;
+    const int b = (int)(k % NST);
+    const int x = x0 + vxs * VEC, prow = p0 + ty;
+    const bool act = vx < NVR && x < a.n && prow < a.P;
+    const int nz = (a.Zn - z0 < U) ? (int)(a.Zn - z0) : U;
+    const unsigned char* st = stage0 + (size_t)b * a.stage_bytes;
+    const T* fs = reinterpret_cast<const T*>(st) + sidx;
+    const T* ps = reinterpret_cast<const T*>(st + a.field_bytes) + pidx;
+    const T* qs = reinterpret_cast<const T*>(st + a.field_bytes + a.pre_bytes) + sidx;
+    mbar_wait(full_u32 + 8u * b, (uint32_t)((k / NST) & 1));
+    Pack pm;
+    *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(qs);
+    XgSharedDivisor<T> dv[VEC];
+#pragma unroll
+    for (int kk = 0; kk < VEC; ++kk) dv[kk].set(pm.v[kk]);
+    Pack pv;
+    T pnb = T(1);
+    if (PRE == XG_PRE_SHARED && !pre_scalar) {
+      *reinterpret_cast<V*>(pv.v) = *reinterpret_cast<const V*>(ps);
+      if (edge_lane) pnb = ps[NBI];
+    }
+    const int64_t row0 = (int64_t)z0 * a.P + prow;
+    const bool at_edge = LO ? (x == 0) : (x + VEC >= a.n);
+    T* op = a.out + row0 * a.n + x;
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (u >= nz) break;  // block-uniform
+      Pack v;
+      *reinterpret_cast<V*>(v.v) = *reinterpret_cast<const V*>(fs + u * LS);
+      T enb = T(0);
+      if (edge_lane) enb = fs[u * LS + NBI];
+      if (PRE != XG_PRE_NONE) {
+        if (PRE == XG_PRE_FULL) {
+          *reinterpret_cast<V*>(pv.v) = *reinterpret_cast<const V*>(ps + u * LS);
+          if (edge_lane) pnb = ps[u * LS + NBI];
+        } else if (pre_scalar) {
+          pnb = __ldg(prep + xg_groups_offset(a.pre.outer, row0 + u * a.P));
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) pv.v[kk] = pnb;
+        }
+#pragma unroll
+        for (int kk = 0; kk < VEC; ++kk) v.v[kk] = v.v[kk] * pv.v[kk];
+        enb = enb * pnb;
+      }
+      T nb = LO ? __shfl_up_sync(FULL, v.v[VEC - 1], 1) : __shfl_down_sync(FULL, v.v[0], 1);
+      if (edge_lane) nb = enb;
+      if (at_edge) {
+        // A[row, s] = in * pre straight from global memory: the row's other end (periodic) only
+        const int64_t row = row0 + u * a.P;
+        auto A = [&](int64_t s_) -> T {
+          T val = __ldg(a.in + row * a.n + s_);
+          if (PRE != XG_PRE_NONE) val = val * __ldg(prep + xg_groups_offset(a.pre.outer, row) + s_ * a.pre.axis_stride);
+          return val;
+        };
+        const T* halo = LO ? a.halo_lo : a.halo_hi;
+        if (halo) nb = __ldg(halo + row);
+        else if (a.bc == XG_BC_FILL) nb = a.fill;
+        else if (a.bc == XG_BC_PERIODIC) nb = A(LO ? a.n - 1 : 0);
+        else if (a.bc == XG_BC_EXTEND) nb = LO ? v.v[0] : v.v[VEC - 1];
+        else nb = LO ? T(2) * v.v[0] - v.v[1] : T(2) * v.v[VEC - 1] - v.v[VEC - 2];
+      }
+      Pack res;
+#pragma unroll
+      for (int kk = 0; kk < VEC; ++kk) {
+        if (LO) res.v[kk] = xg_apply_op<T, OP>(kk == 0 ? nb : v.v[kk > 0 ? kk - 1 : 0], v.v[kk]);
+        else res.v[kk] = xg_apply_op<T, OP>(v.v[kk], kk == VEC - 1 ? nb : v.v[kk < VEC - 1 ? kk + 1 : kk]);
+      }
+#pragma unroll
+      for (int kk = 0; kk < VEC; ++kk) res.v[kk] = dv[kk].div(res.v[kk]);
+      if (act) xg_st_stream<T, VEC>(op + u * zstride, res);
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(empty_u32 + 8u * b);  // this warp is done with stage b
+    ++k;
   }
 }
 
@@ -759,106 +803,147 @@ int launch_row_zb(const StencilArgs<T>& s, cudaStream_t st, bool* launched) {
 }
 
 // Eligibility of the TMA-staged kernel: divisor x-contiguous with a broadcast level group (as for row_zb),
-// rows long enough to fill tiles, and a pre-metric that is absent, laid out like the field, shared like
-// the divisor, or one scalar per row.
+// rows long enough to fill tiles, diff / interp, and a pre-metric that is absent, laid out like the field,
+// shared like the divisor, or one scalar per row.
+template <typename T, int OP, int PRE, bool LO, int U>
+int launch_row_tma_kernel(const CUtensorMap& map_in, const CUtensorMap& map_pre, const CUtensorMap& map_post,
+                          const RowTmaArgs<T>& a, int64_t grid, size_t smem, cudaStream_t st) {
+  auto kern = k_stencil_row_tma<T, OP, PRE, LO, U>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  kern<<<(unsigned)grid, kTmaConsumers + 32, smem, st>>>(map_in, map_pre, map_post, a);
+  return 1;
+}
+
 template <typename T, int VEC, int OP>
 int launch_row_tma(const StencilArgs<T>& s, cudaStream_t st, bool* launched) {
   typedef RowTmaGeo<T> G;
   static_assert(G::VEC == VEC, "vector width");
-  constexpr int U = 4, BOXW = G::TXE + VEC;
+  constexpr int BOXW = G::TXE + VEC;
   *launched = false;
-  static const int enabled = env_int("XG_ROW_TMA", 1);
-  const XgOperand& m = s.post;
-  if (!enabled || !m.ptr || m.axis_stride != 1 || !s.post_axis_vec_ok) return XG_OK;
-  if (s.n < 2 * G::TXE || s.n >= (1ll << 31) || s.outer >= (1ll << 31)) return XG_OK;
-  RowTmaArgs<T> a;
-  int64_t post_rs = 0;
-  if (m.outer.n == 0) { a.Zn = s.outer; a.post_row_zero = 1; }
-  else if (m.outer.n == 1 && m.outer.stride[0] == 0) { a.Zn = m.outer.size[0]; a.post_row_zero = 1; }
-  else if (m.outer.n == 2 && m.outer.stride[0] == 0) { a.Zn = m.outer.size[0]; a.post_row_zero = 0; post_rs = m.outer.stride[1]; }
-  else return XG_OK;
-  if (a.Zn < 2 || s.outer % a.Zn != 0) return XG_OK;
-  a.P = s.outer / a.Zn;
-  if (a.post_row_zero && a.P != 1) return XG_OK;
-  if (!a.post_row_zero && m.outer.size[1] != a.P) return XG_OK;
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (!enc) return XG_OK;
-  a.in = s.in;
-  a.out = s.out;
-  a.n = s.n;
-  a.lo = s.lo;
-  a.bc = s.bc;
-  a.fill = s.fill;
-  a.halo_lo = s.halo_lo;
-  a.halo_hi = s.halo_hi;
-  a.pre = s.pre;
-  a.pre_row_zero = 0;
-  int64_t pre_rs = 0;
-  const XgOperand& q = s.pre;
-  if (!q.ptr) a.pre_mode = XG_PRE_NONE;
-  else if (q.axis_stride == 0) a.pre_mode = XG_PRE_SCALAR;
-  else if (q.axis_stride != 1 || !s.pre_axis_vec_ok) return XG_OK;
-  else if (q.outer.n == 1 && q.outer.stride[0] == s.n && q.outer.size[0] == s.outer) a.pre_mode = XG_PRE_FULL;
-  else if (q.outer.n == 0 || (q.outer.n == 1 && q.outer.stride[0] == 0)) { a.pre_mode = XG_PRE_SHARED; a.pre_row_zero = 1; }
-  else if (q.outer.n == 2 && q.outer.stride[0] == 0 && q.outer.size[0] == a.Zn && q.outer.size[1] == a.P) {
-    a.pre_mode = XG_PRE_SHARED;
-    pre_rs = q.outer.stride[1];
-  } else return XG_OK;
-  if (s.outer == 1 && a.pre_mode == XG_PRE_FULL) return XG_OK;
-
-  auto up128 = [](size_t v) { return (unsigned)((v + 127) / 128 * 128); };
-  a.field_bytes = up128((size_t)BOXW * G::TY * U * sizeof(T));
-  const unsigned metric_bytes = up128((size_t)BOXW * G::TY * sizeof(T));
-  a.pre_bytes = a.pre_mode == XG_PRE_FULL ? a.field_bytes : (a.pre_mode == XG_PRE_SHARED ? metric_bytes : 0);
-  a.post_bytes = metric_bytes;
-  a.stage_bytes = a.field_bytes + a.pre_bytes + a.post_bytes;
-  int dev = 0, sms = 148, smem_max = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  static const int tune_nst = env_int("XG_ROW_TMA_NST", 0);
-  const int per_cta = smem_max / 2 - 2048;  // two CTAs per SM
-  int nst = (per_cta - 128) / (int)a.stage_bytes;
-  if (nst > 6) nst = 6;
-  if (tune_nst > 0 && tune_nst < nst) nst = tune_nst;
-  if (nst < 2) return XG_OK;
-  a.nst = nst;
-  a.ntx = xg_ceil_div(s.n, G::TXE);
-  a.npq = xg_ceil_div(a.P, G::TY);
-  a.ntiles = xg_ceil_div(a.Zn, U) * a.npq * a.ntx;
-  if (a.ntiles >= (1ll << 31)) return XG_OK;
-  a.fd_ntx = xg_fastdiv_make(a.ntx);
-  a.fd_npq = xg_fastdiv_make(a.npq);
-
-  CUtensorMap map_in, map_pre, map_post;
-  const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)a.P, (cuuint64_t)a.Zn};
-  const cuuint64_t s3[2] = {(cuuint64_t)s.n * sizeof(T), (cuuint64_t)a.P * s.n * sizeof(T)};
-  const cuuint32_t b3[3] = {(cuuint32_t)BOXW, (cuuint32_t)G::TY, (cuuint32_t)U};
-  if (xg_encode_map<T>(enc, &map_in, s.in, 3, d3, s3, b3)) return XG_OK;
-  auto encode_rows = [&](CUtensorMap* map, const void* ptr, bool row_zero, int64_t rs) -> int {
-    // a row-less operand is a (n, 1) map read at row 0; its box still spans TY rows (the rest is zero fill)
-    const cuuint64_t d2[2] = {(cuuint64_t)s.n, (cuuint64_t)(row_zero ? 1 : a.P)};
-    const cuuint64_t s2[1] = {(cuuint64_t)(row_zero ? s.n : rs) * sizeof(T)};
-    const cuuint32_t b2[2] = {(cuuint32_t)BOXW, (cuuint32_t)G::TY};
-    return xg_encode_map<T>(enc, map, static_cast<const T*>(ptr), 2, d2, s2, b2);
-  };
-  if (encode_rows(&map_post, m.ptr, a.post_row_zero != 0, post_rs)) return XG_OK;
-  map_pre = map_post;
-  if (a.pre_mode == XG_PRE_FULL) {
-    if (xg_encode_map<T>(enc, &map_pre, static_cast<const T*>(q.ptr), 3, d3, s3, b3)) return XG_OK;
-  } else if (a.pre_mode == XG_PRE_SHARED) {
-    if (encode_rows(&map_pre, q.ptr, a.pre_row_zero != 0, pre_rs)) return XG_OK;
-  }
-  const size_t smem = 128 + (size_t)nst * a.stage_bytes;
-  if (cudaFuncSetAttribute(k_stencil_row_tma<T, OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
-    cudaGetLastError();
+  if constexpr (OP != XG_OP_DIFF && OP != XG_OP_INTERP) {
     return XG_OK;
+  } else {
+    static const int enabled = env_int("XG_ROW_TMA", 1);
+    constexpr int U = 4;  // 8 levels per tile measured no faster (profiles/r2_row_tma_sweep.txt)
+    const XgOperand& m = s.post;
+    if (!enabled || !m.ptr || m.axis_stride != 1 || !s.post_axis_vec_ok) return XG_OK;
+    if (s.n < 2 * G::TXE || s.n >= (1ll << 31) || s.outer >= (1ll << 31)) return XG_OK;
+    RowTmaArgs<T> a;
+    int64_t post_rs = 0;
+    if (m.outer.n == 0) { a.Zn = s.outer; a.post_row_zero = 1; }
+    else if (m.outer.n == 1 && m.outer.stride[0] == 0) { a.Zn = m.outer.size[0]; a.post_row_zero = 1; }
+    else if (m.outer.n == 2 && m.outer.stride[0] == 0) { a.Zn = m.outer.size[0]; a.post_row_zero = 0; post_rs = m.outer.stride[1]; }
+    else return XG_OK;
+    if (a.Zn < 2 || s.outer % a.Zn != 0) return XG_OK;
+    a.P = s.outer / a.Zn;
+    if (a.post_row_zero && a.P != 1) return XG_OK;
+    if (!a.post_row_zero && m.outer.size[1] != a.P) return XG_OK;
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return XG_OK;
+    a.in = s.in;
+    a.out = s.out;
+    a.n = s.n;
+    a.bc = s.bc;
+    a.fill = s.fill;
+    a.halo_lo = s.halo_lo;
+    a.halo_hi = s.halo_hi;
+    a.pre = s.pre;
+    a.pre_row_zero = 0;
+    int64_t pre_rs = 0;
+    const XgOperand& q = s.pre;
+    if (!q.ptr) a.pre_mode = XG_PRE_NONE;
+    else if (q.axis_stride == 0) a.pre_mode = XG_PRE_SCALAR;
+    else if (q.axis_stride != 1 || !s.pre_axis_vec_ok) return XG_OK;
+    else if (q.outer.n == 1 && q.outer.stride[0] == s.n && q.outer.size[0] == s.outer) a.pre_mode = XG_PRE_FULL;
+    else if (q.outer.n == 0 || (q.outer.n == 1 && q.outer.stride[0] == 0)) { a.pre_mode = XG_PRE_SHARED; a.pre_row_zero = 1; }
+    else if (q.outer.n == 2 && q.outer.stride[0] == 0 && q.outer.size[0] == a.Zn && q.outer.size[1] == a.P) {
+      a.pre_mode = XG_PRE_SHARED;
+      pre_rs = q.outer.stride[1];
+    } else return XG_OK;
+
+    auto up128 = [](size_t v) { return (unsigned)((v + 127) / 128 * 128); };
+    a.field_bytes = up128((size_t)BOXW * G::TY * U * sizeof(T));
+    const unsigned metric_bytes = up128((size_t)BOXW * G::TY * sizeof(T));
+    a.pre_bytes = a.pre_mode == XG_PRE_FULL ? a.field_bytes : (a.pre_mode == XG_PRE_SHARED ? metric_bytes : 0);
+    a.post_bytes = metric_bytes;
+    a.stage_bytes = a.field_bytes + a.pre_bytes + a.post_bytes;
+    int dev = 0, sms = 148, smem_sm = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    // Tuning (profiles/r2_row_tma_sweep.txt): two tiles per CTA; three CTAs per SM while the tiles in flight
+    // stay below ~135 KB per SM, else two (more bytes in flight measured slower, as did L2 eviction hints).
+    static const int tune_nst = env_int("XG_ROW_TMA_NST", 0);
+    static const int tune_ctas = env_int("XG_ROW_TMA_CTAS", 0);
+    int ctas = (3 * 2 * (int)a.stage_bytes <= 135 * 1024) ? 3 : 2;
+    if (tune_ctas >= 1 && tune_ctas <= 4) ctas = tune_ctas;
+    int per_cta = smem_sm / ctas - 1024;  // the driver reserves 1 KB per resident CTA
+    if (per_cta > smem_max) per_cta = smem_max;
+    const int fit = (per_cta - 128) / (int)a.stage_bytes;
+    int nst = fit < 2 ? fit : 2;
+    if (tune_nst > 0) nst = tune_nst < fit ? tune_nst : fit;
+    if (nst < 1) return XG_OK;
+    a.nst = nst;
+    static const int tune_hint = env_int("XG_ROW_TMA_HINT", 0);
+    a.l2_hints = tune_hint;
+    // row blocks: ~128 rows each, evened out
+    const int64_t ntx = xg_ceil_div(s.n, G::TXE);
+    a.npq = xg_ceil_div(a.P, G::TY);
+    static const int tune_rb = env_int("XG_ROW_TMA_RB", 128);
+    const int64_t rbq_target = xg_ceil_div(tune_rb > 0 ? tune_rb : 128, G::TY);
+    const int64_t nrb = xg_ceil_div(a.npq, rbq_target);
+    const int64_t rbq = xg_ceil_div(a.npq, nrb);
+    const int64_t nzq = xg_ceil_div(a.Zn, U);
+    a.ntiles = nrb * nzq * rbq * ntx;
+    if (a.ntiles >= (1ll << 31)) return XG_OK;
+    a.fd_ntx = xg_fastdiv_make(ntx);
+    a.fd_rbq = xg_fastdiv_make(rbq);
+    a.fd_nzq = xg_fastdiv_make(nzq);
+
+    CUtensorMap map_in, map_pre, map_post;
+    const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)a.P, (cuuint64_t)a.Zn};
+    const cuuint64_t s3[2] = {(cuuint64_t)s.n * sizeof(T), (cuuint64_t)a.P * s.n * sizeof(T)};
+    const cuuint32_t b3[3] = {(cuuint32_t)BOXW, (cuuint32_t)G::TY, (cuuint32_t)U};
+    if (xg_encode_map<T>(enc, &map_in, s.in, 3, d3, s3, b3)) return XG_OK;
+    auto encode_rows = [&](CUtensorMap* map, const void* ptr, bool row_zero, int64_t rs) -> int {
+      // a row-less operand is a (n, 1) map read at row 0; its box still spans TY rows (the rest is zero fill)
+      const cuuint64_t d2[2] = {(cuuint64_t)s.n, (cuuint64_t)(row_zero ? 1 : a.P)};
+      const cuuint64_t s2[1] = {(cuuint64_t)(row_zero ? s.n : rs) * sizeof(T)};
+      const cuuint32_t b2[2] = {(cuuint32_t)BOXW, (cuuint32_t)G::TY};
+      return xg_encode_map<T>(enc, map, static_cast<const T*>(ptr), 2, d2, s2, b2);
+    };
+    if (encode_rows(&map_post, m.ptr, a.post_row_zero != 0, post_rs)) return XG_OK;
+    map_pre = map_post;
+    if (a.pre_mode == XG_PRE_FULL) {
+      if (xg_encode_map<T>(enc, &map_pre, static_cast<const T*>(q.ptr), 3, d3, s3, b3)) return XG_OK;
+    } else if (a.pre_mode == XG_PRE_SHARED) {
+      if (encode_rows(&map_pre, q.ptr, a.pre_row_zero != 0, pre_rs)) return XG_OK;
+    }
+    const size_t smem = 128 + (size_t)nst * a.stage_bytes;
+    int64_t grid = (int64_t)ctas * sms;
+    if (grid > a.ntiles) grid = a.ntiles;
+    const int pre_t = a.pre_mode == XG_PRE_NONE ? XG_PRE_NONE : (a.pre_mode == XG_PRE_FULL ? XG_PRE_FULL : XG_PRE_SHARED);
+    int ok = 0;
+#define XG_TMA_GO(PRE_, LO_, U_) ok = launch_row_tma_kernel<T, OP, PRE_, LO_, U_>(map_in, map_pre, map_post, a, grid, smem, st)
+#define XG_TMA_LO(PRE_, U_) \
+  if (s.lo) XG_TMA_GO(PRE_, true, U_); \
+  else XG_TMA_GO(PRE_, false, U_)
+#define XG_TMA_PRE(U_)                                   \
+  if (pre_t == XG_PRE_NONE) { XG_TMA_LO(XG_PRE_NONE, U_); }  \
+  else if (pre_t == XG_PRE_FULL) { XG_TMA_LO(XG_PRE_FULL, U_); } \
+  else { XG_TMA_LO(XG_PRE_SHARED, U_); }
+    XG_TMA_PRE(4)
+#undef XG_TMA_PRE
+#undef XG_TMA_LO
+#undef XG_TMA_GO
+    if (!ok) return XG_OK;
+    *launched = true;
+    return xg_check_launch("xg_stencil2(row_tma)");
   }
-  int64_t grid = 2ll * sms;
-  if (grid > a.ntiles) grid = a.ntiles;
-  k_stencil_row_tma<T, OP><<<(unsigned)grid, kThreads, smem, st>>>(map_in, map_pre, map_post, a);
-  *launched = true;
-  return xg_check_launch("xg_stencil2(row_tma)");
 }
 
 template <typename T, int OP, bool MET>
@@ -877,6 +962,37 @@ int dispatch_layout(StencilArgs<T>& a, cudaStream_t st) {
                       (!a.halo_lo || (uintptr_t)a.halo_lo % 16 == 0) &&
                       (!a.halo_hi || (uintptr_t)a.halo_hi % 16 == 0);
   if (a.inner > 1) {
+    if constexpr (MET) {
+      // metrics shared between the outer index (levels): the TMA-staged tile kernel, rows = the operated axis
+      if (ptr_ok && a.inner % VEC == 0) {
+        XgTileSpec<T> ts;
+        ts.Zn = a.outer;
+        ts.Pb = a.n;
+        ts.Po = a.n_out;
+        ts.n = a.inner;
+        ts.a = nullptr;
+        ts.op_a = ts.lo_a = ts.bc_a = 0;
+        ts.fill_a = T(0);
+        ts.b = a.in;
+        ts.op_b = OP;
+        ts.lo_b = a.lo;
+        ts.hi_b = a.hi;
+        ts.bc_b = a.bc;
+        ts.fill_b = a.fill;
+        ts.halo_lo = a.halo_lo;
+        ts.halo_hi = a.halo_hi;
+        ts.subtract = 0;
+        ts.ma.ptr = nullptr;
+        ts.ma.sz = ts.ma.sp = ts.ma.sx = 0;
+        ts.out = a.out;
+        if (xg_tile_operand_from<T>(a.pre, a.outer, a.inner, &ts.mb) &&
+            xg_tile_operand_from<T>(a.post, a.outer, a.inner, &ts.post)) {
+          bool launched = false;
+          const int rc = xg_tile_stencil<T>(ts, st, &launched, "xg_stencil2(tile_tma)");
+          if (rc || launched) return rc;
+        }
+      }
+    }
     if (ptr_ok && a.inner % VEC == 0) return launch_strided<T, VEC, OP, MET>(a, st);
     a.pre.vec_ok = 0;
     a.post.vec_ok = 0;

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "xg_common.cuh"
+#include "xg_stencil_tile.cuh"
 
 namespace {
 
@@ -288,6 +289,33 @@ int pair_typed(const void* a, const void* b, void* out, int ndim, const int64_t*
   if (rc) return rc;
   rc = xg_make_operand(post, post_strides, ndim, shape, axis_b, vec, sizeof(T), &p.post, "xg_stencil_pair(post)");
   if (rc) return rc;
+  if (vec_ok && p.inner == p.nx) {
+    // axis b is the dim next to x and (typically) the metrics are shared between levels: the TMA-staged tile kernel
+    XgTileSpec<T> ts;
+    ts.Zn = p.outer;
+    ts.Pb = ts.Po = p.nb;
+    ts.n = p.nx;
+    ts.a = p.a;
+    ts.op_a = p.op_a;
+    ts.lo_a = p.lo_a;
+    ts.bc_a = p.bc_a;
+    ts.fill_a = p.fill_a;
+    ts.b = p.b;
+    ts.op_b = p.op_b;
+    ts.lo_b = p.lo_b;
+    ts.hi_b = 1 - p.lo_b;
+    ts.bc_b = p.bc_b;
+    ts.fill_b = p.fill_b;
+    ts.halo_lo = ts.halo_hi = nullptr;
+    ts.subtract = p.subtract;
+    ts.out = p.out;
+    if (xg_tile_operand_from<T>(p.ma, p.outer, p.inner, &ts.ma) && xg_tile_operand_from<T>(p.mb, p.outer, p.inner, &ts.mb) &&
+        xg_tile_operand_from<T>(p.post, p.outer, p.inner, &ts.post)) {
+      bool launched = false;
+      rc = xg_tile_stencil<T>(ts, st, &launched, "xg_stencil_pair(tile_tma)");
+      if (rc || launched) return rc;
+    }
+  }
   if (vec_ok) return launch_pair<T, VEC>(p, st);
   return launch_pair<T, 1>(p, st);
 }
