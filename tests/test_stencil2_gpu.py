@@ -218,11 +218,48 @@ def test_metric_tile_kernel_second_to_last_axis(dtype, shape):
                     _check(a, axis, "diff", lo, hi, bc, fill, pre, post)
                 _check(a, axis, "interp", lo, hi, bc, fill, pres[2], post)
             _check(a, axis, "max", lo, hi, bc, fill, pres[1], posts[0])
-            if shape[-1] >= (448 if dtype == np.float32 else 480):  # two tiles per row
+            if shape[-1] >= (448 if dtype == np.float32 else 480) and shape[axis] > 1:  # two tiles per row
                 assert _capi.last_launch() == "xg_stencil2(tile_tma)"
             _check(a, axis, "min", lo, hi, bc, fill, None, posts[0])
             # a full (Z, Y, X) divisor with a shared pre-metric still stages the pre tile once per level batch
             _check(a, axis, "diff", lo, hi, bc, fill, pres[2], metric(range(nd), n_out))
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape,axis", [((5, 6, 904), 2), ((5, 6, 904), 1), ((4, 3, 256), 2), ((3, 4, 130), 1), ((6, 5, 904), 0)])
+def test_halo_planes_with_metrics(dtype, shape, axis):
+    """Explicit halo planes (the neighbour GPU's boundary plane in the sharded path, xgcm_b200.h) replace the
+    boundary rule on their side — through every kernel a metric-fused call can reach (row / tile TMA kernels,
+    the level-batched row kernel, the strided kernel): out = OP(concat(halo_lo, A x pre, halo_hi)) / post."""
+    from xgcm_b200 import ops
+
+    rng = np.random.default_rng(70)
+    a = _field(shape, dtype, seed=71)
+    nd = len(shape)
+    plane = [s for d, s in enumerate(shape) if d != axis]
+    hl, hh = rng.random(plane).astype(dtype), rng.random(plane).astype(dtype)
+    dev = torch.device("cuda:0")
+
+    def metric(dims, n_axis):
+        shp = [shape[d] if d in dims else 1 for d in range(nd)]
+        if axis in dims:
+            shp[axis] = n_axis
+        return (0.5 + rng.random(shp)).astype(dtype)
+
+    for (lo, hi), (bc, fill), op in itertools.product(((1, 0), (0, 1), (1, 1)), (("extend", 0.0), ("fill", 2.5)), ("diff", "interp")):
+        n_out = shape[axis] + lo + hi - 1
+        for pre_dims, post_dims in (((1, 2), (1, 2)), (None, (1, 2)), (range(nd), (1, 2)), ((0,), (2,))):
+            pre = None if pre_dims is None else metric(pre_dims, shape[axis])
+            post = metric(post_dims, n_out)
+            ap = a if pre is None else a * pre
+            parts = ([np.expand_dims(hl, axis)] if lo else []) + [ap] + ([np.expand_dims(hh, axis)] if hi else [])
+            padded = np.concatenate(parts, axis=axis)
+            want = (np.moveaxis(oracle.KERNELS[op](np.moveaxis(padded, axis, -1)), -1, axis) / post).astype(dtype)
+            got = ops.stencil2(torch.from_numpy(a).to(dev), axis, op, lo, hi, bc, fill,
+                               pre=None if pre is None else torch.from_numpy(pre).to(dev), post=torch.from_numpy(post).to(dev),
+                               halo_lo=torch.from_numpy(hl).to(dev) if lo else None,
+                               halo_hi=torch.from_numpy(hh).to(dev) if hi else None).cpu().numpy()
+            np.testing.assert_array_equal(got, want, err_msg=f"{op} lo={lo} hi={hi} {bc} pre={pre_dims} post={post_dims}")
 
 
 def test_metric_4d_outer_broadcast():

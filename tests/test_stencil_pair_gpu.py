@@ -79,7 +79,7 @@ def test_pair_tile_kernel_matches_chain(dtype, shape):
         want = oracle.stencil_pair(op_a, a, nd - 1, lo_a, hi_a, bc_a, fa, m2, op_b, b, axis_b, lo_b, hi_b, bc_b, fb, m2, sub, m2)
         got = ops.stencil_pair(_t(a), _t(b), (op_a, lo_a, hi_a, bc_a, fa), (axis_b, op_b, lo_b, hi_b, bc_b, fb), sub,
                                pre_a=_t(m2), pre_b=_t(m2), post=_t(m2)).cpu().numpy()
-        if shape[-1] >= (448 if dtype == np.float32 else 480):  # two tiles per row
+        if shape[-1] >= (448 if dtype == np.float32 else 480) and op_a != "min":  # two tiles per row; diff / interp
             assert _capi.last_launch() == "xg_stencil_pair(tile_tma)"
         np.testing.assert_array_equal(got, want, err_msg=f"{op_a}/{op_b} lo=({lo_a},{lo_b}) {bc_a}/{bc_b} sub={sub}")
     combos = [(mfull, m2, m2), (mz, mfull, m2), (None, m2, None), (m2, None, m2), (mx, my, m2), (my, mx, mx), (None, None, m2),

@@ -70,18 +70,10 @@ __device__ __forceinline__ void mbar_arrive_tile(uint32_t bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 
-template <typename T>
-__device__ __forceinline__ T tile_op(int op, T lo_v, T hi_v) {
-  switch (op) {
-    case XG_OP_DIFF: return xg_apply_op<T, XG_OP_DIFF>(lo_v, hi_v);
-    case XG_OP_INTERP: return xg_apply_op<T, XG_OP_INTERP>(lo_v, hi_v);
-    case XG_OP_MIN: return xg_apply_op<T, XG_OP_MIN>(lo_v, hi_v);
-    default: return xg_apply_op<T, XG_OP_MAX>(lo_v, hi_v);
-  }
-}
-
-template <typename T, bool HAS_A>
-__global__ void __launch_bounds__(kConsumers + 32, 3)
+// OPA / OPB: the operators, compile-time (a runtime switch per cell doubled the instruction count)
+// LEVELM: some metric changes per level (3-D boxes or per-level scalars); false compiles those paths out
+template <typename T, bool HAS_A, int OPA, int OPB, bool LEVELM>
+__global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's stages only fit twice per SM anyway
     k_tile_stencil(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_b,
                    const __grid_constant__ CUtensorMap map_ma, const __grid_constant__ CUtensorMap map_mb,
                    const __grid_constant__ CUtensorMap map_post, const TileArgs<T> a) {
@@ -160,14 +152,22 @@ __global__ void __launch_bounds__(kConsumers + 32, 3)
   const int lane = tid & 31;
   const int ty = tid / LR, vx = tid - ty * LR;
   const int vxs = vx < NVR ? vx : NVR - 1;  // spare slots shadow the last vector: valid addresses, in the shuffles, no store
+  const int lo_a = HAS_A ? s.lo_a : 0, lo_b = s.lo_b, sub = s.subtract;
+  const int ma_mode = HAS_A ? a.ma_mode : M_NONE, mb_mode = a.mb_mode, post_mode = a.post_mode;
   const int ia = ty * BOXW + vxs * VEC + xs;
-  const int ima = (a.ma_mode == M_SHARED && a.ma_row0) ? vxs * VEC + xs : ia;
+  const int ima = (ma_mode == M_SHARED && a.ma_row0) ? vxs * VEC + xs : ia;
   const int ib = ty * TXE + vxs * VEC;
-  const int imb = (a.mb_mode == M_SHARED && a.mb_row0) ? vxs * VEC : ib;
-  const int imb1 = (a.mb_mode == M_SHARED && a.mb_row0) ? imb : imb + TXE;
-  const int iq = (a.post_mode == M_SHARED && a.post_row0) ? vxs * VEC : ib;
-  const int nbi = s.lo_a ? -1 : VEC;
-  const bool edge_lane = s.lo_a ? (lane == 0) : (lane == 31 || vx >= NVR - 1);
+  const int imb = (mb_mode == M_SHARED && a.mb_row0) ? vxs * VEC : ib;
+  const int imb1 = (mb_mode == M_SHARED && a.mb_row0) ? imb : imb + TXE;
+  const int iq = (post_mode == M_SHARED && a.post_row0) ? vxs * VEC : ib;
+  const int nbi = lo_a ? -1 : VEC;
+  const bool edge_lane = lo_a ? (lane == 0) : (lane == 31 || vx >= NVR - 1);
+  // metrics that change per level need work inside the level loop; everything else is set up once per tile and
+  // an absent metric is a multiplication by one (exact, NaN / zero preserving) instead of a branch per cell
+  const bool ma_level = LEVELM && (ma_mode == M_FULL || ma_mode == M_SCALAR);
+  const bool mb_level = LEVELM && (mb_mode == M_FULL || mb_mode == M_SCALAR);
+  const bool post_level = LEVELM && (post_mode == M_FULL || post_mode == M_SCALAR);
+  const int64_t Pb = s.Pb, Po = s.Po, n = s.n, ostride = s.Po * s.n;
 
   int64_t k = 0;
   for (int64_t i = 0; i < nloc; ++i) {
@@ -175,38 +175,43 @@ __global__ void __launch_bounds__(kConsumers + 32, 3)
     if (!tile_geom(i, z0, p0, x0)) continue;
     const int b = (int)(k % NST);
     const int x = x0 + vxs * VEC, prow = p0 + ty;
-    const bool act = vx < NVR && x < s.n && prow < s.Po;
+    const int prc = prow < Po ? prow : (int)Po - 1;  // clamped row for the scalar metric loads of spare rows
+    const bool act = vx < NVR && x < n && prow < Po;
     const int nz = (s.Zn - z0 < U) ? (int)(s.Zn - z0) : U;
     const unsigned char* st = stage0 + (size_t)b * a.stage_bytes;
-    const T* As = reinterpret_cast<const T*>(st);
-    const T* Bs = reinterpret_cast<const T*>(st + a.off_b);
+    const T* As = reinterpret_cast<const T*>(st) + ia;
+    const T* Bs = reinterpret_cast<const T*>(st + a.off_b) + ib;
     const T* MAs = reinterpret_cast<const T*>(st + a.off_ma);
     const T* MBs = reinterpret_cast<const T*>(st + a.off_mb);
     const T* Qs = reinterpret_cast<const T*>(st + a.off_post);
-    const int s0 = prow - s.lo_b, s1 = s0 + 1;  // source rows of B for this output row
-    const bool low_b = s0 < 0, high_b = s1 >= s.Pb;
-    const bool at_edge = HAS_A && (s.lo_a ? (x == 0) : (x + VEC >= s.n));
+    const int s0 = prow - lo_b, s1 = s0 + 1;  // source rows of B for this output row
+    const bool low_b = s0 < 0, high_b = s1 >= Pb;
+    const bool at_edge = HAS_A && (lo_a ? (x == 0) : (x + VEC >= n));
     mbar_wait(full_u32 + 8u * b, (uint32_t)((k / NST) & 1));
 
     XgSharedDivisor<T> dv[VEC];
-    if (a.post_mode == M_SHARED) {
+    Pack ma_v, mb0, mb1;
+    T ma_nb = T(1);
+#pragma unroll
+    for (int kk = 0; kk < VEC; ++kk) {
+      dv[kk].set(T(1));
+      ma_v.v[kk] = mb0.v[kk] = mb1.v[kk] = T(1);
+    }
+    if (post_mode == M_SHARED) {
       Pack pm;
       *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(Qs + iq);
 #pragma unroll
       for (int kk = 0; kk < VEC; ++kk) dv[kk].set(pm.v[kk]);
     }
-    Pack ma_v, mb0, mb1;
-    T ma_nb = T(1);
-    if (HAS_A && a.ma_mode == M_SHARED) {
+    if (ma_mode == M_SHARED) {
       *reinterpret_cast<V*>(ma_v.v) = *reinterpret_cast<const V*>(MAs + ima);
       if (edge_lane) ma_nb = MAs[ima + nbi];
     }
-    if (a.mb_mode == M_SHARED) {
+    if (mb_mode == M_SHARED) {
       *reinterpret_cast<V*>(mb0.v) = *reinterpret_cast<const V*>(MBs + imb);
       *reinterpret_cast<V*>(mb1.v) = *reinterpret_cast<const V*>(MBs + imb1);
     }
-    T* op = s.out + ((int64_t)z0 * s.Po + prow) * s.n + x;
-    const int64_t ostride = s.Po * s.n;
+    T* op = s.out + ((int64_t)z0 * Po + prow) * n + x;
 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -214,32 +219,32 @@ __global__ void __launch_bounds__(kConsumers + 32, 3)
       const int64_t z = z0 + u;
       // ---- row term: B x mb at source rows s0, s1
       Pack b0, b1;
-      *reinterpret_cast<V*>(b0.v) = *reinterpret_cast<const V*>(Bs + u * LSB + ib);
-      *reinterpret_cast<V*>(b1.v) = *reinterpret_cast<const V*>(Bs + u * LSB + ib + TXE);
-      if (a.mb_mode != M_NONE) {
-        if (a.mb_mode == M_FULL) {
+      *reinterpret_cast<V*>(b0.v) = *reinterpret_cast<const V*>(Bs + u * LSB);
+      *reinterpret_cast<V*>(b1.v) = *reinterpret_cast<const V*>(Bs + u * LSB + TXE);
+      if (mb_level) {
+        if (mb_mode == M_FULL) {
           *reinterpret_cast<V*>(mb0.v) = *reinterpret_cast<const V*>(MBs + u * LSB + ib);
           *reinterpret_cast<V*>(mb1.v) = *reinterpret_cast<const V*>(MBs + u * LSB + ib + TXE);
-        } else if (a.mb_mode == M_SCALAR) {
+        } else {
           const T m0 = __ldg(s.mb.ptr + z * s.mb.sz + (low_b ? 0 : s0) * s.mb.sp);
-          const T m1 = __ldg(s.mb.ptr + z * s.mb.sz + (high_b ? s.Pb - 1 : s1) * s.mb.sp);
+          const T m1 = __ldg(s.mb.ptr + z * s.mb.sz + (high_b ? Pb - 1 : s1) * s.mb.sp);
 #pragma unroll
           for (int kk = 0; kk < VEC; ++kk) {
             mb0.v[kk] = m0;
             mb1.v[kk] = m1;
           }
         }
+      }
 #pragma unroll
-        for (int kk = 0; kk < VEC; ++kk) {
-          b0.v[kk] = b0.v[kk] * mb0.v[kk];
-          b1.v[kk] = b1.v[kk] * mb1.v[kk];
-        }
+      for (int kk = 0; kk < VEC; ++kk) {
+        b0.v[kk] = b0.v[kk] * mb0.v[kk];
+        b1.v[kk] = b1.v[kk] * mb1.v[kk];
       }
       if (low_b || high_b) {
         // (B x mb)[z, row, x .. x + VEC) from global memory: wrap-around and extrapolation partners
         auto Brow = [&](int64_t row) -> Pack {
-          Pack r = xg_ld_cached<T, VEC>(s.b + (z * s.Pb + row) * s.n + x);
-          if (a.mb_mode != M_NONE) {
+          Pack r = xg_ld_cached<T, VEC>(s.b + (z * Pb + row) * n + x);
+          if (mb_mode != M_NONE) {
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk)
               r.v[kk] = r.v[kk] * __ldg(s.mb.ptr + z * s.mb.sz + row * s.mb.sp + (int64_t)(x + kk) * s.mb.sx);
@@ -247,27 +252,27 @@ __global__ void __launch_bounds__(kConsumers + 32, 3)
           return r;
         };
         if (low_b) {  // s0 == -1
-          if (s.halo_lo) b0 = xg_ld_cached<T, VEC>(s.halo_lo + z * s.n + x);
+          if (s.halo_lo) b0 = xg_ld_cached<T, VEC>(s.halo_lo + z * n + x);
           else if (s.bc_b == XG_BC_FILL) {
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk) b0.v[kk] = s.fill_b;
-          } else if (s.bc_b == XG_BC_PERIODIC) b0 = Brow(s.Pb - 1);
+          } else if (s.bc_b == XG_BC_PERIODIC) b0 = Brow(Pb - 1);
           else if (s.bc_b == XG_BC_EXTEND) b0 = b1;
           else {
-            const Pack nxt = Brow(s.Pb > 1 ? 1 : 0);
+            const Pack nxt = Brow(Pb > 1 ? 1 : 0);
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk) b0.v[kk] = T(2) * b1.v[kk] - nxt.v[kk];
           }
         }
         if (high_b) {  // s1 == Pb
-          if (s.halo_hi) b1 = xg_ld_cached<T, VEC>(s.halo_hi + z * s.n + x);
+          if (s.halo_hi) b1 = xg_ld_cached<T, VEC>(s.halo_hi + z * n + x);
           else if (s.bc_b == XG_BC_FILL) {
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk) b1.v[kk] = s.fill_b;
           } else if (s.bc_b == XG_BC_PERIODIC) b1 = Brow(0);
           else if (s.bc_b == XG_BC_EXTEND) b1 = b0;
           else {
-            const Pack prv = Brow(s.Pb > 1 ? s.Pb - 2 : 0);
+            const Pack prv = Brow(Pb > 1 ? Pb - 2 : 0);
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk) b1.v[kk] = T(2) * b0.v[kk] - prv.v[kk];
           }
@@ -275,60 +280,62 @@ __global__ void __launch_bounds__(kConsumers + 32, 3)
       }
       Pack res;
 #pragma unroll
-      for (int kk = 0; kk < VEC; ++kk) res.v[kk] = tile_op<T>(s.op_b, b0.v[kk], b1.v[kk]);
+      for (int kk = 0; kk < VEC; ++kk) res.v[kk] = xg_apply_op<T, OPB>(b0.v[kk], b1.v[kk]);
 
       // ---- x term: A x ma, neighbour from the adjacent lane
       if (HAS_A) {
         Pack v;
-        *reinterpret_cast<V*>(v.v) = *reinterpret_cast<const V*>(As + u * LSA + ia);
+        *reinterpret_cast<V*>(v.v) = *reinterpret_cast<const V*>(As + u * LSA);
         T enb = T(0);
-        if (edge_lane) enb = As[u * LSA + ia + nbi];
-        if (a.ma_mode != M_NONE) {
-          if (a.ma_mode == M_FULL) {
+        if (edge_lane) enb = As[u * LSA + nbi];
+        if (ma_level) {
+          if (ma_mode == M_FULL) {
             *reinterpret_cast<V*>(ma_v.v) = *reinterpret_cast<const V*>(MAs + u * LSA + ia);
             if (edge_lane) ma_nb = MAs[u * LSA + ia + nbi];
-          } else if (a.ma_mode == M_SCALAR) {
-            ma_nb = __ldg(s.ma.ptr + z * s.ma.sz + (int64_t)(prow < s.Po ? prow : s.Po - 1) * s.ma.sp);
+          } else {
+            ma_nb = __ldg(s.ma.ptr + z * s.ma.sz + (int64_t)prc * s.ma.sp);
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk) ma_v.v[kk] = ma_nb;
           }
-#pragma unroll
-          for (int kk = 0; kk < VEC; ++kk) v.v[kk] = v.v[kk] * ma_v.v[kk];
-          enb = enb * ma_nb;
         }
-        T nb = s.lo_a ? __shfl_up_sync(FULL, v.v[VEC - 1], 1) : __shfl_down_sync(FULL, v.v[0], 1);
+#pragma unroll
+        for (int kk = 0; kk < VEC; ++kk) v.v[kk] = v.v[kk] * ma_v.v[kk];
+        enb = enb * ma_nb;
+        T nb = lo_a ? __shfl_up_sync(FULL, v.v[VEC - 1], 1) : __shfl_down_sync(FULL, v.v[0], 1);
         if (edge_lane) nb = enb;
         if (at_edge) {
           if (s.bc_a == XG_BC_FILL) nb = s.fill_a;
           else if (s.bc_a == XG_BC_PERIODIC) {
-            const int64_t row = z * s.Po + (prow < s.Po ? prow : s.Po - 1), xx = s.lo_a ? s.n - 1 : 0;
-            nb = __ldg(s.a + row * s.n + xx);
-            if (a.ma_mode != M_NONE)
-              nb = nb * __ldg(s.ma.ptr + z * s.ma.sz + (row - z * s.Po) * s.ma.sp + xx * s.ma.sx);
-          } else nb = s.lo_a ? v.v[0] : v.v[VEC - 1];  // extend
+            const int64_t xx = lo_a ? n - 1 : 0;
+            nb = __ldg(s.a + (z * Po + prc) * n + xx);
+            if (ma_mode != M_NONE) nb = nb * __ldg(s.ma.ptr + z * s.ma.sz + (int64_t)prc * s.ma.sp + xx * s.ma.sx);
+          } else nb = lo_a ? v.v[0] : v.v[VEC - 1];  // extend
         }
 #pragma unroll
         for (int kk = 0; kk < VEC; ++kk) {
-          const T ta = s.lo_a ? tile_op<T>(s.op_a, kk == 0 ? nb : v.v[kk > 0 ? kk - 1 : 0], v.v[kk])
-                              : tile_op<T>(s.op_a, v.v[kk], kk == VEC - 1 ? nb : v.v[kk < VEC - 1 ? kk + 1 : kk]);
+          const T lo_v = kk == 0 ? nb : v.v[kk > 0 ? kk - 1 : 0];
+          const T hi_v = kk == VEC - 1 ? nb : v.v[kk < VEC - 1 ? kk + 1 : kk];
+          const T ta = lo_a ? xg_apply_op<T, OPA>(lo_v, v.v[kk]) : xg_apply_op<T, OPA>(v.v[kk], hi_v);
           const T tb = res.v[kk];
-          res.v[kk] = s.subtract == 0 ? ta + tb : (s.subtract == 1 ? ta - tb : tb - ta);
+          res.v[kk] = sub == 0 ? ta + tb : (sub == 1 ? ta - tb : tb - ta);
         }
       }
       // ---- divide
-      if (a.post_mode == M_SHARED) {
+      if (post_level) {
+        if (post_mode == M_SCALAR) {
+          XgSharedDivisor<T> d;
+          d.set(__ldg(s.post.ptr + z * s.post.sz + (int64_t)prc * s.post.sp));
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) res.v[kk] = d.div(res.v[kk]);
+        } else {
+          Pack pm;
+          *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(Qs + u * LSQ + ib);
+#pragma unroll
+          for (int kk = 0; kk < VEC; ++kk) res.v[kk] = res.v[kk] / pm.v[kk];
+        }
+      } else {
 #pragma unroll
         for (int kk = 0; kk < VEC; ++kk) res.v[kk] = dv[kk].div(res.v[kk]);
-      } else if (a.post_mode == M_SCALAR) {
-        XgSharedDivisor<T> d;
-        d.set(__ldg(s.post.ptr + z * s.post.sz + (int64_t)(prow < s.Po ? prow : s.Po - 1) * s.post.sp));
-#pragma unroll
-        for (int kk = 0; kk < VEC; ++kk) res.v[kk] = d.div(res.v[kk]);
-      } else if (a.post_mode == M_FULL) {
-        Pack pm;
-        *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(Qs + u * LSQ + ib);
-#pragma unroll
-        for (int kk = 0; kk < VEC; ++kk) res.v[kk] = res.v[kk] / pm.v[kk];
       }
       if (act) xg_st_stream<T, VEC>(op + u * ostride, res);
     }
@@ -345,7 +352,7 @@ int tile_env_int(const char* name, int dflt) {
 
 // NONE / FULL / SHARED / SCALAR from the (z, p, x) strides; -1 when a tensor map cannot describe the operand
 template <typename T>
-int metric_mode(const XgTileOperand<T>& m, int vec, int* row0) {
+int metric_mode(const XgTileOperand<T>& m, int vec, int64_t rows, int* row0) {
   *row0 = 0;
   if (!m.ptr) return M_NONE;
   if (m.sx == 0) return M_SCALAR;
@@ -355,7 +362,7 @@ int metric_mode(const XgTileOperand<T>& m, int vec, int* row0) {
     *row0 = m.sp == 0;
     return M_SHARED;
   }
-  if (m.sp == 0) return -1;  // hFac(Z, 1, X): no row stride for the map
+  if (m.sp == 0 && rows > 1) return -1;  // hFac(Z, 1, X): no row stride for the map
   return M_FULL;
 }
 
@@ -373,11 +380,12 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
   if (((uintptr_t)s.b | (uintptr_t)s.out | (uintptr_t)s.a | (uintptr_t)s.halo_lo | (uintptr_t)s.halo_hi) % 16 != 0)
     return XG_OK;
   if (s.a && (s.Po != s.Pb || s.bc_a == XG_BC_EXTRAPOLATE || s.bc_a == XG_BC_NONE)) return XG_OK;
+  if (s.a && (s.op_a > XG_OP_INTERP || s.op_b > XG_OP_INTERP)) return XG_OK;  // min / max pairs: k_stencil_pair
   TileArgs<T> a;
   a.s = s;
-  a.ma_mode = s.a ? metric_mode<T>(s.ma, VEC, &a.ma_row0) : M_NONE;
-  a.mb_mode = metric_mode<T>(s.mb, VEC, &a.mb_row0);
-  a.post_mode = metric_mode<T>(s.post, VEC, &a.post_row0);
+  a.ma_mode = s.a ? metric_mode<T>(s.ma, VEC, s.Po, &a.ma_row0) : M_NONE;
+  a.mb_mode = metric_mode<T>(s.mb, VEC, s.Pb, &a.mb_row0);
+  a.post_mode = metric_mode<T>(s.post, VEC, s.Po, &a.post_row0);
   if (a.ma_mode < 0 || a.mb_mode < 0 || a.post_mode < 0) return XG_OK;
   // the point of the kernel is the shared divisor / the shared metric tiles: without any, the
   // register-staged kernels are already at the roofline
@@ -411,8 +419,8 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   static const int tune_nst = tile_env_int("XG_TILE_NST", 0);
   static const int tune_ctas = tile_env_int("XG_TILE_CTAS", 0);
-  int ctas = (3 * 2 * (int)a.stage_bytes <= 135 * 1024) ? 3 : 2;  // as for k_stencil_row_tma
-  if (tune_ctas >= 1 && tune_ctas <= 3) ctas = tune_ctas;
+  int ctas = (!s.a && 3 * 2 * (int)a.stage_bytes <= 135 * 1024) ? 3 : 2;  // as for k_stencil_row_tma
+  if (tune_ctas >= 1 && tune_ctas <= (s.a ? 2 : 3)) ctas = tune_ctas;
   int nst = 0;
   for (; ctas >= 1; --ctas) {
     int per_cta = smem_sm / ctas - 1024;
@@ -443,7 +451,7 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
   // tensor maps: fields as (n, rows, Zn); shared metrics as (n, rows) (or (n, 1) when row-less)
   auto field_map = [&](CUtensorMap* map, const T* ptr, int64_t rows, int64_t sp, int64_t sz, int boxw, int boxr) -> int {
     const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)rows, (cuuint64_t)s.Zn};
-    const cuuint64_t s3[2] = {(cuuint64_t)sp * sizeof(T), (cuuint64_t)sz * sizeof(T)};
+    const cuuint64_t s3[2] = {(cuuint64_t)(sp ? sp : s.n) * sizeof(T), (cuuint64_t)sz * sizeof(T)};  // sp == 0: single row
     const cuuint32_t bx[3] = {(cuuint32_t)boxw, (cuuint32_t)boxr, (cuuint32_t)U};
     return xg_encode_map<T>(enc, map, ptr, 3, d3, s3, bx);
   };
@@ -475,7 +483,29 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
     kern<<<(unsigned)grid, kConsumers + 32, smem, st>>>(map_a, map_b, map_ma, map_mb, map_post, a);
     return 1;
   };
-  const int ok = s.a ? go(k_tile_stencil<T, true>) : go(k_tile_stencil<T, false>);
+  const bool levelm = a.ma_mode == M_FULL || a.ma_mode == M_SCALAR || a.mb_mode == M_FULL || a.mb_mode == M_SCALAR ||
+                      a.post_mode == M_FULL || a.post_mode == M_SCALAR;
+  int ok = 0;
+#define XG_TILE_GO(HAS_A_, OPA_, OPB_) \
+  ok = levelm ? go(k_tile_stencil<T, HAS_A_, OPA_, OPB_, true>) : go(k_tile_stencil<T, HAS_A_, OPA_, OPB_, false>)
+  if (s.a) {
+    switch (s.op_a * 4 + s.op_b) {
+      case XG_OP_DIFF * 4 + XG_OP_DIFF: XG_TILE_GO(true, XG_OP_DIFF, XG_OP_DIFF); break;
+      case XG_OP_DIFF * 4 + XG_OP_INTERP: XG_TILE_GO(true, XG_OP_DIFF, XG_OP_INTERP); break;
+      case XG_OP_INTERP * 4 + XG_OP_DIFF: XG_TILE_GO(true, XG_OP_INTERP, XG_OP_DIFF); break;
+      case XG_OP_INTERP * 4 + XG_OP_INTERP: XG_TILE_GO(true, XG_OP_INTERP, XG_OP_INTERP); break;
+      default: break;
+    }
+  } else {
+    switch (s.op_b) {
+      case XG_OP_DIFF: XG_TILE_GO(false, XG_OP_DIFF, XG_OP_DIFF); break;
+      case XG_OP_INTERP: XG_TILE_GO(false, XG_OP_DIFF, XG_OP_INTERP); break;
+      case XG_OP_MIN: XG_TILE_GO(false, XG_OP_DIFF, XG_OP_MIN); break;
+      case XG_OP_MAX: XG_TILE_GO(false, XG_OP_DIFF, XG_OP_MAX); break;
+      default: break;
+    }
+  }
+#undef XG_TILE_GO
   if (!ok) return XG_OK;
   *launched = true;
   return xg_check_launch(label);
