@@ -172,7 +172,8 @@ def test_shared_divisor_division_is_ieee_on_arbitrary_bit_patterns(dtype, X, ker
     with np.errstate(all="ignore"):
         want = (a2 / b)[:, :, 1::2]
     m = torch.from_numpy(b).to(dev)
-    got = ops.stencil2(torch.from_numpy(a2).to(dev), 2, "diff", 1, 0, "fill", 0.0, post=m).cpu().numpy()
+    ones = torch.ones((1, Y, X), dtype=m.dtype, device=dev)  # a level-shared pre-metric: x * 1 is exact
+    got = ops.stencil2(torch.from_numpy(a2).to(dev), 2, "diff", 1, 0, "fill", 0.0, pre=ones, post=m).cpu().numpy()
     assert _capi_last_launch() == f"xg_stencil2({kernel})"
     got = got[:, :, 1::2]
     np.testing.assert_array_equal(np.isnan(got), np.isnan(want))
@@ -226,6 +227,39 @@ def test_metric_tile_kernel_second_to_last_axis(dtype, shape):
 
 
 @pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(9, 5, 452), (6, 3, 904), (5, 2, 3, 676), (3, 7, 1000)])
+def test_metric_tile_kernel_outermost_axis(dtype, shape):
+    """Stencils along the OUTERMOST dim of a (Z, Y, X) field with dz(Z)-like metrics (interp / derivative
+    along Z, metric-weighted): the tile kernel runs them as rows = Z, levels = Y (x Y'), sharing the per-row
+    scalar divisor.  Against the reference's separate passes, every shift, boundary and metric layout."""
+    from xgcm_b200 import _capi
+
+    rng = np.random.default_rng(80)
+    a = _field(shape, dtype, seed=81, nan_frac=0.01)
+    nd = len(shape)
+
+    def metric(dims, n_axis):
+        shp = [shape[d] if d in dims else 1 for d in range(nd)]
+        if 0 in dims:
+            shp[0] = n_axis
+        return (0.5 + rng.random(shp)).astype(dtype)
+
+    for (lo, hi) in SHIFTS:
+        n_out = shape[0] + lo + hi - 1
+        posts = [metric((0,), n_out), metric(range(nd), n_out), metric((nd - 2, nd - 1), n_out)]
+        pres = [None, metric((0,), shape[0]), metric(range(nd), shape[0]), metric((nd - 1,), shape[0])]
+        for (bc, fill) in BCS + [("extrapolate", 0.0)]:
+            for post in posts:
+                for pre in pres:
+                    _check(a, 0, "interp", lo, hi, bc, fill, pre, post)
+            _check(a, 0, "diff", lo, hi, bc, fill, pres[1], posts[0])
+            if shape[-1] >= (448 if dtype == np.float32 else 480):
+                assert _capi.last_launch() == "xg_stencil2(tile_tma)"
+            _check(a, 0, "max", lo, hi, bc, fill, pres[2], posts[0])
+            _check(a, 0, "min", lo, hi, bc, fill, None, posts[0])
+
+
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
 @pytest.mark.parametrize("shape,axis", [((5, 6, 904), 2), ((5, 6, 904), 1), ((4, 3, 256), 2), ((3, 4, 130), 1), ((6, 5, 904), 0)])
 def test_halo_planes_with_metrics(dtype, shape, axis):
     """Explicit halo planes (the neighbour GPU's boundary plane in the sharded path, xgcm_b200.h) replace the
@@ -248,7 +282,8 @@ def test_halo_planes_with_metrics(dtype, shape, axis):
 
     for (lo, hi), (bc, fill), op in itertools.product(((1, 0), (0, 1), (1, 1)), (("extend", 0.0), ("fill", 2.5)), ("diff", "interp")):
         n_out = shape[axis] + lo + hi - 1
-        for pre_dims, post_dims in (((1, 2), (1, 2)), (None, (1, 2)), (range(nd), (1, 2)), ((0,), (2,))):
+        for pre_dims, post_dims in (((1, 2), (1, 2)), (None, (1, 2)), (range(nd), (1, 2)), ((0,), (2,)), ((0,), (0,)),
+                                    (range(nd), (0,)), (None, (1,))):
             pre = None if pre_dims is None else metric(pre_dims, shape[axis])
             post = metric(post_dims, n_out)
             ap = a if pre is None else a * pre

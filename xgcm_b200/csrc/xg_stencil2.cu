@@ -32,6 +32,7 @@ struct StencilArgs {
   const T* in;
   T* out;
   int64_t outer, n, inner, n_out;
+  int64_t nx_last;     // extent of the innermost dim (inner is a multiple of it when inner > 1)
   int lo, hi, bc;
   T fill;
   int J;               // cells marched per warp-unit (strided kernel)
@@ -790,6 +791,10 @@ int launch_row_zb(const StencilArgs<T>& s, cudaStream_t st, bool* launched) {
   a.pre_vec = s.pre_axis_vec_ok;
   a.pre_shared = !s.pre.ptr || s.pre.outer.n == 0 ||
                  (s.pre.outer.stride[0] == 0 && s.pre.outer.size[0] % a.Zn == 0);
+  // measured at C3 (profiles/r2_row_tma_sweep.txt, last line vs k_stencil_row_vec): ahead only when the
+  // pre-metric is level-shared too (1.25 vs 1.54 ms); with no or a per-level pre-metric the four edge loads
+  // per warp cost more than the shared divisor saves (1.18 vs 1.07, 2.02 vs 1.86 ms)
+  if (!s.pre.ptr || !a.pre_shared) return XG_OK;
   a.nwc = xg_ceil_div(s.n / VEC, 32);
   a.nunits = xg_ceil_div(a.Zn, U) * a.P * a.nwc;
   a.small_units = a.nunits < (1ll << 31) && a.P < (1ll << 31);
@@ -963,13 +968,14 @@ int dispatch_layout(StencilArgs<T>& a, cudaStream_t st) {
                       (!a.halo_hi || (uintptr_t)a.halo_hi % 16 == 0);
   if (a.inner > 1) {
     if constexpr (MET) {
-      // metrics shared between the outer index (levels): the TMA-staged tile kernel, rows = the operated axis
+      // the TMA-staged tile kernel, rows = the operated axis.  Either the dim right before x with the outer
+      // index as levels (derivative('Y') on (Z, Y, X): dx(Y, X) is shared between levels), or — a single outer
+      // index, e.g. any stencil along Z of a (Z, Y, X) field — the inner dims split as levels x x with per-row
+      // scalar metrics (dz(Z)) shared by all of them.
       if (ptr_ok && a.inner % VEC == 0) {
         XgTileSpec<T> ts;
-        ts.Zn = a.outer;
         ts.Pb = a.n;
         ts.Po = a.n_out;
-        ts.n = a.inner;
         ts.a = nullptr;
         ts.op_a = ts.lo_a = ts.bc_a = 0;
         ts.fill_a = T(0);
@@ -985,8 +991,39 @@ int dispatch_layout(StencilArgs<T>& a, cudaStream_t st) {
         ts.ma.ptr = nullptr;
         ts.ma.sz = ts.ma.sp = ts.ma.sx = 0;
         ts.out = a.out;
-        if (xg_tile_operand_from<T>(a.pre, a.outer, a.inner, &ts.mb) &&
-            xg_tile_operand_from<T>(a.post, a.outer, a.inner, &ts.post)) {
+        bool ok = false;
+        const int64_t nx = a.nx_last;
+        if (a.outer == 1 && nx > 0 && nx < a.inner && a.inner % nx == 0) {
+          ts.Zn = a.inner / nx;
+          ts.n = nx;
+          ts.f_sp = a.inner;
+          ts.b_sz = ts.o_sz = nx;
+          // metrics: broadcast over the inner dims (sx = sz = 0), or laid out like the field's inner dims
+          auto inner_split = [&](const XgOperand& m, XgTileOperand<T>* o) -> bool {
+            o->ptr = static_cast<const T*>(m.ptr);
+            o->sz = o->sp = o->sx = 0;
+            if (!m.ptr) return true;
+            if (m.outer.n != 0) return false;
+            o->sp = m.axis_stride;
+            if (m.inner.n == 0 || (m.inner.n == 1 && m.inner.stride[0] == 0)) return true;
+            if (m.inner.n == 1 && m.inner.size[0] == a.inner && m.inner.stride[0] == 1) {
+              o->sx = 1;
+              o->sz = nx;
+              return true;
+            }
+            return false;
+          };
+          ok = inner_split(a.pre, &ts.mb) && inner_split(a.post, &ts.post);
+        } else {
+          ts.Zn = a.outer;
+          ts.n = a.inner;
+          ts.f_sp = a.inner;
+          ts.b_sz = a.n * a.inner;
+          ts.o_sz = a.n_out * a.inner;
+          ok = xg_tile_operand_from<T>(a.pre, a.outer, a.inner, &ts.mb) &&
+               xg_tile_operand_from<T>(a.post, a.outer, a.inner, &ts.post);
+        }
+        if (ok) {
           bool launched = false;
           const int rc = xg_tile_stencil<T>(ts, st, &launched, "xg_stencil2(tile_tma)");
           if (rc || launched) return rc;
@@ -1054,6 +1091,7 @@ int stencil2_typed(int op, const void* in, void* out, int ndim, const int64_t* s
   a.n = v.n;
   a.inner = v.inner;
   a.n_out = v.n + lo + hi - 1;
+  a.nx_last = ndim > 0 ? shape[ndim - 1] : 1;
   a.lo = lo;
   a.hi = hi;
   a.bc = bc;

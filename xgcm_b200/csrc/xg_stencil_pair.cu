@@ -295,6 +295,8 @@ int pair_typed(const void* a, const void* b, void* out, int ndim, const int64_t*
     ts.Zn = p.outer;
     ts.Pb = ts.Po = p.nb;
     ts.n = p.nx;
+    ts.f_sp = p.nx;
+    ts.b_sz = ts.o_sz = p.nb * p.nx;
     ts.a = p.a;
     ts.op_a = p.op_a;
     ts.lo_a = p.lo_a;

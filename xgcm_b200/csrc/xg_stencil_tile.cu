@@ -50,13 +50,19 @@ struct TileArgs {
   int64_t npq, ntiles;
   XgFastDiv fd_ntx, fd_rbq, fd_nzq;
   int nst;
+  int swap;      // levels are the faster dim in memory (stencil along Z as rows): boxes are (x, level, row)
   int l2_hints;  // evict-first fields / evict-last metric tiles (measured slower on the row kernel: off by default)
   unsigned off_b, off_ma, off_mb, off_post, stage_bytes, tx_bytes;
 };
 
 // tensor loads with an optional L2 eviction policy
 __device__ __forceinline__ void load3(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2, uint32_t bar,
-                                      bool hint, uint64_t policy) {
+                                      bool hint, uint64_t policy, bool swap = false) {
+  if (swap) {  // (x, level, row) maps
+    const int t = c1;
+    c1 = c2;
+    c2 = t;
+  }
   if (hint) tensor_load_3d_hint(dst, map, c0, c1, c2, bar, policy);
   else tensor_load_3d(dst, map, c0, c1, c2, bar);
 }
@@ -133,14 +139,15 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
         const int pb = p0 - s.lo_b;  // first source row of B the tile needs (may be -1: zero fill, replaced below)
         const bool h = a.l2_hints != 0;
         if (HAS_A) load3(dst, &map_a, x0 - xs, p0, z0, bar, h, once);
-        load3(dst + a.off_b, &map_b, x0, pb, z0, bar, false, once);  // B's halo row is re-read by the next tile row
+        const bool sw = a.swap != 0;
+        load3(dst + a.off_b, &map_b, x0, pb, z0, bar, false, once, sw);  // B's halo row is re-read by the next tile row
         if (HAS_A) {
           if (a.ma_mode == M_FULL) load3(dst + a.off_ma, &map_ma, x0 - xs, p0, z0, bar, h, once);
           else if (a.ma_mode == M_SHARED) load2(dst + a.off_ma, &map_ma, x0 - xs, a.ma_row0 ? 0 : p0, bar, h, keep);
         }
-        if (a.mb_mode == M_FULL) load3(dst + a.off_mb, &map_mb, x0, pb, z0, bar, false, once);
+        if (a.mb_mode == M_FULL) load3(dst + a.off_mb, &map_mb, x0, pb, z0, bar, false, once, sw);
         else if (a.mb_mode == M_SHARED) load2(dst + a.off_mb, &map_mb, x0, a.mb_row0 ? 0 : pb, bar, h, keep);
-        if (a.post_mode == M_FULL) load3(dst + a.off_post, &map_post, x0, p0, z0, bar, h, once);
+        if (a.post_mode == M_FULL) load3(dst + a.off_post, &map_post, x0, p0, z0, bar, h, once, sw);
         else if (a.post_mode == M_SHARED) load2(dst + a.off_post, &map_post, x0, a.post_row0 ? 0 : p0, bar, h, keep);
         ++k;
       }
@@ -156,18 +163,25 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
   const int ma_mode = HAS_A ? a.ma_mode : M_NONE, mb_mode = a.mb_mode, post_mode = a.post_mode;
   const int ia = ty * BOXW + vxs * VEC + xs;
   const int ima = (ma_mode == M_SHARED && a.ma_row0) ? vxs * VEC + xs : ia;
-  const int ib = ty * TXE + vxs * VEC;
-  const int imb = (mb_mode == M_SHARED && a.mb_row0) ? vxs * VEC : ib;
+  // box layouts: (level, row, x) normally; (row, level, x) when the levels are the faster dim in memory
+  const int b_ls = a.swap ? TXE : LSB, b_rs = a.swap ? U * TXE : TXE;
+  const int q_ls = a.swap ? TXE : LSQ;
+  const int ib = ty * b_rs + vxs * VEC;
+  const int ishr = ty * TXE + vxs * VEC;  // 2-D (row, x) boxes of level-shared metrics
+  const int imb = (mb_mode == M_SHARED && a.mb_row0) ? vxs * VEC : ishr;
   const int imb1 = (mb_mode == M_SHARED && a.mb_row0) ? imb : imb + TXE;
-  const int iq = (post_mode == M_SHARED && a.post_row0) ? vxs * VEC : ib;
+  const int iq = (post_mode == M_SHARED && a.post_row0) ? vxs * VEC : ishr;
   const int nbi = lo_a ? -1 : VEC;
   const bool edge_lane = lo_a ? (lane == 0) : (lane == 31 || vx >= NVR - 1);
   // metrics that change per level need work inside the level loop; everything else is set up once per tile and
   // an absent metric is a multiplication by one (exact, NaN / zero preserving) instead of a branch per cell
-  const bool ma_level = LEVELM && (ma_mode == M_FULL || ma_mode == M_SCALAR);
-  const bool mb_level = LEVELM && (mb_mode == M_FULL || mb_mode == M_SCALAR);
-  const bool post_level = LEVELM && (post_mode == M_FULL || post_mode == M_SCALAR);
-  const int64_t Pb = s.Pb, Po = s.Po, n = s.n, ostride = s.Po * s.n;
+  // (a per-row scalar that does not depend on the level — dz(Z) with Z as the rows — is set up per tile like a shared one)
+  const bool ma_rowsc = ma_mode == M_SCALAR && s.ma.sz == 0, mb_rowsc = mb_mode == M_SCALAR && s.mb.sz == 0;
+  const bool post_rowsc = post_mode == M_SCALAR && s.post.sz == 0;
+  const bool ma_level = LEVELM && (ma_mode == M_FULL || (ma_mode == M_SCALAR && !ma_rowsc));
+  const bool mb_level = LEVELM && (mb_mode == M_FULL || (mb_mode == M_SCALAR && !mb_rowsc));
+  const bool post_level = LEVELM && (post_mode == M_FULL || (post_mode == M_SCALAR && !post_rowsc));
+  const int64_t Pb = s.Pb, Po = s.Po, n = s.n, fsp = s.f_sp, bsz = s.b_sz, ostride = s.o_sz;
 
   int64_t k = 0;
   for (int64_t i = 0; i < nloc; ++i) {
@@ -186,6 +200,8 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
     const T* Qs = reinterpret_cast<const T*>(st + a.off_post);
     const int s0 = prow - lo_b, s1 = s0 + 1;  // source rows of B for this output row
     const bool low_b = s0 < 0, high_b = s1 >= Pb;
+    // clamped source rows for the scalar metric loads (boundary rows and the spare rows of the last tile)
+    const int64_t s0c = s0 < 0 ? 0 : (s0 < Pb ? s0 : Pb - 1), s1c = s1 < Pb ? s1 : Pb - 1;
     const bool at_edge = HAS_A && (lo_a ? (x == 0) : (x + VEC >= n));
     mbar_wait(full_u32 + 8u * b, (uint32_t)((k / NST) & 1));
 
@@ -211,7 +227,26 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
       *reinterpret_cast<V*>(mb0.v) = *reinterpret_cast<const V*>(MBs + imb);
       *reinterpret_cast<V*>(mb1.v) = *reinterpret_cast<const V*>(MBs + imb1);
     }
-    T* op = s.out + ((int64_t)z0 * Po + prow) * n + x;
+    if (post_rowsc) {
+      const T d = __ldg(s.post.ptr + (int64_t)prc * s.post.sp);
+#pragma unroll
+      for (int kk = 0; kk < VEC; ++kk) dv[kk].set(d);
+    }
+    if (ma_rowsc) {
+      ma_nb = __ldg(s.ma.ptr + (int64_t)prc * s.ma.sp);
+#pragma unroll
+      for (int kk = 0; kk < VEC; ++kk) ma_v.v[kk] = ma_nb;
+    }
+    if (mb_rowsc) {
+      const T m0 = __ldg(s.mb.ptr + s0c * s.mb.sp);
+      const T m1 = __ldg(s.mb.ptr + s1c * s.mb.sp);
+#pragma unroll
+      for (int kk = 0; kk < VEC; ++kk) {
+        mb0.v[kk] = m0;
+        mb1.v[kk] = m1;
+      }
+    }
+    T* op = s.out + (int64_t)z0 * ostride + (int64_t)prow * fsp + x;
 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -219,15 +254,15 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
       const int64_t z = z0 + u;
       // ---- row term: B x mb at source rows s0, s1
       Pack b0, b1;
-      *reinterpret_cast<V*>(b0.v) = *reinterpret_cast<const V*>(Bs + u * LSB);
-      *reinterpret_cast<V*>(b1.v) = *reinterpret_cast<const V*>(Bs + u * LSB + TXE);
+      *reinterpret_cast<V*>(b0.v) = *reinterpret_cast<const V*>(Bs + u * b_ls);
+      *reinterpret_cast<V*>(b1.v) = *reinterpret_cast<const V*>(Bs + u * b_ls + b_rs);
       if (mb_level) {
         if (mb_mode == M_FULL) {
-          *reinterpret_cast<V*>(mb0.v) = *reinterpret_cast<const V*>(MBs + u * LSB + ib);
-          *reinterpret_cast<V*>(mb1.v) = *reinterpret_cast<const V*>(MBs + u * LSB + ib + TXE);
+          *reinterpret_cast<V*>(mb0.v) = *reinterpret_cast<const V*>(MBs + u * b_ls + ib);
+          *reinterpret_cast<V*>(mb1.v) = *reinterpret_cast<const V*>(MBs + u * b_ls + ib + b_rs);
         } else {
-          const T m0 = __ldg(s.mb.ptr + z * s.mb.sz + (low_b ? 0 : s0) * s.mb.sp);
-          const T m1 = __ldg(s.mb.ptr + z * s.mb.sz + (high_b ? Pb - 1 : s1) * s.mb.sp);
+          const T m0 = __ldg(s.mb.ptr + z * s.mb.sz + s0c * s.mb.sp);
+          const T m1 = __ldg(s.mb.ptr + z * s.mb.sz + s1c * s.mb.sp);
 #pragma unroll
           for (int kk = 0; kk < VEC; ++kk) {
             mb0.v[kk] = m0;
@@ -243,7 +278,7 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
       if (low_b || high_b) {
         // (B x mb)[z, row, x .. x + VEC) from global memory: wrap-around and extrapolation partners
         auto Brow = [&](int64_t row) -> Pack {
-          Pack r = xg_ld_cached<T, VEC>(s.b + (z * Pb + row) * n + x);
+          Pack r = xg_ld_cached<T, VEC>(s.b + z * bsz + row * fsp + x);
           if (mb_mode != M_NONE) {
 #pragma unroll
             for (int kk = 0; kk < VEC; ++kk)
@@ -307,7 +342,7 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
           if (s.bc_a == XG_BC_FILL) nb = s.fill_a;
           else if (s.bc_a == XG_BC_PERIODIC) {
             const int64_t xx = lo_a ? n - 1 : 0;
-            nb = __ldg(s.a + (z * Po + prc) * n + xx);
+            nb = __ldg(s.a + z * ostride + (int64_t)prc * fsp + xx);
             if (ma_mode != M_NONE) nb = nb * __ldg(s.ma.ptr + z * s.ma.sz + (int64_t)prc * s.ma.sp + xx * s.ma.sx);
           } else nb = lo_a ? v.v[0] : v.v[VEC - 1];  // extend
         }
@@ -329,7 +364,7 @@ __global__ void __launch_bounds__(kConsumers + 32, HAS_A ? 2 : 3)  // the pair's
           for (int kk = 0; kk < VEC; ++kk) res.v[kk] = d.div(res.v[kk]);
         } else {
           Pack pm;
-          *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(Qs + u * LSQ + ib);
+          *reinterpret_cast<V*>(pm.v) = *reinterpret_cast<const V*>(Qs + u * q_ls + ib);
 #pragma unroll
           for (int kk = 0; kk < VEC; ++kk) res.v[kk] = res.v[kk] / pm.v[kk];
         }
@@ -377,19 +412,24 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
   if (!enabled || !s.b || !s.out) return XG_OK;
   if (s.n < 2 * TXE || s.n % VEC != 0 || s.n >= (1ll << 31) || s.Zn < 2 || s.Zn >= (1ll << 31)) return XG_OK;
   if (s.Pb < 1 || s.Po < 1 || s.Pb >= (1ll << 31) || s.Po >= (1ll << 31)) return XG_OK;
+  if (s.f_sp % VEC != 0 || s.b_sz % VEC != 0 || s.o_sz % VEC != 0 || s.f_sp <= 0 || s.b_sz <= 0 || s.o_sz <= 0) return XG_OK;
   if (((uintptr_t)s.b | (uintptr_t)s.out | (uintptr_t)s.a | (uintptr_t)s.halo_lo | (uintptr_t)s.halo_hi) % 16 != 0)
     return XG_OK;
   if (s.a && (s.Po != s.Pb || s.bc_a == XG_BC_EXTRAPOLATE || s.bc_a == XG_BC_NONE)) return XG_OK;
   if (s.a && (s.op_a > XG_OP_INTERP || s.op_b > XG_OP_INTERP)) return XG_OK;  // min / max pairs: k_stencil_pair
   TileArgs<T> a;
   a.s = s;
+  a.swap = (s.b_sz < s.f_sp && s.Pb > 1) ? 1 : 0;
+  if (a.swap && (s.a || s.o_sz >= s.f_sp)) return XG_OK;  // the x term's boxes are (level, row, x) only
   a.ma_mode = s.a ? metric_mode<T>(s.ma, VEC, s.Po, &a.ma_row0) : M_NONE;
   a.mb_mode = metric_mode<T>(s.mb, VEC, s.Pb, &a.mb_row0);
   a.post_mode = metric_mode<T>(s.post, VEC, s.Po, &a.post_row0);
   if (a.ma_mode < 0 || a.mb_mode < 0 || a.post_mode < 0) return XG_OK;
-  // the point of the kernel is the shared divisor / the shared metric tiles: without any, the
-  // register-staged kernels are already at the roofline
-  if (a.post_mode != M_SHARED && a.post_mode != M_SCALAR && a.ma_mode != M_SHARED && a.mb_mode != M_SHARED) return XG_OK;
+  // the point of the single-field kernel is the shared divisor / the shared metric tiles: without any, the
+  // register-staged kernels do as well
+  // (the two-field composite is faster here even without metrics: 1.37 vs 1.52 ms at C3, profiles/r2_pair_tma.txt)
+  static const int always = tile_env_int("XG_TILE_ALWAYS", 0);  // benchmarking: take every call
+  if (!always && !s.a && a.post_mode != M_SHARED && a.post_mode != M_SCALAR && a.mb_mode != M_SHARED) return XG_OK;
   EncodeTiledFn enc = encode_tiled_fn();
   if (!enc) return XG_OK;
 
@@ -449,9 +489,18 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
   a.fd_nzq = xg_fastdiv_make(nzq);
 
   // tensor maps: fields as (n, rows, Zn); shared metrics as (n, rows) (or (n, 1) when row-less)
+  // the encoder wants ascending strides: (x, row, level) normally, (x, level, row) when the levels are the faster dim
   auto field_map = [&](CUtensorMap* map, const T* ptr, int64_t rows, int64_t sp, int64_t sz, int boxw, int boxr) -> int {
+    if (sp == 0) sp = s.n;  // single row
+    if ((sz < sp) != (a.swap != 0) && rows > 1) return 1;
+    if (a.swap) {
+      const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)s.Zn, (cuuint64_t)rows};
+      const cuuint64_t s3[2] = {(cuuint64_t)sz * sizeof(T), (cuuint64_t)sp * sizeof(T)};
+      const cuuint32_t bx[3] = {(cuuint32_t)boxw, (cuuint32_t)U, (cuuint32_t)boxr};
+      return xg_encode_map<T>(enc, map, ptr, 3, d3, s3, bx);
+    }
     const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)rows, (cuuint64_t)s.Zn};
-    const cuuint64_t s3[2] = {(cuuint64_t)(sp ? sp : s.n) * sizeof(T), (cuuint64_t)sz * sizeof(T)};  // sp == 0: single row
+    const cuuint64_t s3[2] = {(cuuint64_t)sp * sizeof(T), (cuuint64_t)sz * sizeof(T)};
     const cuuint32_t bx[3] = {(cuuint32_t)boxw, (cuuint32_t)boxr, (cuuint32_t)U};
     return xg_encode_map<T>(enc, map, ptr, 3, d3, s3, bx);
   };
@@ -462,9 +511,9 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
     return xg_encode_map<T>(enc, map, m.ptr, 2, d2, s2, bx);
   };
   CUtensorMap map_a, map_b, map_ma, map_mb, map_post;
-  if (field_map(&map_b, s.b, s.Pb, s.n, s.Pb * s.n, TXE, TY + 1)) return XG_OK;
+  if (field_map(&map_b, s.b, s.Pb, s.f_sp, s.b_sz, TXE, TY + 1)) return XG_OK;
   map_a = map_ma = map_mb = map_post = map_b;
-  if (s.a && field_map(&map_a, s.a, s.Po, s.n, s.Po * s.n, BOXW, TY)) return XG_OK;
+  if (s.a && field_map(&map_a, s.a, s.Po, s.f_sp, s.o_sz, BOXW, TY)) return XG_OK;
   if (a.ma_mode == M_FULL && field_map(&map_ma, s.ma.ptr, s.Po, s.ma.sp, s.ma.sz, BOXW, TY)) return XG_OK;
   if (a.ma_mode == M_SHARED && rows_map(&map_ma, s.ma, a.ma_row0 != 0, s.Po, BOXW, TY)) return XG_OK;
   if (a.mb_mode == M_FULL && field_map(&map_mb, s.mb.ptr, s.Pb, s.mb.sp, s.mb.sz, TXE, TY + 1)) return XG_OK;
@@ -483,8 +532,8 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
     kern<<<(unsigned)grid, kConsumers + 32, smem, st>>>(map_a, map_b, map_ma, map_mb, map_post, a);
     return 1;
   };
-  const bool levelm = a.ma_mode == M_FULL || a.ma_mode == M_SCALAR || a.mb_mode == M_FULL || a.mb_mode == M_SCALAR ||
-                      a.post_mode == M_FULL || a.post_mode == M_SCALAR;
+  auto per_level = [](int mode, const XgTileOperand<T>& m) { return mode == M_FULL || (mode == M_SCALAR && m.sz != 0); };
+  const bool levelm = per_level(a.ma_mode, s.ma) || per_level(a.mb_mode, s.mb) || per_level(a.post_mode, s.post);
   int ok = 0;
 #define XG_TILE_GO(HAS_A_, OPA_, OPB_) \
   ok = levelm ? go(k_tile_stencil<T, HAS_A_, OPA_, OPB_, true>) : go(k_tile_stencil<T, HAS_A_, OPA_, OPB_, false>)

@@ -21,6 +21,10 @@ struct XgTileOperand {
 template <typename T>
 struct XgTileSpec {
   int64_t Zn, Pb, Po, n;  // levels, rows of B, rows of the output (= Pb + lo_b + hi_b - 1; = rows of A), cells per row
+  // element strides (rows are x-contiguous): f_sp between rows of A, B and out; b_sz between levels of B;
+  // o_sz between levels of out and A.  Contiguous (z, p, x) arrays: f_sp = n, b_sz = Pb * n, o_sz = Po * n.
+  // A stencil along Z of a (Z, Y, X) field runs as rows = Z (f_sp = Y * X) and levels = Y (b_sz = o_sz = X).
+  int64_t f_sp, b_sz, o_sz;
   const T* a;             // x term, nullptr when absent (then lo_a.. are ignored); lo_a + hi_a == 1
   int op_a, lo_a, bc_a;
   T fill_a;
