@@ -361,6 +361,41 @@ def test_stencil_multi_equals_sequential(dtype, shape):
             np.testing.assert_array_equal(got, want, err_msg=str(specs))
 
 
+@pytest.mark.parametrize("dtype", [np.float32, np.float64])
+@pytest.mark.parametrize("shape", [(5, 9, 452), (9, 6, 904), (3, 2, 5, 676), (2, 3, 1000), (7, 480), (1, 1, 5, 452)])
+def test_stencil_multi_tma_tiles_equal_sequential(dtype, shape):
+    """The TMA-staged multi-axis kernel (innermost axis first, length-preserving ops, rows of >= 2 tiles):
+    every axis subset of the last three dims, every lo / hi choice, every boundary combination (periodic and
+    extend are materialised in the tile, fill is applied in the chain), all four operators, ragged tiles in
+    x, rows and levels — bit for bit the per-axis passes of grid.py:800-832."""
+    from xgcm_b200 import _capi, ops
+
+    a = _field(shape, dtype, seed=43, nan_frac=0.02)
+    x = torch.from_numpy(a).to("cuda:0")
+    nd = len(shape)
+    lead_one = all(s == 1 for s in shape[: max(nd - 3, 0)])
+    axis_sets = [(nd - 1, nd - 2)]
+    if nd >= 3:
+        axis_sets += [(nd - 2, nd - 3), (nd - 1, nd - 3), (nd - 1, nd - 2, nd - 3)]
+    bcs = [("periodic", 0.0), ("fill", 1.5), ("extend", 0.0), ("fill", float("nan"))]
+    big = shape[-1] >= (448 if dtype == np.float32 else 480)
+    for axes in axis_sets:
+        if any(shape[ax] < 2 for ax in axes):
+            continue
+        for los in itertools.product((0, 1), repeat=len(axes)):
+            for bcsel in itertools.product(range(3), repeat=len(axes)):
+                for op in (("interp", "diff") if sum(bcsel) % 2 else ("interp", "max", "min")):
+                    pick = [3 if (op == "min" and b == 1) else b for b in bcsel]  # min: a NaN fill value
+                    specs = [(ax, op, lo, 1 - lo, bcs[b][0], bcs[b][1]) for ax, lo, b in zip(axes, los, pick)]
+                    want = a
+                    for ax, o, lo, hi, bc, fill in specs:
+                        want = oracle.stencil2(o, want, ax, lo, hi, bc, fill)
+                    got = ops.stencil_multi(x, specs).cpu().numpy()
+                    np.testing.assert_array_equal(got, want, err_msg=str(specs))
+                    if big and (nd - 3 not in axes or lead_one):
+                        assert _capi.last_launch() == "xg_stencil_multi(tile_tma)", str(specs)
+
+
 def test_stencil_multi_c_grid_interp_to_corner():
     """The notebook idiom grid.interp(da, ['X', 'Y']) on a (Z, Y, X) field, plus the 3-axis corner."""
     from xgcm_b200 import ops

@@ -18,6 +18,7 @@
 #include <stdlib.h>
 
 #include "xg_common.cuh"
+#include "xg_stencil_tile.cuh"
 
 namespace {
 
@@ -345,6 +346,44 @@ int multi_typed(const void* in, void* out, int ndim, const int64_t* shape, int n
     a.ax[k].fill = static_cast<T>(fill[k]);
     a.ax[k].n = shape[d];
     a.ax[k].in_stride = in_stride[d];
+  }
+  // the common chain — innermost axis first over the last two / three dims, every op length preserving —
+  // has a TMA-staged form (xg_stencil_multi_tma.cu); everything else runs the kernel below
+  {
+    bool ok = ndim >= 2;
+    for (int k = 0; k < naxes && ok; ++k) {
+      ok = lo[k] + hi[k] == 1 && axes[k] >= ndim - 3 && (k == 0 || axes[k] < axes[k - 1]);
+    }
+    if (ok) {
+      XgMultiTileSpec<T> ms;
+      ms.in = a.in;
+      ms.out = a.out;
+      ms.op = ops[0];
+      for (int q = 0; q < 3; ++q) {
+        ms.has[q] = 0;
+        ms.lo[q] = 0;
+        ms.bc[q] = XG_BC_FILL;
+        ms.fill[q] = T(0);
+      }
+      for (int k = 0; k < naxes; ++k) {
+        const int q = ndim - 1 - axes[k];  // 0 = x, 1 = rows, 2 = levels
+        ms.has[q] = 1;
+        ms.lo[q] = lo[k];
+        ms.bc[q] = bc[k];
+        ms.fill[q] = static_cast<T>(fill[k]);
+      }
+      ms.n = shape[ndim - 1];
+      ms.P = shape[ndim - 2];
+      ms.L = 1;
+      for (int d = 0; d < ndim - 2; ++d) ms.L *= shape[d];
+      // an operated level axis must be the only level dim (the dims before it have extent 1)
+      if (ms.has[2]) ok = ndim >= 3 && ms.L == shape[ndim - 3];
+      if (ok) {
+        bool launched = false;
+        const int rc = xg_multi_tile<T>(ms, st, &launched);
+        if (rc || launched) return rc;
+      }
+    }
   }
   // innermost group: the last dim if it is operated, else the run of trailing non-operated dims
   int last = app_index[ndim - 1];

@@ -61,3 +61,20 @@ inline bool xg_tile_operand_from(const XgOperand& m, int64_t outer, int64_t inne
   out->sp = m.axis_stride;
   return true;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// TMA-staged fused multi-axis stencil (xg_stencil_multi_tma.cu): one operator along x, rows and / or levels
+// of a contiguous (L, P, n) array, applied innermost axis first, every op length preserving.
+template <typename T>
+struct XgMultiTileSpec {
+  const T* in;
+  T* out;
+  int64_t L, P, n;
+  int op;      // XG_OP_*
+  int has[3];  // x, rows, levels operated?
+  int lo[3];   // halo below (hi = 1 - lo) per operated axis
+  int bc[3];   // XG_BC_PERIODIC / FILL / EXTEND
+  T fill[3];
+};
+template <typename T>
+int xg_multi_tile(const XgMultiTileSpec<T>& spec, cudaStream_t st, bool* launched);
