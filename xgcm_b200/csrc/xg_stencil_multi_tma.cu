@@ -47,8 +47,8 @@ struct MultiTileArgs {
   XgMultiTileSpec<T> s;
   int hp, hz;          // halo rows / levels in the box (the axis is operated)
   int ox, op, oz;      // box origin relative to the tile origin: cells / rows / levels before it
-  int64_t npq, ntiles;
-  XgFastDiv fd_ntx, fd_npq;
+  int64_t npq, ntiles;  // tile rows; virtual tiles = nrb * nzq * rbq * ntx (tile rows past npq are skipped)
+  XgFastDiv fd_ntx, fd_rbq, fd_nzq;
   int nst;
   unsigned stage_bytes, tx_bytes;
 };
@@ -79,15 +79,21 @@ __global__ void __launch_bounds__(kConsumersM + 32, 3)
   const int64_t nloc = (a.ntiles > blockIdx.x) ? (a.ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
   constexpr int rows_box = TY + (HP ? 1 : 0), lvl_pitch = rows_box * BOXW, HZI = HZ ? 1 : 0;
 
-  auto tile_geom = [&](int64_t i, int& z0, int& p0, int& x0) {
+  // row blocks (~128 rows) outermost, then the level batches: the halo level of a batch is re-read from L2,
+  // not DRAM, by the next batch.  false for the padding rows of the last row block.
+  auto tile_geom = [&](int64_t i, int& z0, int& p0, int& x0) -> bool {
     const uint32_t g = (uint32_t)(i * gridDim.x + blockIdx.x);
     const uint32_t t = xg_fastdiv_q(g, a.fd_ntx);
     const uint32_t c = g - t * a.fd_ntx.d;
-    const uint32_t zq = xg_fastdiv_q(t, a.fd_npq);
-    const uint32_t pq = t - zq * a.fd_npq.d;
+    const uint32_t t2 = xg_fastdiv_q(t, a.fd_rbq);
+    const uint32_t pql = t - t2 * a.fd_rbq.d;
+    const uint32_t rb = xg_fastdiv_q(t2, a.fd_nzq);
+    const uint32_t zq = t2 - rb * a.fd_nzq.d;
+    const uint32_t pq = rb * a.fd_rbq.d + pql;
     z0 = (int)(zq * U);
     p0 = (int)(pq * TY);
     x0 = (int)(c * TXE);
+    return pq < (uint32_t)a.npq;
   };
 
   if (tid == 0) {
@@ -101,11 +107,13 @@ __global__ void __launch_bounds__(kConsumersM + 32, 3)
 
   if (tid >= kConsumersM) {
     if (tid == kConsumersM) {  // ---- producer
+      int64_t k = 0;
       for (int64_t i = 0; i < nloc; ++i) {
         int z0, p0, x0;
-        tile_geom(i, z0, p0, x0);
-        const int b = (int)(i % NST);
-        if (i >= NST) mbar_wait(empty_u32 + 8u * b, (uint32_t)(((i / NST) - 1) & 1));
+        if (!tile_geom(i, z0, p0, x0)) continue;
+        const int b = (int)(k % NST);
+        if (k >= NST) mbar_wait(empty_u32 + 8u * b, (uint32_t)(((k / NST) - 1) & 1));
+        ++k;
         const uint32_t bar = full_u32 + 8u * b;
         mbar_expect_tx(bar, a.tx_bytes);
         tensor_load_3d(smem_u32(stage0 + (size_t)b * a.stage_bytes), &map_in, x0 - a.ox, p0 - a.op, z0 - a.oz, bar);
@@ -129,15 +137,18 @@ __global__ void __launch_bounds__(kConsumersM + 32, 3)
   const bool fill_x = has_x && s.bc[0] == XG_BC_FILL, fill_p = has_p && s.bc[1] == XG_BC_FILL;
   const bool fill_z = has_z && s.bc[2] == XG_BC_FILL;
 
+  int64_t k = 0;
   for (int64_t i = 0; i < nloc; ++i) {
     int z0, p0, x0;
-    tile_geom(i, z0, p0, x0);
-    const int b = (int)(i % NST);
+    if (!tile_geom(i, z0, p0, x0)) continue;
+    const int b = (int)(k % NST);
+    const uint32_t full_parity = (uint32_t)((k / NST) & 1);
+    ++k;
     T* tile = reinterpret_cast<T*>(stage0 + (size_t)b * a.stage_bytes);
     const int x = x0 + vxs * VEC, prow = p0 + ty;
     const bool act = vx < NVR && x < n && prow < P;
     const int nz = (L - z0 < U) ? (int)(L - z0) : U;
-    mbar_wait(full_u32 + 8u * b, (uint32_t)((i / NST) & 1));
+    mbar_wait(full_u32 + 8u * b, full_parity);
 
     // ---- materialise the padded input where the box left the array along a periodic / extend axis
     const int gx0 = x0 - a.ox, gp0 = p0 - a.op, gz0 = z0 - a.oz;  // global coordinates of the box origin
@@ -312,21 +323,29 @@ int xg_multi_tile(const XgMultiTileSpec<T>& s, cudaStream_t st, bool* launched) 
   cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   static const int tune_nst = multi_env_int("XG_MULTI_NST", 0);
   static const int tune_ctas = multi_env_int("XG_MULTI_CTAS", 0);
-  int ctas = 3;
+  // measured (profiles/r2_multi_tma_sweep.txt): 3 CTAs x 2 tiles with an x op; without one (Y, Z) 4 CTAs x 1 tile
+  int ctas = s.has[0] ? 3 : 4;
   if (tune_ctas >= 1 && tune_ctas <= 4) ctas = tune_ctas;
   int per_cta = smem_sm / ctas - 1024;
   if (per_cta > smem_max) per_cta = smem_max;
   const int fit = (per_cta - 128) / (int)a.stage_bytes;
   int nst = fit < 2 ? fit : 2;
+  if (!s.has[0] && tune_ctas == 0) nst = 1;
   if (tune_nst > 0) nst = tune_nst < fit ? tune_nst : fit;
   if (nst < 1) return XG_OK;
   a.nst = nst;
   const int64_t ntx = xg_ceil_div(s.n, TXE);
   a.npq = xg_ceil_div(s.P, TY);
-  a.ntiles = xg_ceil_div(s.L, U) * a.npq * ntx;
+  static const int tune_rb = multi_env_int("XG_MULTI_RB", 128);
+  const int64_t rbq_target = xg_ceil_div(tune_rb > 0 ? tune_rb : 128, TY);
+  const int64_t nrb = xg_ceil_div(a.npq, rbq_target);
+  const int64_t rbq = xg_ceil_div(a.npq, nrb);
+  const int64_t nzq = xg_ceil_div(s.L, U);
+  a.ntiles = nrb * nzq * rbq * ntx;
   if (a.ntiles >= (1ll << 31)) return XG_OK;
   a.fd_ntx = xg_fastdiv_make(ntx);
-  a.fd_npq = xg_fastdiv_make(a.npq);
+  a.fd_rbq = xg_fastdiv_make(rbq);
+  a.fd_nzq = xg_fastdiv_make(nzq);
   CUtensorMap map_in;
   const cuuint64_t d3[3] = {(cuuint64_t)s.n, (cuuint64_t)s.P, (cuuint64_t)s.L};
   const cuuint64_t s3[2] = {(cuuint64_t)s.n * sizeof(T), (cuuint64_t)s.P * s.n * sizeof(T)};
