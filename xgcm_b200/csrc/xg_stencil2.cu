@@ -835,7 +835,7 @@ int launch_row_tma(const StencilArgs<T>& s, cudaStream_t st, bool* launched) {
     constexpr int U = 4;  // 8 levels per tile measured no faster (profiles/r2_row_tma_sweep.txt)
     const XgOperand& m = s.post;
     if (!enabled || !m.ptr || m.axis_stride != 1 || !s.post_axis_vec_ok) return XG_OK;
-    if (s.n < 2 * G::TXE || s.n >= (1ll << 31) || s.outer >= (1ll << 31)) return XG_OK;
+    if (s.n < 2 * G::TXE || s.n >= (1ll << 30) || s.outer >= (1ll << 30)) return XG_OK;  // 32-bit tile coordinates
     RowTmaArgs<T> a;
     int64_t post_rs = 0;
     if (m.outer.n == 0) { a.Zn = s.outer; a.post_row_zero = 1; }

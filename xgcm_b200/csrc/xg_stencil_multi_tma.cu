@@ -297,8 +297,8 @@ int xg_multi_tile(const XgMultiTileSpec<T>& s, cudaStream_t st, bool* launched) 
   *launched = false;
   static const int enabled = multi_env_int("XG_MULTI_TMA", 1);
   if (!enabled || !s.in || !s.out) return XG_OK;
-  if (s.n < 2 * TXE || s.n % VEC != 0 || s.n >= (1ll << 31) || s.P < 1 || s.P >= (1ll << 31) || s.L < 1 ||
-      s.L >= (1ll << 31))
+  if (s.n < 2 * TXE || s.n % VEC != 0 || s.n >= (1ll << 30) || s.P < 1 || s.P >= (1ll << 30) || s.L < 1 ||
+      s.L >= (1ll << 30))  // 32-bit tile coordinates
     return XG_OK;
   if (((uintptr_t)s.in | (uintptr_t)s.out) % 16 != 0) return XG_OK;
   if (s.op < XG_OP_DIFF || s.op > XG_OP_MAX) return XG_OK;

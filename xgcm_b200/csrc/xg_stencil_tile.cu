@@ -410,8 +410,9 @@ int xg_tile_stencil(const XgTileSpec<T>& s, cudaStream_t st, bool* launched, con
   *launched = false;
   static const int enabled = tile_env_int("XG_TILE_TMA", 1);
   if (!enabled || !s.b || !s.out) return XG_OK;
-  if (s.n < 2 * TXE || s.n % VEC != 0 || s.n >= (1ll << 31) || s.Zn < 2 || s.Zn >= (1ll << 31)) return XG_OK;
-  if (s.Pb < 1 || s.Po < 1 || s.Pb >= (1ll << 31) || s.Po >= (1ll << 31)) return XG_OK;
+  // (tile coordinates are 32-bit: extents below 2^30 leave room for the tile overhang)
+  if (s.n < 2 * TXE || s.n % VEC != 0 || s.n >= (1ll << 30) || s.Zn < 2 || s.Zn >= (1ll << 30)) return XG_OK;
+  if (s.Pb < 1 || s.Po < 1 || s.Pb >= (1ll << 30) || s.Po >= (1ll << 30)) return XG_OK;
   if (s.f_sp % VEC != 0 || s.b_sz % VEC != 0 || s.o_sz % VEC != 0 || s.f_sp <= 0 || s.b_sz <= 0 || s.o_sz <= 0) return XG_OK;
   if (((uintptr_t)s.b | (uintptr_t)s.out | (uintptr_t)s.a | (uintptr_t)s.halo_lo | (uintptr_t)s.halo_hi) % 16 != 0)
     return XG_OK;
