@@ -348,6 +348,22 @@ def _substitute_dummy_axis_names(padding_width, mapping):
     return {real: (0, 0) for real in mapping.values()}
 
 
+def _grid_coords_on(grid, dims):
+    """The coordinates of ``grid._ds`` that live on ``dims`` only.  Memoised per grid and dim tuple (keyed on
+    the dataset's coordinate and variable names, so a dataset edited in place is seen): building the dataset's
+    coordinate view costs more host time per call than the kernel of a small field."""
+    ds = grid._ds
+    stamp = (tuple(getattr(ds, "_coord_names", ())), len(getattr(ds, "_vars", ())))
+    cache = grid.__dict__.setdefault("_coords_on_cache", {})
+    hit = cache.get(dims)
+    if hit is not None and hit[0] == stamp:
+        return hit[1]
+    dimset = set(dims)
+    found = {cname: c for cname, c in ds.coords.items() if all(d in dimset for d in c.dims)}
+    cache[dims] = (stamp, found)
+    return found
+
+
 def _reattach_coords(results, grid, padding_width, out_core_dim_names=None, input_args=None):
     """Coordinates of position-shifted dims come from ``grid._ds``; coordinates living
     purely on untouched dims are kept from the inputs (grid_ufunc.py:1262-1320)."""
@@ -360,11 +376,7 @@ def _reattach_coords(results, grid, padding_width, out_core_dim_names=None, inpu
             input_coords.setdefault(cname, c)
     out = []
     for res in results:
-        matching = {
-            cname: c
-            for cname, c in grid._ds.coords.items()
-            if all(d in res.dims for d in c.dims)
-        }
+        matching = dict(_grid_coords_on(grid, tuple(res.dims)))
         for cname, c in input_coords.items():
             if all(d in res.dims for d in c.dims):
                 matching[cname] = c
