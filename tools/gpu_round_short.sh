@@ -1,3 +1,5 @@
+#!/bin/bash
+# Short GPU-box session: full parity suite, smoke, one driver-style bench line (tools/gpu_round.sh adds the reference arm and ncu).
 TAG=r2
 mkdir -p gpurun_out
 python -m pytest tests -m gpu -x -q 2>&1 | tail -15 | tee gpurun_out/${TAG}_pytest_gpu.txt
