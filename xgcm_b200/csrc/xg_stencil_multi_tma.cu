@@ -60,7 +60,8 @@ __device__ __forceinline__ void mbar_arrive_multi(uint32_t bar) {
 // HX / HP / HZ: which of x, rows, levels are operated — compile-time, so box pitches are constants and the
 // chain is straight-line code (the first version decided these at run time: 860 warp instructions per
 // tile-warp, 17 % of them the operators; profiles/r2_ncu_multi_xyz_tma_v1_summary.json)
-template <typename T, int OP, bool HX, bool HP, bool HZ>
+// LOX: the x op reads its lower (1) or upper (0) neighbour — compile-time too (a run-time choice cost a select per cell)
+template <typename T, int OP, bool HX, bool HP, bool HZ, int LOX>
 __global__ void __launch_bounds__(kConsumersM + 32, 3)
     k_tile_multi(const __grid_constant__ CUtensorMap map_in, const MultiTileArgs<T> a) {
   typedef MultiGeo<T> G;
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(kConsumersM + 32, 3)
   const int ty = tid / LR, vx = tid - ty * LR;
   const int vxs = vx < NVR ? vx : NVR - 1;
   constexpr bool has_x = HX, has_p = HP, has_z = HZ;
-  const int lo_x = s.lo[0], lo_p = s.lo[1], lo_z = s.lo[2];
+  constexpr int lo_x = LOX;
+  const int lo_p = s.lo[1], lo_z = s.lo[2];
   const int nbi = lo_x ? -1 : VEC;
   const bool edge_lane = lo_x ? (lane == 0) : (lane == 31 || vx >= NVR - 1);
   const int64_t n = s.n, P = s.P, L = s.L;
@@ -364,20 +366,24 @@ int xg_multi_tile(const XgMultiTileSpec<T>& s, cudaStream_t st, bool* launched) 
   };
   int ok = 0;
   const int combo = (s.has[0] ? 1 : 0) | (s.has[1] ? 2 : 0) | (s.has[2] ? 4 : 0);
-#define XG_MULTI_OPS(HX_, HP_, HZ_)                                                 \
-  switch (s.op) {                                                                   \
-    case XG_OP_DIFF: ok = go(k_tile_multi<T, XG_OP_DIFF, HX_, HP_, HZ_>); break;     \
-    case XG_OP_INTERP: ok = go(k_tile_multi<T, XG_OP_INTERP, HX_, HP_, HZ_>); break; \
-    case XG_OP_MIN: ok = go(k_tile_multi<T, XG_OP_MIN, HX_, HP_, HZ_>); break;       \
-    default: ok = go(k_tile_multi<T, XG_OP_MAX, HX_, HP_, HZ_>); break;              \
+#define XG_MULTI_OPS(HX_, HP_, HZ_, LOX_)                                                 \
+  switch (s.op) {                                                                         \
+    case XG_OP_DIFF: ok = go(k_tile_multi<T, XG_OP_DIFF, HX_, HP_, HZ_, LOX_>); break;     \
+    case XG_OP_INTERP: ok = go(k_tile_multi<T, XG_OP_INTERP, HX_, HP_, HZ_, LOX_>); break; \
+    case XG_OP_MIN: ok = go(k_tile_multi<T, XG_OP_MIN, HX_, HP_, HZ_, LOX_>); break;       \
+    default: ok = go(k_tile_multi<T, XG_OP_MAX, HX_, HP_, HZ_, LOX_>); break;              \
   }
+#define XG_MULTI_LOX(HP_, HZ_)                      \
+  if (s.lo[0]) { XG_MULTI_OPS(true, HP_, HZ_, 1) } \
+  else { XG_MULTI_OPS(true, HP_, HZ_, 0) }
   switch (combo) {
-    case 3: XG_MULTI_OPS(true, true, false) break;
-    case 5: XG_MULTI_OPS(true, false, true) break;
-    case 6: XG_MULTI_OPS(false, true, true) break;
-    case 7: XG_MULTI_OPS(true, true, true) break;
+    case 3: XG_MULTI_LOX(true, false) break;
+    case 5: XG_MULTI_LOX(false, true) break;
+    case 6: XG_MULTI_OPS(false, true, true, 0) break;
+    case 7: XG_MULTI_LOX(true, true) break;
     default: break;
   }
+#undef XG_MULTI_LOX
 #undef XG_MULTI_OPS
   if (!ok) return XG_OK;
   *launched = true;
